@@ -246,8 +246,8 @@ int ff_thread_get_buffer(AVCodecContext *avctx, ThreadFrame *tf, int flags)
     if (need > h->framebuf_size) {
         free(h->framebuf[0]);
         free(h->framebuf[1]);
-        h->framebuf[0] = malloc(need);
-        h->framebuf[1] = malloc(need);
+        h->framebuf[0] = calloc(1, need);   /* zeroed: rows no slice covers stay deterministic */
+        h->framebuf[1] = calloc(1, need);
         h->framebuf_size = need;
         if (!h->framebuf[0] || !h->framebuf[1])
             return AVERROR(ENOMEM);
