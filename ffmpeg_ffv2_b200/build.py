@@ -1,0 +1,48 @@
+"""Builds ffmpeg_ffv2_b200/libffgpu.so in-tree: gcc for the host C, nvcc (sm_100a only) for
+the kernels and the C-ABI glue.  The CUDA runtime is linked statically so that the library
+has no dependency on which libcudart a host application ships."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libffgpu.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def sources():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + \
+           [os.path.join(HERE, "..", "include", "ffgpu.h")]
+
+
+def build(force=False, verbose=False):
+    if not force and not _newer(OUT, sources()):
+        return OUT
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    run = lambda cmd: subprocess.run(cmd, check=True, stdout=None if verbose else subprocess.PIPE,
+                                     stderr=subprocess.STDOUT)
+    host_o = os.path.join(objdir, "ffv1_host.o")
+    run(["gcc", "-std=gnu11", "-O2", "-fPIC", "-Wall", "-Wextra", "-c",
+         os.path.join(CSRC, "ffv1_host.c"), "-o", host_o])
+    objs = [host_o]
+    for cu in ("ffv1_kernels.cu", "ffgpu_api.cu"):
+        o = os.path.join(objdir, cu.replace(".cu", ".o"))
+        run([NVCC] + ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+                             "-c", os.path.join(CSRC, cu), "-o", o])
+        objs.append(o)
+    run([NVCC] + ARCH + ["-shared", "-cudart", "static", "-o", OUT] + objs)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

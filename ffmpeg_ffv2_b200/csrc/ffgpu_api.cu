@@ -1,0 +1,1234 @@
+/*
+ * ffgpu_api.cu -- the C ABI of include/ffgpu.h: handle management, device memory,
+ * CUDA streams and the launch-group pipeline around the kernels of ffv1_kernels.cu.
+ *
+ * Execution model
+ *   A handle owns `pipeline_depth` launch groups.  A group collects up to `max_batch`
+ *   pictures (encoder) or packets (decoder), uploads them on its own CUDA stream,
+ *   enqueues the kernel chain once for the whole group and downloads the results; the
+ *   host thread meanwhile fills the next group, so H2D, kernels and D2H of different
+ *   groups overlap.  Streams whose adaptive states carry from frame to frame
+ *   (gop_size > 1) run one picture per group on a single stream, in order.
+ *
+ * There is no CPU pixel path anywhere in this file: without a CUDA device every
+ * pixel-path entry point fails with FFGPU_EXTERNAL.
+ */
+#include <cuda_runtime.h>
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/ffgpu.h"
+#include "ffv1_host.h"
+#include "ffv1_launch.h"
+#include "ffv1_slice.cuh"
+
+#define NPREFIX_SETS 8
+#define MAX_DEPTH    8
+
+static thread_local char g_err[512];
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" const char *ffgpu_last_error(void) { return g_err; }
+extern "C" int ffgpu_abi_version(void) { return FFGPU_ABI_VERSION; }
+
+#define CK(call)                                                                            \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return fail(FFGPU_EXTERNAL, "CUDA: %s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" size_t ffgpu_ffv1_frame_layout(const char *pix_fmt, int width, int height,
+                                          size_t plane_offset[4], int plane_pitch[4],
+                                          int plane_rows[4], int plane_rowbytes[4])
+{
+    const FFPixFmt *pf = ff_find_pixfmt(pix_fmt);
+    size_t off = 0;
+    if (!pf || width <= 0 || height <= 0)
+        return 0;
+    for (int k = 0; k < 4; k++) {
+        plane_offset[k] = 0;
+        plane_pitch[k] = plane_rows[k] = plane_rowbytes[k] = 0;
+    }
+    for (int k = 0; k < pf->nplanes; k++) {
+        int rb, rows;
+        ff_plane_geometry(pf, width, height, k, &rb, &rows);
+        plane_offset[k] = off;
+        plane_pitch[k] = (rb + 255) & ~255;
+        plane_rows[k] = rows;
+        plane_rowbytes[k] = rb;
+        off += (size_t)plane_pitch[k] * rows;
+    }
+    return off;
+}
+
+/* quant tables in the layout the kernels index: [table][5*256 + flag] */
+static void flatten_qt(const FFStream *s, int16_t *q)
+{
+    memset(q, 0, sizeof(int16_t) * FF_MAX_QUANT_TABLES * FF_QT_STRIDE);
+    for (int i = 0; i < s->qt_count; i++) {
+        memcpy(q + (size_t)i * FF_QT_STRIDE, s->qt[i], sizeof(s->qt[i]));
+        q[(size_t)i * FF_QT_STRIDE + FF_MAX_CTX_INPUTS * 256] = s->qt[i][3][127] || s->qt[i][4][127];
+    }
+}
+
+static int upload_picture(const FFDevParams *P, const FFPixFmt *pf, int w, int h,
+                          const ffgpu_picture *pic, uint8_t *d_frame, cudaStream_t st)
+{
+    for (int k = 0; k < pf->nplanes; k++) {
+        int rb, rows;
+        ff_plane_geometry(pf, w, h, k, &rb, &rows);
+        if (!pic->data[k] || pic->linesize[k] < rb)
+            return fail(FFGPU_EINVAL, "picture plane %d missing or linesize too small", k);
+        CK(cudaMemcpy2DAsync(d_frame + P->plane_off[k], P->pitch[k], pic->data[k], pic->linesize[k],
+                             rb, rows, cudaMemcpyHostToDevice, st));
+    }
+    return 0;
+}
+
+/* ====================================================================== */
+/* encoder                                                                 */
+/* ====================================================================== */
+enum { JOB_FREE = 0, JOB_FILLING, JOB_RUNNING, JOB_DRAINING };
+
+struct EncJob {
+    cudaStream_t stream;
+    cudaEvent_t done;
+    int n, state, drained, fetched;
+    uint8_t *d_frames;
+    uint32_t *d_tokens;
+    uint8_t *d_state;
+    uint8_t *d_bs;
+    uint32_t *d_slice_bytes, *d_slice_off, *d_pkt_size, *d_pkt_off, *d_overflow;
+    uint8_t *d_pkt;
+    uint8_t *d_frame_set, *d_frame_key;
+    /* pinned host */
+    uint8_t *h_frame_set, *h_frame_key;
+    uint32_t *h_pkt_size, *h_pkt_off, *h_overflow;
+    uint8_t *h_pkt;
+    size_t h_pkt_cap;
+    int64_t *pts;
+    int *key;
+};
+
+struct PrefixSet {
+    int valid, key, ps, sar_num, sar_den;
+};
+
+struct ffgpu_encoder {
+    ffgpu_enc_options opt;
+    char pix_fmt[32];
+    FFStream s;
+    FFDevParams P;
+    FFDevSlice *h_slices;
+    uint8_t *extradata;
+    int extradata_size;
+    int intra;                  /* every frame is a key frame -> groups of many pictures */
+    int max_batch, depth;
+    int prefix_stride;
+    /* device */
+    int dev_ready;
+    FFDevSlice *d_slices;
+    int16_t *d_qt;
+    FFRacTables *d_tab;
+    FFRacPrefix *d_prefix;
+    uint8_t *d_prefix_bytes;
+    uint8_t *d_state_shared;    /* carried-state streams: one arena for all groups */
+    PrefixSet sets[NPREFIX_SETS];
+    EncJob jobs[MAX_DEPTH];
+    int fill, head;             /* ring positions */
+    int flushing, eof;
+    int64_t picture_number;
+    uint64_t launches;
+};
+
+static int enc_free_job(EncJob *j)
+{
+    cudaFree(j->d_frames); cudaFree(j->d_tokens); cudaFree(j->d_state); cudaFree(j->d_bs);
+    cudaFree(j->d_slice_bytes); cudaFree(j->d_slice_off); cudaFree(j->d_pkt_size);
+    cudaFree(j->d_pkt_off); cudaFree(j->d_overflow); cudaFree(j->d_pkt);
+    cudaFree(j->d_frame_set); cudaFree(j->d_frame_key);
+    cudaFreeHost(j->h_frame_set); cudaFreeHost(j->h_frame_key); cudaFreeHost(j->h_pkt_size);
+    cudaFreeHost(j->h_pkt_off); cudaFreeHost(j->h_overflow); cudaFreeHost(j->h_pkt);
+    free(j->pts); free(j->key);
+    if (j->done) cudaEventDestroy(j->done);
+    if (j->stream) cudaStreamDestroy(j->stream);
+    memset(j, 0, sizeof(*j));
+    return 0;
+}
+
+static int enc_device_init(ffgpu_encoder *e)
+{
+    const FFDevParams *P = &e->P;
+    const int golomb = P->ac == FF_AC_GOLOMB;
+    const size_t state_frame = (size_t)P->nslices * P->total_ctx * (golomb ? 8 : FF_CONTEXT_SIZE);
+    int16_t *qt;
+    int ndev = 0;
+
+    if (e->dev_ready)
+        return 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(FFGPU_EXTERNAL, "no CUDA device: the FFV1 pixel path has no CPU fallback");
+    CK(cudaSetDevice(e->opt.device));
+    CK(cudaMalloc(&e->d_slices, sizeof(FFDevSlice) * P->nslices));
+    CK(cudaMemcpy(e->d_slices, e->h_slices, sizeof(FFDevSlice) * P->nslices, cudaMemcpyHostToDevice));
+    qt = (int16_t *)malloc(sizeof(int16_t) * FF_MAX_QUANT_TABLES * FF_QT_STRIDE);
+    if (!qt)
+        return fail(FFGPU_ENOMEM, "out of memory");
+    flatten_qt(&e->s, qt);
+    CK(cudaMalloc(&e->d_qt, sizeof(int16_t) * FF_MAX_QUANT_TABLES * FF_QT_STRIDE));
+    CK(cudaMemcpy(e->d_qt, qt, sizeof(int16_t) * FF_MAX_QUANT_TABLES * FF_QT_STRIDE, cudaMemcpyHostToDevice));
+    free(qt);
+    CK(cudaMalloc(&e->d_tab, sizeof(FFRacTables)));
+    CK(cudaMemcpy(e->d_tab, &e->s.cur_tab, sizeof(FFRacTables), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&e->d_prefix, sizeof(FFRacPrefix) * NPREFIX_SETS * P->nslices));
+    CK(cudaMalloc(&e->d_prefix_bytes, (size_t)NPREFIX_SETS * P->nslices * e->prefix_stride));
+    if (!e->intra) {
+        CK(cudaMalloc(&e->d_state_shared, state_frame));
+    }
+    for (int i = 0; i < e->depth; i++) {
+        EncJob *j = &e->jobs[i];
+        const size_t B = (size_t)e->max_batch;
+        CK(cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&j->done, cudaEventDisableTiming));
+        CK(cudaMalloc(&j->d_frames, B * P->frame_bytes));
+        CK(cudaMalloc(&j->d_tokens, B * P->frame_tokens * sizeof(uint32_t)));
+        if (e->intra)
+            CK(cudaMalloc(&j->d_state, B * state_frame));
+        CK(cudaMalloc(&j->d_bs, B * P->frame_bs));
+        CK(cudaMalloc(&j->d_slice_bytes, B * P->nslices * sizeof(uint32_t)));
+        CK(cudaMalloc(&j->d_slice_off, B * P->nslices * sizeof(uint32_t)));
+        CK(cudaMalloc(&j->d_pkt_size, B * sizeof(uint32_t)));
+        CK(cudaMalloc(&j->d_pkt_off, (B + 1) * sizeof(uint32_t)));
+        CK(cudaMalloc(&j->d_overflow, sizeof(uint32_t)));
+        CK(cudaMalloc(&j->d_pkt, B * P->pkt_stride));
+        CK(cudaMalloc(&j->d_frame_set, B));
+        CK(cudaMalloc(&j->d_frame_key, B));
+        CK(cudaHostAlloc(&j->h_frame_set, B, cudaHostAllocDefault));
+        CK(cudaHostAlloc(&j->h_frame_key, B, cudaHostAllocDefault));
+        CK(cudaHostAlloc(&j->h_pkt_size, B * sizeof(uint32_t), cudaHostAllocDefault));
+        CK(cudaHostAlloc(&j->h_pkt_off, (B + 1) * sizeof(uint32_t), cudaHostAllocDefault));
+        CK(cudaHostAlloc(&j->h_overflow, sizeof(uint32_t), cudaHostAllocDefault));
+        j->h_pkt_cap = align_up(B * (P->frame_bytes / 4 + 65536), 4096);
+        CK(cudaHostAlloc(&j->h_pkt, j->h_pkt_cap, cudaHostAllocDefault));
+        j->pts = (int64_t *)calloc(B, sizeof(int64_t));
+        j->key = (int *)calloc(B, sizeof(int));
+        if (!j->pts || !j->key)
+            return fail(FFGPU_ENOMEM, "out of memory");
+    }
+    e->dev_ready = 1;
+    return 0;
+}
+
+extern "C" int ffgpu_ffv1_encode_init(ffgpu_encoder **penc, const ffgpu_enc_options *opt)
+{
+    ffgpu_encoder *e;
+    int r;
+    if (!penc || !opt)
+        return fail(FFGPU_EINVAL, "null argument");
+    *penc = NULL;
+    g_err[0] = 0;
+    e = (ffgpu_encoder *)calloc(1, sizeof(*e));
+    if (!e)
+        return fail(FFGPU_ENOMEM, "out of memory");
+    e->opt = *opt;
+    snprintf(e->pix_fmt, sizeof(e->pix_fmt), "%s", opt->pix_fmt ? opt->pix_fmt : "");
+    e->opt.pix_fmt = e->pix_fmt;
+    if ((r = ff_stream_from_options(&e->s, &e->opt)) < 0) {
+        free(e);
+        return fail(r, "encode_init: options rejected (%d)", r);
+    }
+    if ((r = ff_write_extradata(&e->s, opt->gop_size, &e->extradata, &e->extradata_size)) < 0) {
+        free(e);
+        return fail(r, "encode_init: extradata");
+    }
+    e->h_slices = (FFDevSlice *)calloc((size_t)e->s.nh * e->s.nv, sizeof(FFDevSlice));
+    if (!e->h_slices) {
+        free(e->extradata);
+        free(e);
+        return fail(FFGPU_ENOMEM, "out of memory");
+    }
+    ff_fill_dev_params(&e->s, 1, &e->P, e->h_slices);
+    e->intra = opt->gop_size <= 1;
+    e->prefix_stride = e->s.version > 2 ? 64 : 4096;
+    if (e->intra) {
+        /* enough pictures per group for ~48k resident slice coders, bounded by memory */
+        const size_t per_frame = e->P.frame_bytes + e->P.frame_tokens * 4 + e->P.frame_bs + e->P.pkt_stride +
+                                 (size_t)e->P.nslices * e->P.total_ctx * FF_CONTEXT_SIZE;
+        int b = opt->max_batch > 0 ? opt->max_batch : (49152 + e->P.nslices - 1) / e->P.nslices;
+        size_t cap = ((size_t)12 << 30) / (per_frame ? per_frame : 1);
+        if (b > 256) b = 256;
+        if (opt->max_batch <= 0 && (size_t)b > cap) b = (int)cap;
+        if (b < 1) b = 1;
+        e->max_batch = b;
+        e->depth = opt->pipeline_depth > 0 ? opt->pipeline_depth : 3;
+    } else {
+        e->max_batch = 1;
+        e->depth = 1;
+    }
+    if (e->depth > MAX_DEPTH)
+        e->depth = MAX_DEPTH;
+    *penc = e;
+    return 0;
+}
+
+extern "C" int ffgpu_ffv1_encoder_extradata(const ffgpu_encoder *e, const uint8_t **data)
+{
+    if (data)
+        *data = e->extradata;
+    return e->extradata_size;
+}
+
+extern "C" void ffgpu_ffv1_encoder_info(const ffgpu_encoder *e, int info[8])
+{
+    info[0] = e->s.version; info[1] = e->s.micro_version; info[2] = e->s.ac; info[3] = e->s.nh;
+    info[4] = e->s.nv; info[5] = e->s.ec; info[6] = e->s.bits; info[7] = e->s.colorspace;
+}
+
+extern "C" size_t ffgpu_ffv1_encoder_max_packet(const ffgpu_encoder *e)
+{
+    return e->P.pkt_stride;
+}
+
+extern "C" uint64_t ffgpu_ffv1_encoder_launches(const ffgpu_encoder *e) { return e->launches; }
+
+/* find or build the prefix set for (key, picture structure, SAR) */
+static int enc_prefix_set(ffgpu_encoder *e, int key, int ps, int sn, int sd)
+{
+    const FFDevParams *P = &e->P;
+    int slot = -1;
+    for (int i = 0; i < NPREFIX_SETS; i++) {
+        PrefixSet *p = &e->sets[i];
+        if (p->valid && p->key == key && p->ps == ps && p->sar_num == sn && p->sar_den == sd)
+            return i;
+        if (!p->valid && slot < 0)
+            slot = i;
+    }
+    if (slot < 0) {
+        /* cache full: wait for everything in flight, then start over */
+        CK(cudaDeviceSynchronize());
+        memset(e->sets, 0, sizeof(e->sets));
+        slot = 0;
+    }
+    {
+        FFRacPrefix *pre = (FFRacPrefix *)calloc(P->nslices, sizeof(FFRacPrefix));
+        uint8_t *bytes = (uint8_t *)calloc((size_t)P->nslices, e->prefix_stride);
+        int r = 0;
+        if (!pre || !bytes) {
+            free(pre); free(bytes);
+            return fail(FFGPU_ENOMEM, "out of memory");
+        }
+        for (int i = 0; i < P->nslices && r >= 0; i++) {
+            FFSliceRect rc = { e->h_slices[i].x, e->h_slices[i].y, e->h_slices[i].w, e->h_slices[i].h };
+            r = ff_enc_slice_prefix(&e->s, i, &rc, key, ps, sn, sd, &pre[i],
+                                    bytes + (size_t)i * e->prefix_stride, e->prefix_stride);
+            pre[i].byte_off = (uint32_t)(((size_t)slot * P->nslices + i) * e->prefix_stride);
+        }
+        if (r >= 0) {
+            cudaError_t ce = cudaMemcpy(e->d_prefix + (size_t)slot * P->nslices, pre,
+                                        sizeof(FFRacPrefix) * P->nslices, cudaMemcpyHostToDevice);
+            if (ce == cudaSuccess)
+                ce = cudaMemcpy(e->d_prefix_bytes + (size_t)slot * P->nslices * e->prefix_stride, bytes,
+                                (size_t)P->nslices * e->prefix_stride, cudaMemcpyHostToDevice);
+            if (ce != cudaSuccess)
+                r = fail(FFGPU_EXTERNAL, "CUDA: prefix upload: %s", cudaGetErrorString(ce));
+        } else {
+            fail(r, "slice header does not fit its prefix buffer");
+        }
+        free(pre);
+        free(bytes);
+        if (r < 0)
+            return r;
+    }
+    e->sets[slot].valid = 1;
+    e->sets[slot].key = key;
+    e->sets[slot].ps = ps;
+    e->sets[slot].sar_num = sn;
+    e->sets[slot].sar_den = sd;
+    return slot;
+}
+
+static void enc_fill_dev(const ffgpu_encoder *e, const EncJob *j, const uint8_t *frames, FFEncDev *E)
+{
+    memset(E, 0, sizeof(*E));
+    E->slices = e->d_slices;
+    E->qt = e->d_qt;
+    E->tab = e->d_tab;
+    E->frames = frames;
+    E->tokens = j->d_tokens;
+    E->state = e->intra ? j->d_state : e->d_state_shared;
+    E->prefix = e->d_prefix;
+    E->prefix_bytes = e->d_prefix_bytes;
+    E->frame_prefix_set = j->d_frame_set;
+    E->frame_key = j->d_frame_key;
+    E->bs = j->d_bs;
+    E->slice_bytes = j->d_slice_bytes;
+    E->slice_off = j->d_slice_off;
+    E->pkt_size = j->d_pkt_size;
+    E->pkt_off = j->d_pkt_off;
+    E->overflow = j->d_overflow;
+    E->pkt = j->d_pkt;
+    E->state_per_frame = e->intra;
+}
+
+/* enqueue the kernel chain + result download of a filled group */
+static int enc_launch(ffgpu_encoder *e, EncJob *j)
+{
+    FFEncDev E;
+    int r;
+    enc_fill_dev(e, j, j->d_frames, &E);
+    CK(cudaMemcpyAsync(j->d_frame_set, j->h_frame_set, j->n, cudaMemcpyHostToDevice, j->stream));
+    CK(cudaMemcpyAsync(j->d_frame_key, j->h_frame_key, j->n, cudaMemcpyHostToDevice, j->stream));
+    CK(cudaMemsetAsync(j->d_overflow, 0, sizeof(uint32_t), j->stream));
+    r = ffk_encode_group(&e->P, &E, j->n, j->stream);
+    if (r < 0)
+        return fail(r, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    e->launches += r;
+    CK(cudaMemcpyAsync(j->h_pkt_size, j->d_pkt_size, sizeof(uint32_t) * j->n, cudaMemcpyDeviceToHost, j->stream));
+    CK(cudaMemcpyAsync(j->h_pkt_off, j->d_pkt_off, sizeof(uint32_t) * (j->n + 1), cudaMemcpyDeviceToHost, j->stream));
+    CK(cudaMemcpyAsync(j->h_overflow, j->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, j->stream));
+    CK(cudaEventRecord(j->done, j->stream));
+    j->state = JOB_RUNNING;
+    j->fetched = 0;
+    j->drained = 0;
+    return 0;
+}
+
+/* wait for a running group and bring its packets to pinned host memory */
+static int enc_fetch(ffgpu_encoder *e, EncJob *j)
+{
+    size_t total;
+    (void)e;
+    if (j->fetched)
+        return 0;
+    CK(cudaEventSynchronize(j->done));
+    if (*j->h_overflow)
+        return fail(FFGPU_INVALIDDATA, "encoded frame too large");   /* ffv1enc_template.c:34-44 */
+    total = j->h_pkt_off[j->n];
+    if (total > j->h_pkt_cap) {
+        cudaFreeHost(j->h_pkt);
+        j->h_pkt = NULL;
+        j->h_pkt_cap = align_up(total + total / 2, 4096);
+        CK(cudaHostAlloc(&j->h_pkt, j->h_pkt_cap, cudaHostAllocDefault));
+    }
+    CK(cudaMemcpyAsync(j->h_pkt, j->d_pkt, total, cudaMemcpyDeviceToHost, j->stream));
+    CK(cudaStreamSynchronize(j->stream));
+    j->fetched = 1;
+    j->state = JOB_DRAINING;
+    return 0;
+}
+
+extern "C" int ffgpu_ffv1_encode_send_frame(ffgpu_encoder *e, const ffgpu_picture *pic)
+{
+    EncJob *j;
+    int r, key, set, ps;
+    if (!e)
+        return fail(FFGPU_EINVAL, "null encoder");
+    if ((r = enc_device_init(e)) < 0)
+        return r;
+    j = &e->jobs[e->fill];
+    if (!pic) {
+        e->flushing = 1;
+        if (j->state == JOB_FILLING && j->n > 0) {
+            if ((r = enc_launch(e, j)) < 0)
+                return r;
+            e->fill = (e->fill + 1) % e->depth;
+        }
+        return 0;
+    }
+    if (e->flushing)
+        return fail(FFGPU_EOF, "send_frame after flush");
+    if (j->state == JOB_RUNNING || j->state == JOB_DRAINING)
+        return FFGPU_EAGAIN;                       /* every group is busy: receive first */
+    if (j->state == JOB_FREE) {
+        j->state = JOB_FILLING;
+        j->n = 0;
+    }
+    key = e->opt.gop_size == 0 || e->picture_number % e->opt.gop_size == 0;
+    ps = !pic->interlaced_frame ? 3 : 1 + !pic->top_field_first;   /* ffv1enc.c:944-947 */
+    set = enc_prefix_set(e, key, ps, pic->sar_num, pic->sar_den);
+    if (set < 0)
+        return set;
+    if ((r = upload_picture(&e->P, e->s.pf, e->s.width, e->s.height, pic,
+                            j->d_frames + (size_t)j->n * e->P.frame_bytes, j->stream)) < 0)
+        return r;
+    j->h_frame_set[j->n] = (uint8_t)set;
+    j->h_frame_key[j->n] = (uint8_t)key;
+    j->pts[j->n] = pic->pts;
+    j->key[j->n] = key;
+    j->n++;
+    e->picture_number++;
+    if (j->n == e->max_batch) {
+        if ((r = enc_launch(e, j)) < 0)
+            return r;
+        e->fill = (e->fill + 1) % e->depth;
+    }
+    return 0;
+}
+
+extern "C" int ffgpu_ffv1_encode_receive_packet(ffgpu_encoder *e, uint8_t *pkt, size_t cap,
+                                                size_t *size, int *key_frame, int64_t *pts)
+{
+    EncJob *j;
+    int r, i;
+    if (!e || !e->dev_ready)
+        return e && e->flushing ? FFGPU_EOF : FFGPU_EAGAIN;
+    j = &e->jobs[e->head];
+    if (j->state == JOB_FREE || j->state == JOB_FILLING)
+        return e->flushing ? FFGPU_EOF : FFGPU_EAGAIN;
+    if (j->state == JOB_RUNNING) {
+        /* block only if the caller cannot make progress otherwise */
+        const EncJob *f = &e->jobs[e->fill];
+        const int must_wait = e->flushing || f->state == JOB_RUNNING || f->state == JOB_DRAINING;
+        if (!must_wait && cudaEventQuery(j->done) == cudaErrorNotReady)
+            return FFGPU_EAGAIN;
+        if ((r = enc_fetch(e, j)) < 0) {
+            j->state = JOB_FREE;
+            e->head = (e->head + 1) % e->depth;
+            return r;
+        }
+    }
+    i = j->drained;
+    if (j->h_pkt_size[i] > cap)
+        return fail(FFGPU_ENOSPC, "packet buffer too small: need %u bytes", j->h_pkt_size[i]);
+    memcpy(pkt, j->h_pkt + j->h_pkt_off[i], j->h_pkt_size[i]);
+    if (size) *size = j->h_pkt_size[i];
+    if (key_frame) *key_frame = j->key[i];
+    if (pts) *pts = j->pts[i];
+    if (++j->drained == j->n) {
+        j->state = JOB_FREE;
+        j->n = 0;
+        e->head = (e->head + 1) % e->depth;
+    }
+    return 0;
+}
+
+extern "C" int ffgpu_ffv1_encode_frame(ffgpu_encoder *e, const ffgpu_picture *pic, uint8_t *pkt,
+                                       size_t cap, size_t *size, int *key_frame)
+{
+    EncJob *j;
+    int r;
+    if (!e || !pic)
+        return fail(FFGPU_EINVAL, "null argument");
+    if ((r = enc_device_init(e)) < 0)
+        return r;
+    for (int i = 0; i < e->depth; i++)
+        if (e->jobs[i].state != JOB_FREE)
+            return fail(FFGPU_EINVAL, "encode_frame while send/receive pictures are pending");
+    if ((r = ffgpu_ffv1_encode_send_frame(e, pic)) < 0)
+        return r;
+    j = &e->jobs[e->fill];
+    if (j->state == JOB_FILLING) {
+        if ((r = enc_launch(e, j)) < 0)
+            return r;
+        e->fill = (e->fill + 1) % e->depth;
+    }
+    /* the group is running: force completion */
+    j = &e->jobs[e->head];
+    if ((r = enc_fetch(e, j)) < 0) {
+        j->state = JOB_FREE;
+        j->n = 0;
+        e->head = (e->head + 1) % e->depth;
+        return r;
+    }
+    return ffgpu_ffv1_encode_receive_packet(e, pkt, cap, size, key_frame, NULL);
+}
+
+extern "C" int ffgpu_ffv1_encode_device(ffgpu_encoder *e, const void *d_frames, int nframes,
+                                        void *cuda_stream)
+{
+    EncJob *j;
+    FFEncDev E;
+    cudaStream_t st;
+    int r, set;
+    if (!e || !d_frames || nframes <= 0)
+        return fail(FFGPU_EINVAL, "bad argument");
+    if ((r = enc_device_init(e)) < 0)
+        return r;
+    if (nframes > e->max_batch)
+        return fail(FFGPU_EINVAL, "nframes %d exceeds max_batch %d", nframes, e->max_batch);
+    if (nframes > 1 && !e->intra)
+        return fail(FFGPU_EINVAL, "device batches need gop_size <= 1");
+    j = &e->jobs[0];
+    if (j->state != JOB_FREE)
+        return fail(FFGPU_EINVAL, "encode_device while send/receive pictures are pending");
+    st = cuda_stream ? (cudaStream_t)cuda_stream : j->stream;
+    for (int i = 0; i < nframes; i++) {
+        const int key = e->opt.gop_size == 0 || (e->picture_number + i) % e->opt.gop_size == 0;
+        set = enc_prefix_set(e, key, 3, 0, 1);
+        if (set < 0)
+            return set;
+        j->h_frame_set[i] = (uint8_t)set;
+        j->h_frame_key[i] = (uint8_t)key;
+        j->key[i] = key;
+    }
+    e->picture_number += nframes;
+    j->n = nframes;
+    enc_fill_dev(e, j, (const uint8_t *)d_frames, &E);
+    CK(cudaMemcpyAsync(j->d_frame_set, j->h_frame_set, nframes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(j->d_frame_key, j->h_frame_key, nframes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(j->d_overflow, 0, sizeof(uint32_t), st));
+    r = ffk_encode_group(&e->P, &E, nframes, st);
+    if (r < 0)
+        return fail(r, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    e->launches += r;
+    return 0;
+}
+
+static int enc_device_sizes(ffgpu_encoder *e, EncJob *j)
+{
+    (void)e;
+    CK(cudaMemcpy(j->h_pkt_size, j->d_pkt_size, sizeof(uint32_t) * j->n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(j->h_pkt_off, j->d_pkt_off, sizeof(uint32_t) * (j->n + 1), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(j->h_overflow, j->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (*j->h_overflow)
+        return fail(FFGPU_INVALIDDATA, "encoded frame too large");
+    return 0;
+}
+
+extern "C" int ffgpu_ffv1_encode_device_result(ffgpu_encoder *e, int frame, const void **d_pkt,
+                                               size_t *pkt_size)
+{
+    EncJob *j;
+    int r;
+    if (!e || !e->dev_ready)
+        return fail(FFGPU_EINVAL, "no device batch");
+    j = &e->jobs[0];
+    if (frame < 0 || frame >= j->n)
+        return fail(FFGPU_EINVAL, "frame index out of range");
+    if ((r = enc_device_sizes(e, j)) < 0)
+        return r;
+    if (d_pkt) *d_pkt = j->d_pkt + j->h_pkt_off[frame];
+    if (pkt_size) *pkt_size = j->h_pkt_size[frame];
+    return 0;
+}
+
+extern "C" int ffgpu_ffv1_encode_device_fetch(ffgpu_encoder *e, int frame, uint8_t *pkt, size_t cap,
+                                              size_t *pkt_size)
+{
+    const void *d;
+    size_t n;
+    int r = ffgpu_ffv1_encode_device_result(e, frame, &d, &n);
+    if (r < 0)
+        return r;
+    if (n > cap)
+        return fail(FFGPU_ENOSPC, "packet buffer too small: need %zu bytes", n);
+    CK(cudaMemcpy(pkt, d, n, cudaMemcpyDeviceToHost));
+    if (pkt_size) *pkt_size = n;
+    return 0;
+}
+
+extern "C" int ffgpu_ffv1_encode_close(ffgpu_encoder *e)
+{
+    if (!e)
+        return 0;
+    if (e->dev_ready) {
+        cudaDeviceSynchronize();
+        for (int i = 0; i < MAX_DEPTH; i++)
+            enc_free_job(&e->jobs[i]);
+        cudaFree(e->d_slices); cudaFree(e->d_qt); cudaFree(e->d_tab); cudaFree(e->d_prefix);
+        cudaFree(e->d_prefix_bytes); cudaFree(e->d_state_shared);
+    }
+    free(e->h_slices);
+    free(e->extradata);
+    ff_stream_free(&e->s);
+    free(e);
+    return 0;
+}
+
+/* ====================================================================== */
+/* decoder                                                                 */
+/* ====================================================================== */
+struct DecFrameMeta {
+    FFDecFrameInfo info;
+    int64_t pts;
+    int nslices;
+    int has_dst;
+    ffgpu_picture_out dst;
+    uint8_t damaged[FF_MAX_SLICES];
+    FFSliceRect rect[FF_MAX_SLICES];
+};
+
+struct DecJob {
+    cudaStream_t stream;
+    cudaEvent_t done;
+    int n, state, drained, fetched;
+    uint8_t *h_pkt, *d_pkt;
+    size_t pkt_cap, pkt_used;
+    FFDecSlice *h_work, *d_work;
+    int *h_nslices, *d_nslices;
+    uint8_t *d_state;
+    int32_t *d_lines;
+    uint8_t *d_frames;
+    FFDecResult *d_result, *h_result;
+    DecFrameMeta *meta;
+};
+
+struct ffgpu_decoder {
+    ffgpu_dec_options opt;
+    FFStream s;
+    FFDecHostState hs;
+    FFDevParams P;
+    FFDevSlice *h_slices;
+    int have_params;
+    int intra;
+    int max_batch, depth, max_slices, max_ctx, line_stride;
+    int dev_ready;
+    int16_t *d_qt;
+    FFRacTables *d_tab;
+    uint8_t *d_initial;
+    uint8_t *d_state_shared;
+    uint8_t *d_prev;            /* last output picture, for concealment */
+    int have_prev;
+    DecJob jobs[MAX_DEPTH];
+    int fill, head, flushing;
+    uint64_t launches;
+};
+
+static void dec_free_job(DecJob *j)
+{
+    cudaFreeHost(j->h_pkt); cudaFree(j->d_pkt); cudaFreeHost(j->h_work); cudaFree(j->d_work);
+    cudaFreeHost(j->h_nslices); cudaFree(j->d_nslices); cudaFree(j->d_state); cudaFree(j->d_lines);
+    cudaFree(j->d_frames); cudaFree(j->d_result); cudaFreeHost(j->h_result);
+    free(j->meta);
+    if (j->done) cudaEventDestroy(j->done);
+    if (j->stream) cudaStreamDestroy(j->stream);
+    memset(j, 0, sizeof(*j));
+}
+
+/* (re)derive the kernel parameters once the stream is known (after the extradata, or after
+ * the first v0/v1 key frame) */
+static int dec_setup_stream(ffgpu_decoder *d)
+{
+    int r;
+    if (!d->s.pf && (r = ff_pick_decoder_format(&d->s)) < 0)
+        return fail(r, "format not supported");
+    free(d->h_slices);
+    d->h_slices = (FFDevSlice *)calloc((size_t)d->s.nh * d->s.nv, sizeof(FFDevSlice));
+    if (!d->h_slices)
+        return fail(FFGPU_ENOMEM, "out of memory");
+    ff_fill_dev_params(&d->s, 0, &d->P, d->h_slices);
+    d->max_slices = d->s.nh * d->s.nv;
+    d->max_ctx = d->P.total_ctx / d->P.nsets;
+    d->line_stride = 8;
+    for (int i = 0; i < d->max_slices; i++)
+        if (d->h_slices[i].w + 8 > d->line_stride)
+            d->line_stride = d->h_slices[i].w + 8;
+    /* a slice header may describe any rectangle of the picture; size the scratch for the
+     * worst case only when the stream is not trusted to match the grid */
+    if (d->s.version > 2 && d->line_stride < d->s.width + 8 && d->max_slices <= 16)
+        d->line_stride = d->s.width + 8;
+    d->intra = d->s.version > 2 && d->s.intra;
+    if (d->intra) {
+        const size_t per_frame = d->P.frame_bytes * 2 + (size_t)d->max_slices * d->P.total_ctx * FF_CONTEXT_SIZE;
+        int b = d->opt.max_batch > 0 ? d->opt.max_batch : (49152 + d->max_slices - 1) / d->max_slices;
+        size_t cap = ((size_t)12 << 30) / (per_frame ? per_frame : 1);
+        if (b > 256) b = 256;
+        if (d->opt.max_batch <= 0 && (size_t)b > cap) b = (int)cap;
+        if (b < 1) b = 1;
+        d->max_batch = b;
+        d->depth = d->opt.pipeline_depth > 0 ? d->opt.pipeline_depth : 3;
+    } else {
+        d->max_batch = 1;
+        d->depth = 1;
+    }
+    if (d->depth > MAX_DEPTH)
+        d->depth = MAX_DEPTH;
+    d->have_params = 1;
+    return 0;
+}
+
+static int dec_device_init(ffgpu_decoder *d)
+{
+    const FFDevParams *P = &d->P;
+    const int golomb = P->ac == FF_AC_GOLOMB;
+    const size_t state_frame = (size_t)d->max_slices * P->total_ctx * (golomb ? 8 : FF_CONTEXT_SIZE);
+    int16_t *qt;
+    int ndev = 0, any_initial = 0;
+    if (d->dev_ready)
+        return 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(FFGPU_EXTERNAL, "no CUDA device: the FFV1 pixel path has no CPU fallback");
+    CK(cudaSetDevice(d->opt.device));
+    qt = (int16_t *)malloc(sizeof(int16_t) * FF_MAX_QUANT_TABLES * FF_QT_STRIDE);
+    if (!qt)
+        return fail(FFGPU_ENOMEM, "out of memory");
+    flatten_qt(&d->s, qt);
+    CK(cudaMalloc(&d->d_qt, sizeof(int16_t) * FF_MAX_QUANT_TABLES * FF_QT_STRIDE));
+    CK(cudaMemcpy(d->d_qt, qt, sizeof(int16_t) * FF_MAX_QUANT_TABLES * FF_QT_STRIDE, cudaMemcpyHostToDevice));
+    free(qt);
+    CK(cudaMalloc(&d->d_tab, sizeof(FFRacTables)));
+    CK(cudaMemcpy(d->d_tab, &d->s.cur_tab, sizeof(FFRacTables), cudaMemcpyHostToDevice));
+    for (int i = 0; i < d->s.qt_count; i++)
+        any_initial |= d->s.initial[i] != NULL;
+    if (any_initial) {
+        const size_t per = (size_t)d->max_ctx * FF_CONTEXT_SIZE;
+        uint8_t *tmp = (uint8_t *)malloc(per * FF_MAX_QUANT_TABLES);
+        if (!tmp)
+            return fail(FFGPU_ENOMEM, "out of memory");
+        memset(tmp, 128, per * FF_MAX_QUANT_TABLES);
+        for (int i = 0; i < d->s.qt_count; i++)
+            if (d->s.initial[i])
+                memcpy(tmp + per * i, d->s.initial[i], (size_t)d->s.ctx_count[i] * FF_CONTEXT_SIZE);
+        CK(cudaMalloc(&d->d_initial, per * FF_MAX_QUANT_TABLES));
+        CK(cudaMemcpy(d->d_initial, tmp, per * FF_MAX_QUANT_TABLES, cudaMemcpyHostToDevice));
+        free(tmp);
+    }
+    if (!d->intra)
+        CK(cudaMalloc(&d->d_state_shared, state_frame));
+    CK(cudaMalloc(&d->d_prev, P->frame_bytes));
+    CK(cudaMemset(d->d_prev, 0, P->frame_bytes));
+    for (int i = 0; i < d->depth; i++) {
+        DecJob *j = &d->jobs[i];
+        const size_t B = (size_t)d->max_batch;
+        CK(cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&j->done, cudaEventDisableTiming));
+        j->pkt_cap = align_up(B * (P->frame_bytes / 2 + 65536) + 256, 4096);
+        CK(cudaHostAlloc(&j->h_pkt, j->pkt_cap, cudaHostAllocDefault));
+        CK(cudaMalloc(&j->d_pkt, j->pkt_cap));
+        CK(cudaHostAlloc(&j->h_work, B * d->max_slices * sizeof(FFDecSlice), cudaHostAllocDefault));
+        CK(cudaMalloc(&j->d_work, B * d->max_slices * sizeof(FFDecSlice)));
+        CK(cudaHostAlloc(&j->h_nslices, B * sizeof(int), cudaHostAllocDefault));
+        CK(cudaMalloc(&j->d_nslices, B * sizeof(int)));
+        if (d->intra)
+            CK(cudaMalloc(&j->d_state, B * state_frame));
+        CK(cudaMalloc(&j->d_lines, B * d->max_slices * P->ncoded * 2 * d->line_stride * sizeof(int32_t)));
+        CK(cudaMalloc(&j->d_frames, B * P->frame_bytes));
+        CK(cudaMemset(j->d_frames, 0, B * P->frame_bytes));
+        CK(cudaMalloc(&j->d_result, B * d->max_slices * sizeof(FFDecResult)));
+        CK(cudaHostAlloc(&j->h_result, B * d->max_slices * sizeof(FFDecResult), cudaHostAllocDefault));
+        j->meta = (DecFrameMeta *)calloc(B, sizeof(DecFrameMeta));
+        if (!j->meta)
+            return fail(FFGPU_ENOMEM, "out of memory");
+    }
+    d->dev_ready = 1;
+    return 0;
+}
+
+extern "C" int ffgpu_ffv1_decode_init(ffgpu_decoder **pdec, const ffgpu_dec_options *opt)
+{
+    ffgpu_decoder *d;
+    int r;
+    if (!pdec || !opt)
+        return fail(FFGPU_EINVAL, "null argument");
+    *pdec = NULL;
+    g_err[0] = 0;
+    if (!opt->width || !opt->height)
+        return fail(FFGPU_INVALIDDATA, "decode_init: zero dimensions");
+    d = (ffgpu_decoder *)calloc(1, sizeof(*d));
+    if (!d)
+        return fail(FFGPU_ENOMEM, "out of memory");
+    d->opt = *opt;
+    d->opt.extradata = NULL;
+    d->s.width = opt->width;
+    d->s.height = opt->height;
+    d->s.nh = d->s.nv = 1;
+    ff_default_tables(&d->s.def_tab);
+    d->s.cur_tab = d->s.def_tab;
+    if (opt->extradata_size > 0) {
+        if ((r = ff_parse_extradata(&d->s, opt->extradata, opt->extradata_size)) < 0) {
+            ff_stream_free(&d->s);
+            free(d);
+            return fail(r, "decode_init: invalid extradata (%d)", r);
+        }
+        if ((r = dec_setup_stream(d)) < 0) {
+            ff_stream_free(&d->s);
+            free(d);
+            return r;
+        }
+    }
+    d->hs.max_slices = d->s.nh * d->s.nv;
+    *pdec = d;
+    return 0;
+}
+
+extern "C" const char *ffgpu_ffv1_decoder_pix_fmt(const ffgpu_decoder *d)
+{
+    return d && d->s.pf ? d->s.pf->name : NULL;
+}
+
+extern "C" void ffgpu_ffv1_decoder_info(const ffgpu_decoder *d, int info[8])
+{
+    info[0] = d->s.version; info[1] = d->s.micro_version; info[2] = d->s.ac; info[3] = d->s.nh;
+    info[4] = d->s.nv; info[5] = d->s.ec; info[6] = d->s.bits; info[7] = d->s.colorspace;
+}
+
+extern "C" uint64_t ffgpu_ffv1_decoder_launches(const ffgpu_decoder *d) { return d->launches; }
+
+static void dec_fill_dev(const ffgpu_decoder *d, const DecJob *j, uint8_t *frames, FFDecDev *D)
+{
+    memset(D, 0, sizeof(*D));
+    D->work = j->d_work;
+    D->nslices = j->d_nslices;
+    D->qt = d->d_qt;
+    D->tab = d->d_tab;
+    D->initial = d->d_initial;
+    D->pkt = j->d_pkt;
+    D->state = d->intra ? j->d_state : d->d_state_shared;
+    D->lines = j->d_lines;
+    D->line_stride = d->line_stride;
+    D->frames = frames;
+    D->result = j->d_result;
+    D->max_slices = d->max_slices;
+    D->max_ctx = d->max_ctx;
+    D->state_per_frame = d->intra;
+}
+
+static int download_picture(const ffgpu_decoder *d, const uint8_t *d_frame, const ffgpu_picture_out *dst,
+                            cudaStream_t st)
+{
+    const FFPixFmt *pf = d->s.pf;
+    for (int k = 0; k < pf->nplanes; k++) {
+        int rb, rows;
+        ff_plane_geometry(pf, d->s.width, d->s.height, k, &rb, &rows);
+        if (!dst->data[k] || dst->linesize[k] < rb)
+            return fail(FFGPU_EINVAL, "output plane %d missing or linesize too small", k);
+        CK(cudaMemcpy2DAsync(dst->data[k], dst->linesize[k], d_frame + d->P.plane_off[k], d->P.pitch[k],
+                             rb, rows, cudaMemcpyDeviceToHost, st));
+    }
+    return 0;
+}
+
+static int dec_launch(ffgpu_decoder *d, DecJob *j, uint8_t *frames, cudaStream_t st, int download)
+{
+    FFDecDev D;
+    int r;
+    dec_fill_dev(d, j, frames, &D);
+    CK(cudaMemcpyAsync(j->d_pkt, j->h_pkt, align_up(j->pkt_used + 64, 16), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(j->d_work, j->h_work, (size_t)j->n * d->max_slices * sizeof(FFDecSlice),
+                       cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(j->d_nslices, j->h_nslices, j->n * sizeof(int), cudaMemcpyHostToDevice, st));
+    r = ffk_decode_group(&d->P, &D, j->n, st);
+    if (r < 0)
+        return fail(r, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    d->launches += r;
+    CK(cudaMemcpyAsync(j->h_result, j->d_result, (size_t)j->n * d->max_slices * sizeof(FFDecResult),
+                       cudaMemcpyDeviceToHost, st));
+    if (download)
+        for (int i = 0; i < j->n; i++)
+            if (j->meta[i].has_dst &&
+                (r = download_picture(d, j->d_frames + (size_t)i * d->P.frame_bytes, &j->meta[i].dst, st)) < 0)
+                return r;
+    return 0;
+}
+
+/* append one packet to the group being filled; parses its frame/slice headers on the host */
+static int dec_add_packet(ffgpu_decoder *d, DecJob *j, const uint8_t *pkt, size_t size, int64_t pts,
+                          const ffgpu_picture_out *dst)
+{
+    DecFrameMeta *m;
+    size_t off = align_up(j->pkt_used, 16);
+    int n;
+    if (off + size + 64 > j->pkt_cap) {
+        if (j->n > 0)
+            return FFGPU_EAGAIN;                   /* caller launches the group first */
+        cudaFreeHost(j->h_pkt);
+        cudaFree(j->d_pkt);
+        j->h_pkt = j->d_pkt = NULL;
+        j->pkt_cap = align_up(size * 2 + 4096, 4096);
+        CK(cudaHostAlloc(&j->h_pkt, j->pkt_cap, cudaHostAllocDefault));
+        CK(cudaMalloc(&j->d_pkt, j->pkt_cap));
+        off = 0;
+    }
+    memcpy(j->h_pkt + off, pkt, size);
+    memset(j->h_pkt + off + size, 0, 64);          /* AV_INPUT_BUFFER_PADDING_SIZE */
+    m = &j->meta[j->n];
+    memset(m, 0, sizeof(*m));
+    n = ff_dec_parse_packet(&d->s, &d->hs, j->h_pkt + off, size, (uint32_t)off,
+                            j->h_work + (size_t)j->n * d->max_slices, &m->info);
+    if (n < 0)
+        return fail(n, "invalid packet (%d)", n);
+    m->nslices = n;
+    m->pts = pts;
+    memcpy(m->damaged, d->hs.damaged, sizeof(m->damaged));
+    memcpy(m->rect, d->hs.rect, sizeof(FFSliceRect) * (n > 0 ? n : 0));
+    if (dst) {
+        m->dst = *dst;
+        m->has_dst = 1;
+    }
+    j->h_nslices[j->n] = n;
+    j->pkt_used = off + size;
+    j->n++;
+    return 0;
+}
+
+/* after a group has finished: damage bookkeeping (ffv1dec.c:351-359, :940-969) */
+static int dec_finish_frame(ffgpu_decoder *d, DecJob *j, int i, ffgpu_picture_out *out)
+{
+    DecFrameMeta *m = &j->meta[i];
+    const FFDevParams *P = &d->P;
+    uint8_t *frame = j->d_frames + (size_t)i * P->frame_bytes;
+    int damaged = 0, r;
+    for (int s = 0; s < m->nslices; s++) {
+        const FFDecSlice *w = &j->h_work[(size_t)i * d->max_slices + s];
+        const FFDecResult *res = &j->h_result[(size_t)i * d->max_slices + s];
+        if (!w->skip && P->ac != FF_AC_GOLOMB && P->version > 2) {
+            const int v = (int)w->size - (int)res->end_pos - 2 - 5 * P->ec;
+            if (v) {
+                m->damaged[s] = 1;                 /* "bytestream end mismatching by %d" */
+                d->hs.damaged[s] = 1;
+            }
+        }
+        damaged += m->damaged[s];
+    }
+    if (damaged && d->have_prev) {
+        const uint8_t *prev = i > 0 ? j->d_frames + (size_t)(i - 1) * P->frame_bytes : d->d_prev;
+        for (int s = m->nslices - 1; s >= 0; s--)
+            if (m->damaged[s]) {
+                r = ffk_conceal_rect(P, frame, prev, m->rect[s].x, m->rect[s].y, m->rect[s].w, m->rect[s].h,
+                                     d->s.pf->depth > 8, j->stream);
+                if (r < 0)
+                    return fail(r, "conceal launch failed");
+                d->launches += r;
+            }
+        if (m->has_dst && (r = download_picture(d, frame, &m->dst, j->stream)) < 0)
+            return r;
+        CK(cudaStreamSynchronize(j->stream));
+    }
+    if (i == j->n - 1) {
+        /* keep the last picture of the group for the next group's concealment */
+        CK(cudaMemcpyAsync(d->d_prev, frame, P->frame_bytes, cudaMemcpyDeviceToDevice, j->stream));
+        CK(cudaStreamSynchronize(j->stream));
+    }
+    d->have_prev = 1;
+    if (out) {
+        out->key_frame = m->info.key_frame;
+        out->interlaced_frame = m->info.interlaced_frame;
+        out->top_field_first = m->info.top_field_first;
+        out->sar_num = m->info.sar_num;
+        out->sar_den = m->info.sar_den;
+        out->damaged_slices = damaged;
+        out->pts = m->pts;
+    }
+    return 0;
+}
+
+static int dec_launch_group(ffgpu_decoder *d, DecJob *j)
+{
+    int r = dec_launch(d, j, j->d_frames, j->stream, 1);
+    if (r < 0)
+        return r;
+    CK(cudaEventRecord(j->done, j->stream));
+    j->state = JOB_RUNNING;
+    j->drained = 0;
+    return 0;
+}
+
+extern "C" int ffgpu_ffv1_decode_send_packet(ffgpu_decoder *d, const uint8_t *pkt, size_t size,
+                                              int64_t pts, const ffgpu_picture_out *dst)
+{
+    DecJob *j;
+    int r;
+    if (!d)
+        return fail(FFGPU_EINVAL, "null decoder");
+    if (!pkt) {
+        d->flushing = 1;
+        if (d->dev_ready) {
+            j = &d->jobs[d->fill];
+            if (j->state == JOB_FILLING && j->n > 0) {
+                if ((r = dec_launch_group(d, j)) < 0)
+                    return r;
+                d->fill = (d->fill + 1) % d->depth;
+            }
+        }
+        return 0;
+    }
+    if (d->flushing)
+        return fail(FFGPU_EOF, "send_packet after flush");
+    if (d->dev_ready) {
+        j = &d->jobs[d->fill];
+        if (j->state == JOB_RUNNING || j->state == JOB_DRAINING)
+            return FFGPU_EAGAIN;
+    }
+    /* the first packet may have to create the device side */
+    if (!d->dev_ready) {
+        if (!d->have_params) {
+            FFDecSlice tmp[1];
+            FFDecFrameInfo info;
+            FFDecHostState hs = d->hs;
+            hs.max_slices = 1;
+            r = ff_dec_parse_packet(&d->s, &hs, pkt, size, 0, tmp, &info);
+            if (r < 0)
+                return fail(r, "invalid packet (%d)", r);
+            if ((r = dec_setup_stream(d)) < 0)
+                return r;
+            d->hs.max_slices = d->max_slices;
+        }
+        if ((r = dec_device_init(d)) < 0)
+            return r;
+    }
+    j = &d->jobs[d->fill];
+    if (j->state == JOB_FREE) {
+        j->state = JOB_FILLING;
+        j->n = 0;
+        j->pkt_used = 0;
+    }
+    r = dec_add_packet(d, j, pkt, size, pts, dst);
+    if (r == FFGPU_EAGAIN) {
+        /* packet arena full: launch what we have, the caller retries */
+        if ((r = dec_launch_group(d, j)) < 0)
+            return r;
+        d->fill = (d->fill + 1) % d->depth;
+        return ffgpu_ffv1_decode_send_packet(d, pkt, size, pts, dst);
+    }
+    if (r < 0) {
+        if (j->n == 0)
+            j->state = JOB_FREE;
+        return r;
+    }
+    if (j->n == d->max_batch) {
+        if ((r = dec_launch_group(d, j)) < 0)
+            return r;
+        d->fill = (d->fill + 1) % d->depth;
+    }
+    return 0;
+}
+
+extern "C" int ffgpu_ffv1_decode_receive_frame(ffgpu_decoder *d, ffgpu_picture_out *out)
+{
+    DecJob *j;
+    int r, i;
+    if (!d || !d->dev_ready)
+        return d && d->flushing ? FFGPU_EOF : FFGPU_EAGAIN;
+    j = &d->jobs[d->head];
+    if (j->state == JOB_FREE || j->state == JOB_FILLING)
+        return d->flushing ? FFGPU_EOF : FFGPU_EAGAIN;
+    if (j->state == JOB_RUNNING) {
+        const DecJob *f = &d->jobs[d->fill];
+        const int must_wait = d->flushing || f->state == JOB_RUNNING || f->state == JOB_DRAINING;
+        if (!must_wait && cudaEventQuery(j->done) == cudaErrorNotReady)
+            return FFGPU_EAGAIN;
+        CK(cudaEventSynchronize(j->done));
+        j->state = JOB_DRAINING;
+    }
+    i = j->drained;
+    if (!j->meta[i].has_dst) {
+        /* destination supplied only now: copy this picture out synchronously */
+        if (!out)
+            return fail(FFGPU_EINVAL, "no destination picture");
+        j->meta[i].dst = *out;
+        j->meta[i].has_dst = 1;
+        if ((r = download_picture(d, j->d_frames + (size_t)i * d->P.frame_bytes, out, j->stream)) < 0)
+            return r;
+        CK(cudaStreamSynchronize(j->stream));
+    }
+    if ((r = dec_finish_frame(d, j, i, out)) < 0)
+        return r;
+    if (++j->drained == j->n) {
+        j->state = JOB_FREE;
+        j->n = 0;
+        d->head = (d->head + 1) % d->depth;
+    }
+    return 0;
+}
+
+extern "C" int ffgpu_ffv1_decode_frame(ffgpu_decoder *d, const uint8_t *pkt, size_t size,
+                                       ffgpu_picture_out *out, int *got_frame)
+{
+    DecJob *j;
+    int r;
+    if (got_frame)
+        *got_frame = 0;
+    if (!d || !pkt || !out)
+        return fail(FFGPU_EINVAL, "null argument");
+    if (d->dev_ready)
+        for (int i = 0; i < d->depth; i++)
+            if (d->jobs[i].state != JOB_FREE)
+                return fail(FFGPU_EINVAL, "decode_frame while send/receive packets are pending");
+    if ((r = ffgpu_ffv1_decode_send_packet(d, pkt, size, 0, out)) < 0)
+        return r;
+    j = &d->jobs[d->fill];
+    if (j->state == JOB_FILLING) {
+        if ((r = dec_launch_group(d, j)) < 0)
+            return r;
+        d->fill = (d->fill + 1) % d->depth;
+    }
+    j = &d->jobs[d->head];
+    CK(cudaEventSynchronize(j->done));
+    j->state = JOB_DRAINING;
+    if ((r = ffgpu_ffv1_decode_receive_frame(d, out)) < 0)
+        return r;
+    if (got_frame)
+        *got_frame = 1;
+    return (int)size;
+}
+
+extern "C" int ffgpu_ffv1_decode_device(ffgpu_decoder *d, const uint8_t *const *pkts,
+                                        const size_t *sizes, int nframes, void *d_frames,
+                                        void *cuda_stream)
+{
+    DecJob *j;
+    cudaStream_t st;
+    int r;
+    if (!d || !pkts || !sizes || nframes <= 0 || !d_frames)
+        return fail(FFGPU_EINVAL, "bad argument");
+    if (d->dev_ready)
+        for (int i = 0; i < d->depth; i++)
+            if (d->jobs[i].state != JOB_FREE)
+                return fail(FFGPU_EINVAL, "decode_device while send/receive packets are pending");
+    if (!d->have_params || !d->dev_ready) {
+        if (!d->have_params) {
+            FFDecSlice tmp[1];
+            FFDecFrameInfo info;
+            FFDecHostState hs = d->hs;
+            hs.max_slices = 1;
+            r = ff_dec_parse_packet(&d->s, &hs, pkts[0], sizes[0], 0, tmp, &info);
+            if (r < 0)
+                return fail(r, "invalid packet (%d)", r);
+            if ((r = dec_setup_stream(d)) < 0)
+                return r;
+            d->hs.max_slices = d->max_slices;
+        }
+        if ((r = dec_device_init(d)) < 0)
+            return r;
+    }
+    if (nframes > d->max_batch)
+        return fail(FFGPU_EINVAL, "nframes %d exceeds max_batch %d", nframes, d->max_batch);
+    j = &d->jobs[0];
+    j->n = 0;
+    j->pkt_used = 0;
+    for (int i = 0; i < nframes; i++) {
+        r = dec_add_packet(d, j, pkts[i], sizes[i], 0, NULL);
+        if (r == FFGPU_EAGAIN)
+            return fail(FFGPU_ENOSPC, "packets of the batch exceed the packet arena");
+        if (r < 0) {
+            j->n = 0;
+            return r;
+        }
+    }
+    st = cuda_stream ? (cudaStream_t)cuda_stream : j->stream;
+    r = dec_launch(d, j, (uint8_t *)d_frames, st, 0);
+    j->n = 0;
+    j->state = JOB_FREE;
+    return r;
+}
+
+extern "C" int ffgpu_ffv1_decode_close(ffgpu_decoder *d)
+{
+    if (!d)
+        return 0;
+    if (d->dev_ready) {
+        cudaDeviceSynchronize();
+        for (int i = 0; i < MAX_DEPTH; i++)
+            dec_free_job(&d->jobs[i]);
+        cudaFree(d->d_qt); cudaFree(d->d_tab); cudaFree(d->d_initial); cudaFree(d->d_state_shared);
+        cudaFree(d->d_prev);
+    }
+    free(d->h_slices);
+    ff_stream_free(&d->s);
+    free(d);
+    return 0;
+}

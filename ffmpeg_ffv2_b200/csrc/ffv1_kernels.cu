@@ -1,0 +1,321 @@
+/*
+ * ffv1_kernels.cu -- sm_100a kernels of the FFV1 slice pixel path.
+ *
+ * The work is integer, byte-granular and, inside a slice, a strict dependence chain
+ * (adaptive probability states + range coder low/range).  Parallelism therefore comes from
+ *   - samples            (stage A: one thread per sample, HBM-bound, coalesced along x)
+ *   - slices x pictures  (stage B / decode: one thread per slice; a launch group holds
+ *                         max_batch pictures so that tens of thousands of independent
+ *                         coders are resident on the 148 SMs)
+ * No tensor cores: nothing here is a contraction.
+ *
+ * Kernel        reference span it replaces
+ * k_symbolize   encode_plane / encode_rgb_frame sample loads + get_context + predict
+ *               (ffv1enc.c:274-312, ffv1enc_template.c:125-201, ffv1_template.c:23-52)
+ * k_fill_state  ff_ffv1_clear_slice_state (ffv1.c:182-207)
+ * k_code_*      encode_line / put_symbol_inline / put_vlc_symbol per slice, the job
+ *               avctx->execute(encode_slice) fans out (ffv1enc.c:1233, :1045-1120)
+ * k_pack_*      the serial compaction loop of encode_frame (ffv1enc.c:1236-1262): device
+ *               prefix sums over slice and packet sizes + gather + size/CRC trailers
+ * k_decode      decode_slice after its header (ffv1dec.c:304-359) for every slice of every
+ *               packet of the group
+ */
+#include <cuda_runtime.h>
+#include <cub/block/block_scan.cuh>
+
+#include "../../include/ffgpu.h"
+#include "ffv1_launch.h"
+#include "ffv1_slice.cuh"
+
+#define CODE_THREADS 128
+#define SYM_THREADS  256
+
+static inline int launch_ok(void)
+{
+    return cudaGetLastError() == cudaSuccess;
+}
+
+/* ---------------- stage A ---------------- */
+__global__ void __launch_bounds__(SYM_THREADS)
+k_symbolize(const FFDevParams P, const FFDevSlice *__restrict__ slices,
+            const uint8_t *__restrict__ frames, const int16_t *__restrict__ qt,
+            uint32_t *__restrict__ tokens)
+{
+    const FFDevSlice sl = slices[blockIdx.x];
+    const uint8_t *frame = frames + (size_t)blockIdx.y * P.frame_bytes;
+    uint32_t *tok = tokens + (size_t)blockIdx.y * P.frame_tokens + sl.tok_off;
+    for (uint32_t i = blockIdx.z * SYM_THREADS + threadIdx.x; i < sl.ntok; i += gridDim.z * SYM_THREADS)
+        tok[i] = ff_symbolize_index(P, sl, frame, qt, i);
+}
+
+/* ---------------- adaptive state reset ---------------- */
+/* fills the state arenas of the frames flagged as key frames with a 64-bit pattern
+ * (range coder: 128 in every byte; Golomb: {drift 0, error_sum 4, bias 0, count 1}) */
+__global__ void k_fill_state(uint2 *__restrict__ state, size_t words_per_frame,
+                             const uint8_t *__restrict__ frame_key, int state_per_frame,
+                             uint32_t lo, uint32_t hi)
+{
+    const int f = blockIdx.y;
+    if (!frame_key[f])
+        return;
+    uint2 *p = state + (state_per_frame ? (size_t)f * words_per_frame : 0);
+    const uint2 v = make_uint2(lo, hi);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words_per_frame;
+         i += (size_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+/* ---------------- stage B ---------------- */
+__global__ void __launch_bounds__(CODE_THREADS)
+k_code_range(const FFDevParams P, const FFEncDev E, int nframes)
+{
+    __shared__ FFRacTables tab;
+    for (int i = threadIdx.x; i < (int)sizeof(FFRacTables) / 4; i += CODE_THREADS)
+        ((uint32_t *)&tab)[i] = ((const uint32_t *)E.tab)[i];
+    __syncthreads();
+    const int gid = blockIdx.x * CODE_THREADS + threadIdx.x;
+    if (gid >= nframes * P.nslices)
+        return;
+    const int f = gid / P.nslices, s = gid - f * P.nslices;
+    const FFDevSlice sl = E.slices[s];
+    const size_t st_slot = (size_t)(E.state_per_frame ? f : 0) * P.nslices + s;
+    uint32_t ovf = 0;
+    const uint32_t n = ff_encode_slice_range(
+        sl, E.tokens + (size_t)f * P.frame_tokens + sl.tok_off,
+        E.state + st_slot * P.total_ctx * FF_CONTEXT_SIZE, &tab,
+        E.prefix[(size_t)E.frame_prefix_set[f] * P.nslices + s], E.prefix_bytes,
+        E.bs + (size_t)f * P.frame_bs + sl.bs_off, &ovf);
+    E.slice_bytes[gid] = n;
+    if (ovf)
+        atomicOr(E.overflow, 1u);
+}
+
+__global__ void __launch_bounds__(CODE_THREADS)
+k_code_golomb(const FFDevParams P, const FFEncDev E, int nframes)
+{
+    const int gid = blockIdx.x * CODE_THREADS + threadIdx.x;
+    if (gid >= nframes * P.nslices)
+        return;
+    const int f = gid / P.nslices, s = gid - f * P.nslices;
+    const FFDevSlice sl = E.slices[s];
+    const size_t st_slot = (size_t)(E.state_per_frame ? f : 0) * P.nslices + s;
+    uint32_t ovf = 0;
+    const uint32_t n = ff_encode_slice_golomb(
+        P, sl, E.tokens + (size_t)f * P.frame_tokens + sl.tok_off,
+        (uint2 *)E.state + st_slot * P.total_ctx,
+        E.prefix[(size_t)E.frame_prefix_set[f] * P.nslices + s], E.prefix_bytes,
+        E.bs + (size_t)f * P.frame_bs + sl.bs_off, &ovf);
+    E.slice_bytes[gid] = n;
+    if (ovf)
+        atomicOr(E.overflow, 1u);
+}
+
+/* ---------------- packet assembly ---------------- */
+/* per picture: exclusive scan of the packed slice sizes -> slice offsets + packet size */
+__global__ void __launch_bounds__(1024)
+k_pack_slice_scan(const FFDevParams P, const FFEncDev E)
+{
+    typedef cub::BlockScan<uint32_t, 1024> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    const int f = blockIdx.x, s = threadIdx.x;
+    uint32_t v = s < P.nslices ? ff_slice_packed_size(P, s, E.slice_bytes[(size_t)f * P.nslices + s]) : 0;
+    uint32_t off, total;
+    Scan(tmp).ExclusiveSum(v, off, total);
+    if (s < P.nslices)
+        E.slice_off[(size_t)f * P.nslices + s] = off;
+    if (s == 0)
+        E.pkt_size[f] = total;
+}
+
+/* over the pictures of the group: exclusive scan of packet sizes (16-byte aligned starts) */
+__global__ void __launch_bounds__(1024)
+k_pack_frame_scan(const FFEncDev E, int nframes)
+{
+    typedef cub::BlockScan<uint32_t, 1024> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    const int f = threadIdx.x;
+    uint32_t v = f < nframes ? ((E.pkt_size[f] + 15u) & ~15u) : 0;
+    uint32_t off, total;
+    Scan(tmp).ExclusiveSum(v, off, total);
+    if (f < nframes)
+        E.pkt_off[f] = off;
+    if (f == 0)
+        E.pkt_off[nframes] = total;
+}
+
+__global__ void __launch_bounds__(CODE_THREADS)
+k_pack_gather(const FFDevParams P, const FFEncDev E)
+{
+    __shared__ uint32_t crc_tab[256];
+    for (int i = threadIdx.x; i < 256; i += CODE_THREADS)
+        crc_tab[i] = ff_crc_table_entry(i);
+    __syncthreads();
+    const int f = blockIdx.y, s = blockIdx.x * CODE_THREADS + threadIdx.x;
+    if (s >= P.nslices)
+        return;
+    const FFDevSlice sl = E.slices[s];
+    ff_pack_slice(P, s, E.bs + (size_t)f * P.frame_bs + sl.bs_off,
+                  E.slice_bytes[(size_t)f * P.nslices + s],
+                  E.pkt + E.pkt_off[f] + E.slice_off[(size_t)f * P.nslices + s], crc_tab);
+}
+
+extern "C" int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nframes, ffk_stream stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    int launches = 0;
+    uint32_t max_tok = 0;
+    if (nframes <= 0 || nframes > 1024 || P->nslices > 1024)
+        return FFGPU_EINVAL;
+
+    /* stage A */
+    {
+        /* enough z-blocks to cover large slices; small slices get one block each */
+        max_tok = (uint32_t)(P->frame_tokens / (size_t)P->nslices) + 1;
+        int z = (int)((max_tok + SYM_THREADS * 16 - 1) / (SYM_THREADS * 16));
+        if (z < 1) z = 1;
+        if (z > 64) z = 64;
+        dim3 grid(P->nslices, nframes, z);
+        k_symbolize<<<grid, SYM_THREADS, 0, st>>>(*P, E->slices, E->frames, E->qt, E->tokens);
+        launches++;
+        if (!launch_ok()) return FFGPU_EXTERNAL;
+    }
+    /* state reset for key frames */
+    {
+        const int golomb = P->ac == FF_AC_GOLOMB;
+        const size_t bytes = (size_t)P->nslices * P->total_ctx * (golomb ? 8 : FF_CONTEXT_SIZE);
+        const size_t words = bytes / 8;
+        int bx = (int)((words + 255) / 256);
+        if (bx > 2048) bx = 2048;
+        dim3 grid(bx, nframes);
+        k_fill_state<<<grid, 256, 0, st>>>((uint2 *)E->state, words, E->frame_key, E->state_per_frame,
+                                           golomb ? FF_VLC_INIT_LO : 0x80808080u,
+                                           golomb ? FF_VLC_INIT_HI : 0x80808080u);
+        launches++;
+        if (!launch_ok()) return FFGPU_EXTERNAL;
+    }
+    /* stage B */
+    {
+        const int total = nframes * P->nslices;
+        const int blocks = (total + CODE_THREADS - 1) / CODE_THREADS;
+        if (P->ac == FF_AC_GOLOMB)
+            k_code_golomb<<<blocks, CODE_THREADS, 0, st>>>(*P, *E, nframes);
+        else
+            k_code_range<<<blocks, CODE_THREADS, 0, st>>>(*P, *E, nframes);
+        launches++;
+        if (!launch_ok()) return FFGPU_EXTERNAL;
+    }
+    /* packet assembly */
+    k_pack_slice_scan<<<nframes, 1024, 0, st>>>(*P, *E);
+    k_pack_frame_scan<<<1, 1024, 0, st>>>(*E, nframes);
+    {
+        dim3 grid((P->nslices + CODE_THREADS - 1) / CODE_THREADS, nframes);
+        k_pack_gather<<<grid, CODE_THREADS, 0, st>>>(*P, *E);
+    }
+    launches += 3;
+    if (!launch_ok()) return FFGPU_EXTERNAL;
+    return launches;
+}
+
+/* ---------------- decoder ---------------- */
+/* reset the adaptive states of the slices of key frames: 128 or the stream's initial
+ * states per quant table (ffv1.c:182-207) */
+__global__ void k_dec_init_state(const FFDevParams P, const FFDecDev D, int golomb)
+{
+    const int f = blockIdx.y, s = blockIdx.x;
+    if (s >= D.nslices[f])
+        return;
+    const FFDecSlice w = D.work[(size_t)f * D.max_slices + s];
+    if (!w.key_frame || w.skip)
+        return;
+    const size_t slot = (size_t)(D.state_per_frame ? f : 0) * D.max_slices + s;
+    if (golomb) {
+        uint2 *p = (uint2 *)D.state + slot * P.total_ctx;
+        for (int i = threadIdx.x; i < P.total_ctx; i += blockDim.x)
+            p[i] = make_uint2(FF_VLC_INIT_LO, FF_VLC_INIT_HI);
+    } else {
+        uint32_t *p = (uint32_t *)(D.state + slot * P.total_ctx * FF_CONTEXT_SIZE);
+        const int words_per_set = D.max_ctx * FF_CONTEXT_SIZE / 4;
+        for (int set = 0; set < P.nsets; set++) {
+            const uint32_t *init = D.initial
+                ? (const uint32_t *)(D.initial + (size_t)w.qidx[set] * D.max_ctx * FF_CONTEXT_SIZE) : 0;
+            for (int i = threadIdx.x; i < words_per_set; i += blockDim.x)
+                p[set * words_per_set + i] = init ? init[i] : 0x80808080u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CODE_THREADS)
+k_decode(const FFDevParams P, const FFDecDev D, int nframes)
+{
+    __shared__ FFRacTables tab;
+    for (int i = threadIdx.x; i < (int)sizeof(FFRacTables) / 4; i += CODE_THREADS)
+        ((uint32_t *)&tab)[i] = ((const uint32_t *)D.tab)[i];
+    __syncthreads();
+    const int gid = blockIdx.x * CODE_THREADS + threadIdx.x;
+    if (gid >= nframes * D.max_slices)
+        return;
+    const int f = gid / D.max_slices, s = gid - f * D.max_slices;
+    FFDecResult r;
+    r.end_pos = 0; r.overread = 0; r.error = 0; r.pad = 1;      /* pad=1: not decoded */
+    if (s < D.nslices[f]) {
+        const FFDecSlice w = D.work[gid];
+        if (!w.skip) {
+            const size_t slot = (size_t)(D.state_per_frame ? f : 0) * D.max_slices + s;
+            FFDecCtx C;
+            C.qt_all = D.qt;
+            C.tab = &tab;
+            C.rstate = D.state + slot * P.total_ctx * FF_CONTEXT_SIZE;
+            C.vstate = (uint2 *)D.state + slot * P.total_ctx;
+            C.lines = D.lines + (size_t)gid * P.ncoded * 2 * D.line_stride;
+            C.line_stride = D.line_stride;
+            C.frame = D.frames + (size_t)f * P.frame_bytes;
+            ff_decode_slice(P, w, D.pkt, C, &r);
+        }
+    }
+    D.result[gid] = r;
+}
+
+extern "C" int ffk_decode_group(const FFDevParams *P, const FFDecDev *D, int nframes, ffk_stream stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nframes <= 0)
+        return FFGPU_EINVAL;
+    dim3 g0(D->max_slices, nframes);
+    k_dec_init_state<<<g0, 256, 0, st>>>(*P, *D, P->ac == FF_AC_GOLOMB);
+    const int total = nframes * D->max_slices;
+    k_decode<<<(total + CODE_THREADS - 1) / CODE_THREADS, CODE_THREADS, 0, st>>>(*P, *D, nframes);
+    if (!launch_ok()) return FFGPU_EXTERNAL;
+    return 2;
+}
+
+/* ---------------- concealment ---------------- */
+__global__ void k_conceal(const FFDevParams P, uint8_t *dst, const uint8_t *src,
+                          int x, int y, int w, int h, int pixshift, int nplanes, int planar_chroma)
+{
+    for (int p = 0; p < nplanes; p++) {
+        const int sh = (planar_chroma && (p == 1 || p == 2)) ? P.hs : 0;
+        const int sv = (planar_chroma && (p == 1 || p == 2)) ? P.vs : 0;
+        const int bpp = P.layout == FF_LAY_PLANAR ? (P.sbits > 8 ? 2 : 1) :
+                        P.layout == FF_LAY_GBRP ? 2 : P.layout == FF_LAY_YA8 ? 2 : P.rgb_pixbytes;
+        const int bw = ff_crshift(w, sh) * bpp, rows = ff_crshift(h, sv);
+        const size_t xo = (size_t)((x >> sh) << pixshift);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < bw * rows; i += gridDim.x * blockDim.x) {
+            const int r = i / bw, c = i - r * bw;
+            const size_t o = P.plane_off[p] + (size_t)((y >> sv) + r) * P.pitch[p] + xo + c;
+            dst[o] = src[o];
+        }
+    }
+}
+
+extern "C" int ffk_conceal_rect(const FFDevParams *P, uint8_t *dst_frame, const uint8_t *src_frame,
+                                int x, int y, int w, int h, int depth_gt8, ffk_stream stream)
+{
+    int nplanes = 0;
+    for (int p = 0; p < FF_MAX_PLANES; p++)
+        if (P->rows[p])
+            nplanes = p + 1;
+    k_conceal<<<64, 256, 0, (cudaStream_t)stream>>>(*P, dst_frame, src_frame, x, y, w, h, depth_gt8,
+                                                    nplanes, P->layout == FF_LAY_PLANAR && P->chroma_planes);
+    if (!launch_ok()) return FFGPU_EXTERNAL;
+    return 1;
+}

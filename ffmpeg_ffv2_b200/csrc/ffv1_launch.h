@@ -1,0 +1,69 @@
+/*
+ * ffv1_launch.h -- host-callable launchers of the CUDA kernels in ffv1_kernels.cu.
+ * Every function enqueues on `stream` and returns the number of kernels it launched
+ * (>= 0) or a negative FFGPU_EXTERNAL on a launch error.
+ */
+#ifndef FFGPU_FFV1_LAUNCH_H
+#define FFGPU_FFV1_LAUNCH_H
+
+#include "ffv1_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *ffk_stream;      /* cudaStream_t */
+
+/* encoder work arrays of one launch group (all device pointers) */
+typedef struct FFEncDev {
+    const FFDevSlice *slices;       /* [nslices]                                        */
+    const int16_t *qt;              /* [FF_MAX_QUANT_TABLES][FF_QT_STRIDE]              */
+    const FFRacTables *tab;         /* transition tables of the slice coders            */
+    const uint8_t *frames;          /* [nframes][frame_bytes]                           */
+    uint32_t *tokens;               /* [nframes][frame_tokens]                          */
+    uint8_t *state;                 /* [nstate_frames][nslices][total_ctx][32 | 8]      */
+    const FFRacPrefix *prefix;      /* [nprefix_sets][nslices]                          */
+    const uint8_t *prefix_bytes;    /* arena addressed by FFRacPrefix.byte_off          */
+    const uint8_t *frame_prefix_set;/* [nframes] which prefix set a frame uses          */
+    const uint8_t *frame_key;       /* [nframes] 1 = reset the adaptive states first    */
+    uint8_t *bs;                    /* [nframes][frame_bs] slice bitstream arenas        */
+    uint32_t *slice_bytes;          /* [nframes][nslices]                               */
+    uint32_t *slice_off;            /* [nframes][nslices] offset inside the frame packet */
+    uint32_t *pkt_size;             /* [nframes]                                        */
+    uint32_t *pkt_off;              /* [nframes + 1] offset inside the packed output     */
+    uint32_t *overflow;             /* [1] sticky flag                                  */
+    uint8_t *pkt;                   /* packed output of the whole group                 */
+    int state_per_frame;            /* 1: state[frame][slice] (intra), 0: state[slice]   */
+} FFEncDev;
+
+int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nframes, ffk_stream stream);
+
+typedef struct FFDecDev {
+    const FFDecSlice *work;         /* [nframes][max_slices]                            */
+    const int *nslices;             /* [nframes] slices present in each packet          */
+    const int16_t *qt;
+    const FFRacTables *tab;
+    const uint8_t *initial;         /* [FF_MAX_QUANT_TABLES][max_ctx][32] or NULL        */
+    const uint8_t *has_initial;     /* [FF_MAX_QUANT_TABLES] (host pointer)             */
+    const uint8_t *pkt;             /* packet arena of the group                        */
+    uint8_t *state;                 /* [nstate_frames][max_slices][total_ctx][32 | 8]   */
+    int32_t *lines;                 /* [nframes*max_slices][ncoded][2][line_stride]     */
+    int line_stride;
+    uint8_t *frames;                /* [nframes][frame_bytes] output pictures           */
+    FFDecResult *result;            /* [nframes][max_slices]                            */
+    int max_slices;
+    int max_ctx;                    /* contexts per set (largest quant table)           */
+    int state_per_frame;
+} FFDecDev;
+
+int ffk_decode_group(const FFDevParams *P, const FFDecDev *D, int nframes, ffk_stream stream);
+
+/* concealment: copy the rectangle of a damaged slice from the previous picture
+ * (ffv1dec.c:940-969); rect in luma samples */
+int ffk_conceal_rect(const FFDevParams *P, uint8_t *dst_frame, const uint8_t *src_frame,
+                     int x, int y, int w, int h, int depth_gt8, ffk_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,815 @@
+/*
+ * ffv1_slice.cuh -- the FFV1 slice pixel path as __host__ __device__ functions.
+ *
+ * The CUDA kernels in ffv1_kernels.cu are thin wrappers that map CUDA threads onto
+ * these functions; tests/emul compiles the very same functions with g++ so the
+ * device logic can be checked against the oracle on a machine without a GPU.
+ * (The emulation build is test infrastructure; the product never runs it.)
+ *
+ * Encoder, two stages:
+ *   A  symbolize   one thread per sample: load (+RCT), neighbourhood, context,
+ *                  median prediction, fold -> 32-bit token (residual:17 | context:15)
+ *                  ffv1enc.c:274-312 encode_plane, ffv1enc_template.c:125-201
+ *                  encode_rgb_frame, ffv1_template.c:23-52 predict/get_context
+ *   B  code        one thread per slice: adaptive range coder / Golomb-Rice coder over
+ *                  the slice's token stream, ffv1enc_template.c:23-123 encode_line,
+ *                  ffv1enc.c:185-262 put_symbol_inline / put_vlc_symbol
+ * Decoder: one thread per slice, ffv1dec.c:119-165 decode_plane,
+ *   ffv1dec_template.c:23-193 decode_line / decode_rgb_frame.
+ */
+#ifndef FFGPU_FFV1_SLICE_CUH
+#define FFGPU_FFV1_SLICE_CUH
+
+#include "ffv1_types.h"
+
+#define FF_TOKEN_CTX_BITS 15
+#define FF_TOKEN_CTX_MASK 0x7FFF
+
+#if !defined(__CUDACC__)
+typedef struct uint2 { uint32_t x, y; } uint2;    /* CPU emulation build only */
+#endif
+
+/* ff_log2_run[41], libavcodec/bitstream.c:39-46: 0,0,0,0,1,1,1,1,2,2,2,2,3,3,3,3,
+ * 4,4,5,5,6,6,7,7,8,9,...,24 -- four entries per step, then two, then one */
+FFGPU_HD int ff_run_log2(int i)
+{
+    return i < 16 ? i >> 2 : (i < 24 ? 4 + ((i - 16) >> 1) : i - 16);
+}
+
+/* a quant table set: int16 [5][256] followed by the "uses 5 inputs" flag */
+#define FF_QT_STRIDE (FF_MAX_CTX_INPUTS * 256 + 8)
+
+FFGPU_HD int ff_min(int a, int b) { return a < b ? a : b; }
+FFGPU_HD int ff_max(int a, int b) { return a > b ? a : b; }
+FFGPU_HD int ff_crshift(int a, int b) { return -((-a) >> b); }
+
+/* mid_pred, mathops.h:98-112 */
+FFGPU_HD int ff_median3(int a, int b, int c)
+{
+    return ff_max(ff_min(a, b), ff_min(ff_max(a, b), c));
+}
+
+/* fold, ffv1.h:151-160: sign-extend from `bits` bits */
+FFGPU_HD int ff_fold(int diff, int bits)
+{
+    const int sh = 32 - bits;
+    return (int)((uint32_t)diff << sh) >> sh;
+}
+
+/* ------------------------------------------------------------------ */
+/* stage A: sample access                                               */
+/* ------------------------------------------------------------------ */
+
+FFGPU_HD int ff_rd16(const uint8_t *p)
+{
+    return p[0] | (p[1] << 8);
+}
+
+/* coded sample of plane k at absolute position (X,Y) of that plane's grid, already wrapped
+ * to the coder's sample type (int16 unless use32).  encode_plane ffv1enc.c:291-305,
+ * encode_rgb_frame ffv1enc_template.c:150-186. */
+FFGPU_HD int ff_coded_sample(const FFDevParams &P, const uint8_t *frame, int k, int X, int Y)
+{
+    if (P.colorspace == 0) {
+        const FFDevPlane cp = P.cp[k];
+        const uint8_t *p = frame + P.plane_off[cp.mem] + (size_t)Y * P.pitch[cp.mem] +
+                           (size_t)X * cp.step + cp.off;
+        int v;
+        if (P.sbits <= 8)
+            v = p[0];
+        else if (P.packed_lsb)
+            v = ff_rd16(p);
+        else
+            v = ff_rd16(p) >> (16 - P.sbits);
+        return (int16_t)v;
+    } else {
+        int r, g, b, a = 0, v;
+        if (P.layout == FF_LAY_BGR32) {
+            const uint8_t *p = frame + P.plane_off[0] + (size_t)Y * P.pitch[0] + (size_t)X * 4;
+            b = p[0]; g = p[1]; r = p[2]; a = p[3];
+        } else if (P.layout == FF_LAY_RGB48) {
+            const uint8_t *p = frame + P.plane_off[0] + (size_t)Y * P.pitch[0] +
+                               (size_t)X * P.rgb_pixbytes;
+            r = ff_rd16(p); g = ff_rd16(p + 2); b = ff_rd16(p + 4);
+            if (P.transparency)
+                a = ff_rd16(p + 6);
+        } else {
+            const int p0 = ff_rd16(frame + P.plane_off[0] + (size_t)Y * P.pitch[0] + (size_t)X * 2);
+            const int p1 = ff_rd16(frame + P.plane_off[1] + (size_t)Y * P.pitch[1] + (size_t)X * 2);
+            r = ff_rd16(frame + P.plane_off[2] + (size_t)Y * P.pitch[2] + (size_t)X * 2);
+            if (P.use32 || P.transparency) {
+                g = p0; b = p1;                 /* ffv1enc_template.c:163-168 */
+            } else {
+                b = p0; g = p1;                 /* ffv1enc_template.c:169-173 */
+            }
+            if (P.transparency)
+                a = ff_rd16(frame + P.plane_off[3] + (size_t)Y * P.pitch[3] + (size_t)X * 2);
+        }
+        if (k == 3) {
+            v = a;
+        } else {
+            b -= g;
+            r -= g;
+            g += (b + r) >> 2;                  /* slice_rct_by_coef = slice_rct_ry_coef = 1 */
+            v = k == 0 ? g : (k == 1 ? b : r) + (1 << P.sbits);
+        }
+        return P.use32 ? v : (int)(int16_t)v;
+    }
+}
+
+/* The reference's rotating line buffers (ffv1enc.c:284-289), unrolled: for sample (x,y)
+ * of a w-wide plane whose top-left is (X0,Y0),
+ *   T  = S(x,y-1)                        0 above the slice
+ *   L  = S(x-1,y)    ; x==0   -> T
+ *   LT = S(x-1,y-1)  ; x==0   -> S(0,y-2)
+ *   RT = S(x+1,y-1)  ; x==w-1 -> T
+ *   LL = S(x-2,y)    ; x==1   -> S(0,y-1) ; x==0 -> 0
+ *   TT = S(x,y-2)
+ * Neighbours never cross the slice border.  Returns the token. */
+FFGPU_HD uint32_t ff_symbolize_sample(const FFDevParams &P, const uint8_t *frame,
+                                      const int16_t *qt, int k, int X0, int Y0, int w,
+                                      int x, int y, int ctx_base)
+{
+#define S_(xx, yy) ((yy) < 0 ? 0 : ff_coded_sample(P, frame, k, X0 + (xx), Y0 + (yy)))
+    const int cur = S_(x, y);
+    const int T   = S_(x, y - 1);
+    const int L   = x ? S_(x - 1, y) : T;
+    const int LT  = x ? S_(x - 1, y - 1) : S_(0, y - 2);
+    const int RT  = (x + 1 < w) ? S_(x + 1, y - 1) : T;
+    int ctx = qt[(L - LT) & 0xFF] + qt[256 + ((LT - T) & 0xFF)] + qt[512 + ((T - RT) & 0xFF)];
+    int diff;
+    if (qt[FF_MAX_CTX_INPUTS * 256]) {      /* quant_table[3][127] || quant_table[4][127] */
+        const int LL = x >= 2 ? S_(x - 2, y) : (x == 1 ? S_(0, y - 1) : 0);
+        const int TT = S_(x, y - 2);
+        ctx += qt[768 + ((LL - L) & 0xFF)] + qt[1024 + ((TT - T) & 0xFF)];
+    }
+#undef S_
+    diff = cur - ff_median3(L, L + T - LT, T);
+    if (ctx < 0) {
+        ctx = -ctx;
+        diff = -diff;
+    }
+    diff = ff_fold(diff, P.cbits);
+    return ((uint32_t)diff << FF_TOKEN_CTX_BITS) | (uint32_t)(ctx_base + ctx);
+}
+
+/* token index -> (plane, x, y) and the token itself; tokens are laid out in CODING order:
+ * YCbCr plane after plane, RGB line-interleaved G,B,R[,A] (ffv1enc_template.c:188-198) */
+FFGPU_HD uint32_t ff_symbolize_index(const FFDevParams &P, const FFDevSlice &sl,
+                                     const uint8_t *frame, const int16_t *qt_all, uint32_t idx)
+{
+    int k, x, y, w;
+    if (P.colorspace == 0) {
+        uint32_t base = 0;
+        for (k = 0; k < P.ncoded - 1; k++) {
+            const uint32_t n = (uint32_t)sl.seg_w[k] * sl.seg_lines[k];
+            if (idx < base + n)
+                break;
+            base += n;
+        }
+        w = sl.seg_w[k];
+        y = (int)((idx - base) / (uint32_t)w);
+        x = (int)((idx - base) - (uint32_t)y * w);
+    } else {
+        const uint32_t line = idx / (uint32_t)sl.w;
+        w = sl.w;
+        x = (int)(idx - line * (uint32_t)w);
+        y = (int)(line / (uint32_t)P.ncoded);
+        k = (int)(line - (uint32_t)y * P.ncoded);
+    }
+    {
+        const FFDevPlane cp = P.cp[k];
+        const int16_t *qt = qt_all + (size_t)P.set_qidx[cp.set] * FF_QT_STRIDE;
+        return ff_symbolize_sample(P, frame, qt, k, sl.x >> cp.hs, sl.y >> cp.vs, w, x, y,
+                                   P.set_base[cp.set]);
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* stage B: range coder over the token stream                           */
+/* ------------------------------------------------------------------ */
+
+FFGPU_HD void ff_enc_resume(FFRacEnc *c, const FFRacPrefix &pre, const uint8_t *pre_bytes,
+                            uint8_t *out, uint32_t cap)
+{
+    uint32_t i;
+    ffrac_enc_init(c, out, cap);
+    for (i = 0; i < pre.nbytes && i < cap; i++)
+        out[i] = pre_bytes[pre.byte_off + i];
+    c->pos = pre.nbytes;
+    c->low = pre.low;
+    c->range = pre.range;
+    c->pending = pre.pending;
+    c->run = pre.run;
+}
+
+/* returns the slice's byte count; *overflow != 0 if the arena was too small */
+FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *tokens,
+                                        uint8_t *state, const FFRacTables *tab,
+                                        const FFRacPrefix &pre, const uint8_t *pre_bytes,
+                                        uint8_t *out, uint32_t *overflow)
+{
+    FFRacEnc c;
+    uint32_t i, n;
+    ff_enc_resume(&c, pre, pre_bytes, out, sl.bs_cap);
+    for (i = 0; i < sl.ntok; i++) {
+        const uint32_t tok = tokens[i];
+        const int diff = (int32_t)tok >> FF_TOKEN_CTX_BITS;
+        uint8_t *st = state + (size_t)(tok & FF_TOKEN_CTX_MASK) * FF_CONTEXT_SIZE;
+        ffrac_put_symbol(&c, tab, st, diff, 1);
+    }
+    n = ffrac_enc_finish(&c, tab, 1);           /* ffv1enc.c:1242 */
+    *overflow = c.overflow;
+    return n;
+}
+
+/* ------------------------------------------------------------------ */
+/* stage B: Golomb-Rice coder                                            */
+/* ------------------------------------------------------------------ */
+
+/* VlcState (ffv1.h:61-66) packed in 8 bytes: lo = drift | error_sum << 16,
+ * hi = (uint8)bias | count << 8 */
+typedef struct FFVlc {
+    int drift;
+    int error_sum;
+    int bias;
+    int count;
+} FFVlc;
+
+#define FF_VLC_INIT_LO (4u << 16)
+#define FF_VLC_INIT_HI (1u << 8)
+
+FFGPU_HD FFVlc ff_vlc_load(const uint2 *p)
+{
+    const uint2 v = *p;
+    FFVlc s;
+    s.drift = (int16_t)(v.x & 0xFFFF);
+    s.error_sum = (int)(v.x >> 16);
+    s.bias = (int8_t)(v.y & 0xFF);
+    s.count = (int)((v.y >> 8) & 0xFF);
+    return s;
+}
+
+FFGPU_HD void ff_vlc_store(uint2 *p, const FFVlc &s)
+{
+    uint2 v;
+    v.x = ((uint32_t)s.drift & 0xFFFFu) | ((uint32_t)(s.error_sum & 0xFFFF) << 16);
+    v.y = ((uint32_t)s.bias & 0xFFu) | ((uint32_t)s.count << 8);
+    *p = v;
+}
+
+/* update_vlc_state, ffv1.h:162-188 */
+FFGPU_HD void ff_vlc_adapt(FFVlc *s, int v)
+{
+    int drift = s->drift, count = s->count;
+    s->error_sum = (s->error_sum + (v < 0 ? -v : v)) & 0xFFFF;
+    drift += v;
+    if (count == 128) {
+        count >>= 1;
+        drift >>= 1;
+        s->error_sum >>= 1;
+    }
+    count++;
+    if (drift <= -count) {
+        s->bias = ff_max(s->bias - 1, -128);
+        drift = ff_max(drift + count, -count + 1);
+    } else if (drift > 0) {
+        s->bias = ff_min(s->bias + 1, 127);
+        drift = ff_min(drift - count, 0);
+    }
+    s->drift = (int16_t)drift;
+    s->count = count;
+}
+
+FFGPU_HD int ff_vlc_k(const FFVlc &s)
+{
+    int i = s.count, k = 0;
+    while (i < s.error_sum) {
+        k++;
+        i += i;
+    }
+    return k;
+}
+
+/* MSB-first bit writer (put_bits.h) with a 64-bit accumulator */
+typedef struct FFBitW {
+    uint8_t *buf;
+    uint32_t pos, cap;     /* bytes written / capacity */
+    uint64_t acc;          /* pending bits, right aligned */
+    int      nacc;
+    uint32_t overflow;
+} FFBitW;
+
+FFGPU_HD void ff_bw_put(FFBitW *b, int n, uint32_t v)
+{
+    b->acc = (b->acc << n) | (uint64_t)v;
+    b->nacc += n;
+    while (b->nacc >= 8) {
+        b->nacc -= 8;
+        if (b->pos < b->cap)
+            b->buf[b->pos] = (uint8_t)(b->acc >> b->nacc);
+        else
+            b->overflow = 1;
+        b->pos++;
+    }
+}
+
+/* flush_put_bits: zero padding to a byte boundary */
+FFGPU_HD void ff_bw_flush(FFBitW *b)
+{
+    if (b->nacc > 0)
+        ff_bw_put(b, 8 - b->nacc, 0);
+}
+
+/* put_vlc_symbol ffv1enc.c:240-262 + set_sr_golomb / set_ur_golomb golomb.h:676-731 */
+FFGPU_HD void ff_vlc_put(FFBitW *b, uint2 *sp, int v, int bits)
+{
+    FFVlc s = ff_vlc_load(sp);
+    int k, code, u, e;
+    v = ff_fold(v - s.bias, bits);
+    k = ff_vlc_k(s);
+    code = v ^ ((2 * s.drift + s.count) >> 31);
+    u = -2 * code - 1;
+    u ^= u >> 31;
+    e = u >> k;
+    if (e < 12)
+        ff_bw_put(b, e + k + 1, (1u << k) + ((uint32_t)u & ((1u << k) - 1)));
+    else
+        ff_bw_put(b, 12 + bits, (uint32_t)(u - 11));
+    ff_vlc_adapt(&s, v);
+    ff_vlc_store(sp, s);
+}
+
+/* encode_line's Golomb branch incl. run mode, ffv1enc_template.c:58-119, over all lines */
+FFGPU_HD uint32_t ff_encode_slice_golomb(const FFDevParams &P, const FFDevSlice &sl,
+                                         const uint32_t *tokens, uint2 *vstate,
+                                         const FFRacPrefix &pre, const uint8_t *pre_bytes,
+                                         uint8_t *out, uint32_t *overflow)
+{
+    FFBitW bw;
+    uint32_t i, t = 0;
+    int seg;
+    for (i = 0; i < pre.nbytes && i < sl.bs_cap; i++)
+        out[i] = pre_bytes[pre.byte_off + i];
+    bw.buf = out;
+    bw.pos = pre.golomb_start;
+    bw.cap = sl.bs_cap;
+    bw.acc = 0;
+    bw.nacc = 0;
+    bw.overflow = 0;
+    for (seg = 0; seg < sl.nseg; seg++) {
+        const int w = sl.seg_w[seg];
+        int run_index = 0, line;
+        for (line = 0; line < sl.seg_lines[seg]; line++) {
+            /* context 0 of the line's plane-context set */
+            const int set = P.colorspace == 0 ? P.cp[seg].set : P.cp[line % P.ncoded].set;
+            const uint32_t ctx0 = (uint32_t)P.set_base[set];
+            int run_count = 0, run_mode = 0, x;
+            for (x = 0; x < w; x++) {
+                const uint32_t tok = tokens[t++];
+                const uint32_t ctx = tok & FF_TOKEN_CTX_MASK;
+                int diff = (int32_t)tok >> FF_TOKEN_CTX_BITS;
+                if (ctx == ctx0)
+                    run_mode = 1;
+                if (run_mode) {
+                    if (diff) {
+                        while (run_count >= 1 << ff_run_log2(run_index)) {
+                            run_count -= 1 << ff_run_log2(run_index);
+                            run_index++;
+                            ff_bw_put(&bw, 1, 1);
+                        }
+                        ff_bw_put(&bw, 1 + ff_run_log2(run_index), (uint32_t)run_count);
+                        if (run_index)
+                            run_index--;
+                        run_count = 0;
+                        run_mode = 0;
+                        if (diff > 0)
+                            diff--;
+                    } else {
+                        run_count++;
+                    }
+                }
+                if (!run_mode)
+                    ff_vlc_put(&bw, vstate + ctx, diff, P.cbits);
+            }
+            if (run_mode) {
+                while (run_count >= 1 << ff_run_log2(run_index)) {
+                    run_count -= 1 << ff_run_log2(run_index);
+                    run_index++;
+                    ff_bw_put(&bw, 1, 1);
+                }
+                if (run_count)
+                    ff_bw_put(&bw, 1, 1);
+            }
+        }
+    }
+    ff_bw_flush(&bw);                           /* ffv1enc.c:1244-1245 */
+    *overflow = bw.overflow;
+    return bw.pos;
+}
+
+/* ------------------------------------------------------------------ */
+/* packet assembly                                                      */
+/* ------------------------------------------------------------------ */
+
+/* bytes slice i occupies in the packet: payload, 24-bit size, optional 0x00 + CRC
+ * (ffv1enc.c:1248-1261) */
+FFGPU_HD uint32_t ff_slice_packed_size(const FFDevParams &P, int i, uint32_t payload)
+{
+    uint32_t n = payload;
+    if (i > 0 || P.version > 2)
+        n += 3;
+    if (P.ec)
+        n += 5;
+    return n;
+}
+
+/* CRC-32 IEEE (0x04C11DB7) MSB-first, init 0, no final xor: libavutil/crc.c:336
+ * AV_CRC_32_IEEE.  The register is kept in textbook form; av_crc()'s byte-swapped value
+ * stored with AV_WL32 (ffv1enc.c:1258) puts exactly these four bytes, MSB first. */
+FFGPU_HD uint32_t ff_crc_table_entry(int i)
+{
+    uint32_t c = (uint32_t)i << 24;
+    int k;
+    for (k = 0; k < 8; k++)
+        c = (c << 1) ^ ((c >> 31) ? 0x04C11DB7u : 0u);
+    return c;
+}
+
+/* copy slice i's payload to its place in the packet and append the trailer:
+ * 24-bit big-endian size, then (ec) a zero error-status byte and the CRC over
+ * payload+size+status, ffv1enc.c:1248-1261.  One thread per slice. */
+FFGPU_HD void ff_pack_slice(const FFDevParams &P, int i, const uint8_t *src, uint32_t payload,
+                            uint8_t *dst, const uint32_t *crc_tab)
+{
+    uint32_t n, j, r = 0;
+    for (n = 0; n < payload; n++)
+        dst[n] = src[n];
+    if (i > 0 || P.version > 2) {
+        dst[n++] = (uint8_t)(payload >> 16);
+        dst[n++] = (uint8_t)(payload >> 8);
+        dst[n++] = (uint8_t)payload;
+    }
+    if (P.ec) {
+        dst[n++] = 0;
+        for (j = 0; j < n; j++)
+            r = (r << 8) ^ crc_tab[(r >> 24) ^ dst[j]];
+        dst[n++] = (uint8_t)(r >> 24);
+        dst[n++] = (uint8_t)(r >> 16);
+        dst[n++] = (uint8_t)(r >> 8);
+        dst[n++] = (uint8_t)r;
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* decoder                                                               */
+/* ------------------------------------------------------------------ */
+
+/* MSB-first bit reader (get_bits.h, checked reader) */
+typedef struct FFBitR {
+    const uint8_t *buf;
+    int64_t pos, size_bits;
+} FFBitR;
+
+FFGPU_HD uint32_t ff_br_peek32(const FFBitR *r)
+{
+    const uint8_t *p = r->buf + (r->pos >> 3);
+    const uint64_t w = ((uint64_t)p[0] << 32) | ((uint64_t)p[1] << 24) | ((uint64_t)p[2] << 16) |
+                       ((uint64_t)p[3] << 8) | (uint64_t)p[4];
+    return (uint32_t)(w >> (8 - (int)(r->pos & 7)));
+}
+
+FFGPU_HD void ff_br_skip(FFBitR *r, int n)
+{
+    r->pos += n;
+    if (r->pos > r->size_bits + 8)
+        r->pos = r->size_bits + 8;
+}
+
+FFGPU_HD uint32_t ff_br_get(FFBitR *r, int n)
+{
+    uint32_t v;
+    if (!n)
+        return 0;
+    v = ff_br_peek32(r) >> (32 - n);
+    ff_br_skip(r, n);
+    return v;
+}
+
+/* get_vlc_symbol ffv1dec.c:71-94 + get_sr_golomb / get_ur_golomb golomb.h:373-413,529-534 */
+FFGPU_HD int ff_vlc_get(FFBitR *r, uint2 *sp, int bits)
+{
+    FFVlc s = ff_vlc_load(sp);
+    const int k = ff_vlc_k(s);
+    uint32_t buf = ff_br_peek32(r);
+    const int log = ffrac_ilog2(buf);
+    uint32_t u;
+    int v, ret;
+    if (log > 31 - 12) {
+        buf >>= log - k;
+        buf += (uint32_t)(30 - log) << k;
+        ff_br_skip(r, 32 + k - log);
+        u = buf;
+    } else {
+        ff_br_skip(r, 12);
+        u = ff_br_get(r, bits) + 11;
+    }
+    v = (int)(u >> 1) ^ -(int)(u & 1);
+    v ^= (2 * s.drift + s.count) >> 31;
+    ret = ff_fold(v + s.bias, bits);
+    ff_vlc_adapt(&s, v);
+    ff_vlc_store(sp, s);
+    return ret;
+}
+
+/* everything a slice decode needs besides the stream parameters */
+typedef struct FFDecCtx {
+    const int16_t *qt_all;      /* quant table sets, FF_QT_STRIDE apart               */
+    const FFRacTables *tab;
+    uint8_t *rstate;            /* range: [total_ctx][32]                             */
+    uint2   *vstate;            /* golomb: [total_ctx]                                */
+    int32_t *lines;             /* [ncoded][2][line_stride] scratch                   */
+    int      line_stride;
+    uint8_t *frame;             /* output picture                                     */
+} FFDecCtx;
+
+FFGPU_HD int ff_wrap_sample(const FFDevParams &P, int v)
+{
+    return P.use32 ? v : (int)(int16_t)v;
+}
+
+/* decode_line (range coder branch), ffv1dec_template.c:23-126.  prev/cur are the two line
+ * buffers of the plane: prev holds line y-1, cur still holds line y-2 and is overwritten. */
+FFGPU_HD int ff_decode_line_range(const FFDevParams &P, FFRacDec *c, const FFDecCtx &D,
+                                  const int16_t *qt, uint8_t *state, int w,
+                                  const int32_t *prev, int32_t *cur)
+{
+    const int five = qt[FF_MAX_CTX_INPUTS * 256];
+    const uint32_t mask = (1u << P.cbits) - 1;
+    int x;
+    int T = prev[0], LT = cur[0], L = prev[0], LL = 0;
+    if (c->overread > 2)                          /* is_input_end, ffv1dec.c:96-107 */
+        return -1;
+    for (x = 0; x < w; x++) {
+        const int RT = prev[ff_min(x + 1, w - 1)];
+        int ctx, sign = 0, diff, v;
+        if (!(x & 1023) && c->overread > 2)
+            return -1;
+        ctx = qt[(L - LT) & 0xFF] + qt[256 + ((LT - T) & 0xFF)] + qt[512 + ((T - RT) & 0xFF)];
+        if (five) {
+            const int TT = cur[x];
+            ctx += qt[768 + ((LL - L) & 0xFF)] + qt[1024 + ((TT - T) & 0xFF)];
+        }
+        if (ctx < 0) {
+            ctx = -ctx;
+            sign = 1;
+        }
+        diff = ffrac_get_symbol(c, D.tab, state + (size_t)ctx * FF_CONTEXT_SIZE, 1);
+        if (sign)
+            diff = -diff;
+        v = ff_wrap_sample(P, (int)(((uint32_t)ff_median3(L, L + T - LT, T) + (uint32_t)diff) & mask));
+        cur[x] = v;
+        LL = L;
+        L = v;
+        LT = T;
+        T = RT;
+    }
+    return 0;
+}
+
+/* decode_line (Golomb branch incl. run mode), ffv1dec_template.c:70-113 */
+FFGPU_HD int ff_decode_line_golomb(const FFDevParams &P, FFBitR *br, const FFDecCtx &D,
+                                   const int16_t *qt, uint2 *vstate, int w,
+                                   const int32_t *prev, int32_t *cur, int *run_index_io)
+{
+    const int five = qt[FF_MAX_CTX_INPUTS * 256];
+    const uint32_t mask = (1u << P.cbits) - 1;
+    int run_index = *run_index_io, run_count = 0, run_mode = 0;
+    int x;
+    int T = prev[0], LT = cur[0], L = prev[0], LL = 0;
+    if (br->size_bits - br->pos < 1)              /* is_input_end */
+        return -1;
+    for (x = 0; x < w; x++) {
+        int RT = prev[ff_min(x + 1, w - 1)];
+        int ctx, sign = 0, diff, v;
+        if (!(x & 1023) && br->size_bits - br->pos < 1)
+            return -1;
+        ctx = qt[(L - LT) & 0xFF] + qt[256 + ((LT - T) & 0xFF)] + qt[512 + ((T - RT) & 0xFF)];
+        if (five) {
+            const int TT = cur[x];
+            ctx += qt[768 + ((LL - L) & 0xFF)] + qt[1024 + ((TT - T) & 0xFF)];
+        }
+        if (ctx < 0) {
+            ctx = -ctx;
+            sign = 1;
+        }
+        if (ctx == 0 && run_mode == 0)
+            run_mode = 1;
+        if (run_mode) {
+            if (run_count == 0 && run_mode == 1) {
+                if (ff_br_get(br, 1)) {
+                    run_count = 1 << ff_run_log2(run_index);
+                    if (x + run_count <= w)
+                        run_index++;
+                } else {
+                    run_count = ff_run_log2(run_index) ? (int)ff_br_get(br, ff_run_log2(run_index)) : 0;
+                    if (run_index)
+                        run_index--;
+                    run_mode = 2;
+                }
+            }
+            /* zero residuals: each sample equals its prediction */
+            while (run_count > 1 && w - x > 1) {
+                v = ff_wrap_sample(P, ff_median3(L, L + T - LT, T));
+                cur[x] = v;
+                LL = L;
+                L = v;
+                LT = T;
+                T = RT;
+                x++;
+                RT = prev[ff_min(x + 1, w - 1)];
+                run_count--;
+            }
+            run_count--;
+            if (run_count < 0) {
+                run_mode = 0;
+                run_count = 0;
+                diff = ff_vlc_get(br, vstate + ctx, P.cbits);
+                if (diff >= 0)
+                    diff++;
+            } else {
+                diff = 0;
+            }
+        } else {
+            diff = ff_vlc_get(br, vstate + ctx, P.cbits);
+        }
+        if (sign)
+            diff = -diff;
+        v = ff_wrap_sample(P, (int)(((uint32_t)ff_median3(L, L + T - LT, T) + (uint32_t)diff) & mask));
+        cur[x] = v;
+        LL = L;
+        L = v;
+        LT = T;
+        T = RT;
+    }
+    *run_index_io = run_index;
+    return 0;
+}
+
+/* decode_plane's store, ffv1dec.c:142-161 */
+FFGPU_HD void ff_store_line_ycc(const FFDevParams &P, uint8_t *frame, int k, int X0, int Y,
+                                int w, const int32_t *line)
+{
+    const FFDevPlane cp = P.cp[k];
+    uint8_t *p = frame + P.plane_off[cp.mem] + (size_t)Y * P.pitch[cp.mem] + (size_t)X0 * cp.step + cp.off;
+    int x;
+    for (x = 0; x < w; x++) {
+        const int v = line[x];
+        if (P.sbits <= 8) {
+            p[(size_t)x * cp.step] = (uint8_t)v;
+        } else {
+            uint32_t o;
+            if (P.packed_lsb)
+                o = (uint32_t)v & 0xFFFF;
+            else
+                o = (uint32_t)((v << (16 - P.sbits)) | ((v & 0xFFFF) >> (2 * P.sbits - 16))) & 0xFFFF;
+            p[2 * x] = (uint8_t)o;
+            p[2 * x + 1] = (uint8_t)(o >> 8);
+        }
+    }
+}
+
+/* decode_rgb_frame's inverse RCT + store, ffv1dec_template.c:160-190 */
+FFGPU_HD void ff_store_line_rgb(const FFDevParams &P, uint8_t *frame, int X0, int Y, int w,
+                                const int32_t *lg, const int32_t *lb, const int32_t *lr,
+                                const int32_t *la)
+{
+    const int offset = 1 << P.sbits;
+    int x;
+    for (x = 0; x < w; x++) {
+        int g = lg[x], b = lb[x], r = lr[x];
+        const int a = la ? la[x] : 0;
+        b -= offset;
+        r -= offset;
+        g -= (b + r) >> 2;
+        b += g;
+        r += g;
+        if (P.layout == FF_LAY_BGR32) {
+            uint8_t *p = frame + P.plane_off[0] + (size_t)Y * P.pitch[0] + (size_t)(X0 + x) * 4;
+            const uint32_t v = (uint32_t)b + ((uint32_t)g << 8) + ((uint32_t)r << 16) + ((uint32_t)a << 24);
+            p[0] = (uint8_t)v;
+            p[1] = (uint8_t)(v >> 8);
+            p[2] = (uint8_t)(v >> 16);
+            p[3] = (uint8_t)(v >> 24);
+        } else {
+            int v0, v1;
+            uint8_t *p0 = frame + P.plane_off[0] + (size_t)Y * P.pitch[0] + (size_t)(X0 + x) * 2;
+            uint8_t *p1 = frame + P.plane_off[1] + (size_t)Y * P.pitch[1] + (size_t)(X0 + x) * 2;
+            uint8_t *p2 = frame + P.plane_off[2] + (size_t)Y * P.pitch[2] + (size_t)(X0 + x) * 2;
+            if (P.use32 || P.transparency) {
+                v0 = g; v1 = b;
+            } else {
+                v0 = b; v1 = g;
+            }
+            p0[0] = (uint8_t)v0; p0[1] = (uint8_t)(v0 >> 8);
+            p1[0] = (uint8_t)v1; p1[1] = (uint8_t)(v1 >> 8);
+            p2[0] = (uint8_t)r;  p2[1] = (uint8_t)(r >> 8);
+            if (P.transparency) {
+                uint8_t *p3 = frame + P.plane_off[3] + (size_t)Y * P.pitch[3] + (size_t)(X0 + x) * 2;
+                p3[0] = (uint8_t)a; p3[1] = (uint8_t)(a >> 8);
+            }
+        }
+    }
+}
+
+/* decode_slice after the header, ffv1dec.c:304-359 */
+FFGPU_HD void ff_decode_slice(const FFDevParams &P, const FFDecSlice &d, const uint8_t *pkt,
+                              const FFDecCtx &D, FFDecResult *res)
+{
+    const uint8_t *base = pkt + d.pkt_off;
+    FFRacDec c;
+    FFBitR br;
+    int k, y, x, err = 0;
+    const int golomb = P.ac == FF_AC_GOLOMB;
+
+    c.buf = base;
+    c.low = d.low;
+    c.range = d.range;
+    c.pos = d.pos;
+    c.end = d.size;
+    c.overread = d.overread;
+    br.buf = base + d.golomb_start;
+    br.size_bits = (int64_t)(d.size - d.golomb_start) * 8;
+    br.pos = 0;
+
+    /* zero the line buffers: memset of sample_buffer, ffv1dec.c:131 / ffv1dec_template.c:146 */
+    for (k = 0; k < P.ncoded; k++)
+        for (x = 0; x < 2 * D.line_stride; x++)
+            D.lines[(size_t)k * 2 * D.line_stride + x] = 0;
+
+    if (P.colorspace == 0) {
+        for (k = 0; k < P.ncoded; k++) {
+            const FFDevPlane cp = P.cp[k];
+            const int w = ff_crshift(d.w, cp.hs), h = ff_crshift(d.h, cp.vs);
+            const int16_t *qt = D.qt_all + (size_t)d.qidx[cp.set] * FF_QT_STRIDE;
+            const size_t sbase = (size_t)P.set_base[cp.set];
+            int32_t *l0 = D.lines + (size_t)k * 2 * D.line_stride;
+            int32_t *l1 = l0 + D.line_stride;
+            int run_index = 0;
+            for (y = 0; y < h; y++) {
+                int32_t *cur = (y & 1) ? l1 : l0;
+                const int32_t *prev = (y & 1) ? l0 : l1;
+                int r;
+                if (golomb)
+                    r = ff_decode_line_golomb(P, &br, D, qt, D.vstate + sbase, w, prev, cur, &run_index);
+                else
+                    r = ff_decode_line_range(P, &c, D, qt, D.rstate + sbase * FF_CONTEXT_SIZE, w, prev, cur);
+                if (r < 0) {
+                    err = 1;
+                    break;                       /* decode_plane returns, next plane still runs */
+                }
+                ff_store_line_ycc(P, D.frame, k, d.x >> cp.hs, (d.y >> cp.vs) + y, w, cur);
+            }
+        }
+    } else {
+        int run_index = 0;
+        for (y = 0; y < d.h && !err; y++) {
+            for (k = 0; k < P.ncoded; k++) {
+                const FFDevPlane cp = P.cp[k];
+                const int16_t *qt = D.qt_all + (size_t)d.qidx[cp.set] * FF_QT_STRIDE;
+                const size_t sbase = (size_t)P.set_base[cp.set];
+                int32_t *l0 = D.lines + (size_t)k * 2 * D.line_stride;
+                int32_t *l1 = l0 + D.line_stride;
+                int32_t *cur = (y & 1) ? l1 : l0;
+                const int32_t *prev = (y & 1) ? l0 : l1;
+                int r;
+                if (golomb)
+                    r = ff_decode_line_golomb(P, &br, D, qt, D.vstate + sbase, d.w, prev, cur, &run_index);
+                else
+                    r = ff_decode_line_range(P, &c, D, qt, D.rstate + sbase * FF_CONTEXT_SIZE, d.w, prev, cur);
+                if (r < 0) {
+                    err = 1;
+                    break;
+                }
+            }
+            if (!err) {
+                const int o = (y & 1) ? D.line_stride : 0;
+                ff_store_line_rgb(P, D.frame, d.x, d.y + y, d.w,
+                                  D.lines + o, D.lines + 2 * D.line_stride + o,
+                                  D.lines + 4 * D.line_stride + o,
+                                  P.ncoded > 3 ? D.lines + 6 * D.line_stride + o : (const int32_t *)0);
+            }
+        }
+    }
+    /* end-of-slice check, ffv1dec.c:351-359 */
+    if (!golomb && P.version > 2) {
+        uint8_t term = 129;
+        ffrac_get(&c, D.tab, &term);
+    }
+    res->end_pos = c.pos;
+    res->overread = c.overread;
+    res->error = err;
+    res->pad = 0;
+}
+
+#endif /* FFGPU_FFV1_SLICE_CUH */

@@ -1,0 +1,258 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (libffgpu.so via
+ffmpeg_ffv2_b200), against the oracle on the same seeded inputs -- bit-exact packets for
+the encoder, identical pictures for the decoder -- plus the FATE-chained golden packets
+and size-independent round-trip properties at the BASELINE.json sizes."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cpucodec as cc
+import synth
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def gpu():
+    import ffmpeg_ffv2_b200 as F
+    return F
+
+
+def md5(b):
+    return hashlib.md5(b).hexdigest()
+
+
+FORMATS_SMALL = [
+    "yuv420p", "yuv444p", "yuv422p", "yuv410p", "gray", "ya8", "yuva420p",
+    "yuv420p10le", "yuv422p10le", "yuv444p16le", "yuv420p16le", "gray16le", "gray10le",
+    "yuva444p10le", "bgr0", "bgra", "gbrp10le", "gbrp16le", "gbrap12le", "rgb48le", "rgba64le",
+]
+OPTIONS = [
+    dict(),
+    dict(slices=4),
+    dict(slices=9, coder=2),
+    dict(slices=4, coder=-2, context=1),
+    dict(level=3, coder=0, context=1),
+    dict(level=1, coder=1),
+    dict(level=3, slicecrc=0, gop_size=1, slices=12),
+    dict(level=3, slices=30, context=1, gop_size=1),
+]
+
+
+@pytest.mark.parametrize("fmt", FORMATS_SMALL)
+def test_encoder_packets_match_oracle(fmt):
+    F = gpu()
+    w, h = 97, 61
+    for kw in OPTIONS:
+        try:
+            ref = cc.Encoder("oracle", w, h, fmt, **kw)
+        except cc.CodecError as e:
+            with pytest.raises(F.FFGpuError) as ei:
+                F.FFV1Encoder(w, h, fmt, **kw)
+            assert ei.value.code == e.code
+            continue
+        enc = F.FFV1Encoder(w, h, fmt, **kw)
+        assert enc.info == ref.info and enc.extradata == ref.extradata
+        for kind in ("smooth", "noise", "extremes", "testsrc2"):
+            e2 = F.FFV1Encoder(w, h, fmt, **kw)
+            r2 = cc.Encoder("oracle", w, h, fmt, **kw)
+            for fr in range(3):
+                planes = synth.GENERATORS[kind](fmt, w, h, fr)
+                assert e2.encode(planes) == r2.encode(planes), (fmt, kw, kind, fr)
+            e2.close()
+        enc.close()
+
+
+@pytest.mark.parametrize("fmt", FORMATS_SMALL)
+def test_decoder_pictures_match_oracle(fmt):
+    F = gpu()
+    w, h = 97, 61
+    for kw in OPTIONS:
+        try:
+            enc = cc.Encoder("oracle", w, h, fmt, **kw)
+        except cc.CodecError:
+            continue
+        for kind in ("smooth", "noise", "testsrc2"):
+            enc = cc.Encoder("oracle", w, h, fmt, **kw)
+            ref = cc.Decoder("oracle", w, h, enc.extradata)
+            dec = F.FFV1Decoder(w, h, enc.extradata)
+            for fr in range(3):
+                pkt = enc.encode(synth.GENERATORS[kind](fmt, w, h, fr))
+                want = ref.decode(pkt)
+                got = dec.decode(pkt, fmt_hint=ref.pix_fmt)
+                assert dec.pix_fmt == ref.pix_fmt
+                for a, b in zip(want, got):
+                    assert np.array_equal(a, b), (fmt, kw, kind, fr)
+            dec.close()
+
+
+def test_fate_golden_packets():
+    """the reference's own FATE vectors (tests/golden/make_fate_golden.py)"""
+    F = gpu()
+    full = json.load(open(os.path.join(HERE, "golden", "fate_full.json")))
+    inputs = np.load(os.path.join(HERE, "golden", "fate_inputs.npz"))
+    for test in sorted(inputs.files):
+        g = full[test]
+        w, h, fmt = g["width"], g["height"], g["pix_fmt"]
+        kw = dict(g["options"])
+        if "strict" in kw:
+            kw["strict"] = kw.pop("strict")
+        enc = F.FFV1Encoder(w, h, fmt, **kw)
+        assert enc.extradata.hex() == g["extradata"]
+        dec = F.FFV1Decoder(w, h, enc.extradata)
+        for i, flat in enumerate(inputs[test]):
+            planes, off = [], 0
+            for bw, rows in cc.plane_geometry(fmt, w, h):
+                planes.append(np.ascontiguousarray(flat[off:off + bw * rows].reshape(rows, bw)))
+                off += bw * rows
+            pkt = enc.encode(planes)
+            assert md5(pkt) == g["packet_md5"][i], (test, i)
+            out = dec.decode(pkt, fmt_hint="gbrp16le" if fmt == "rgb48le" else fmt)
+            if fmt == "rgb48le":
+                px = planes[0].view("<u2").reshape(h, w, 3)
+                want = [px[:, :, 1], px[:, :, 2], px[:, :, 0]]
+                got = [o.view("<u2") for o in out]
+            elif fmt == "bgr0":
+                want = [planes[0].reshape(h, w, 4)[:, :, :3]]
+                got = [out[0].reshape(h, w, 4)[:, :, :3]]
+            else:
+                want, got = planes, out
+            for a, b in zip(want, got):
+                assert np.array_equal(a, b), (test, i)
+        enc.close()
+        dec.close()
+
+
+def test_pipelined_matches_synchronous():
+    """send/receive (launch groups over several streams) gives the same packets, in order"""
+    F = gpu()
+    w, h, fmt = 320, 240, "yuv420p10le"
+    kw = dict(slices=30, gop_size=1)
+    frames = [synth.testsrc2_like(fmt, w, h, i) for i in range(23)]
+    ref = cc.Encoder("oracle", w, h, fmt, **kw)
+    want = [ref.encode(f) for f in frames]
+    enc = F.FFV1Encoder(w, h, fmt, max_batch=4, pipeline_depth=3, **kw)
+    got, i = [], 0
+    while True:
+        if i < len(frames):
+            if enc.send_frame(frames[i], pts=i):
+                i += 1
+                continue
+        elif i == len(frames):
+            enc.send_frame(None)
+            i += 1
+        r = enc.receive_packet()
+        if r == F.EOF:
+            break
+        if r is not None:
+            got.append(r)
+    assert [g[2] for g in got] == list(range(len(frames)))
+    assert [g[0] for g in got] == want
+    # and decode them back, pipelined, straight into caller-provided pictures
+    dec = F.FFV1Decoder(w, h, enc.extradata, max_batch=4, pipeline_depth=3)
+    out, i = [], 0
+    while True:
+        if i < len(want):
+            if dec.send_packet(want[i], pts=i, dst=dec.alloc_picture()):
+                i += 1
+                continue
+        elif i == len(want):
+            dec.send_packet(None)
+            i += 1
+        r = dec.receive_frame()
+        if r == F.EOF:
+            break
+        if r is not None:
+            out.append(r)
+    assert len(out) == len(frames)
+    for (po, arrs), src in zip(out, frames):
+        assert po.damaged_slices == 0
+        for a, b in zip(arrs, src):
+            assert np.array_equal(a, b)
+
+
+CONFIGS_FULL = [
+    # BASELINE.json configs[0..4] (frames reduced; geometry and options as stated)
+    ("C1", 1920, 1080, "yuv420p", dict(), 2),
+    ("C2", 3840, 2160, "yuv420p10le", dict(slices=1023, gop_size=1), 2),
+    ("C3", 3840, 2160, "bgr0", dict(coder=2, context=1, gop_size=1), 1),
+    ("C4", 3840, 2160, "yuv444p16le", dict(gop_size=1), 1),
+    ("C5", 7680, 4320, "yuv420p10le", dict(gop_size=1), 1),
+]
+
+
+@pytest.mark.parametrize("name,w,h,fmt,kw,nframes", CONFIGS_FULL)
+def test_full_size_roundtrip_and_oracle(name, w, h, fmt, kw, nframes):
+    """at BASELINE sizes: packet md5 == oracle (the oracle finishes a 4K frame in seconds),
+    and decode(encode(x)) == x through the GPU decoder"""
+    F = gpu()
+    enc = F.FFV1Encoder(w, h, fmt, **kw)
+    ref = cc.Encoder("oracle", w, h, fmt, threads=8, **kw)
+    assert enc.extradata == ref.extradata
+    dec = F.FFV1Decoder(w, h, enc.extradata)
+    for i in range(nframes):
+        src = synth.testsrc2_like(fmt, w, h, i)
+        pkt = enc.encode(src)
+        assert md5(pkt) == md5(ref.encode(src)), (name, i)
+        out = dec.decode(pkt)
+        if fmt == "bgr0":
+            assert np.array_equal(out[0].reshape(h, w, 4)[:, :, :3], src[0].reshape(h, w, 4)[:, :, :3])
+        else:
+            for a, b in zip(out, src):
+                assert np.array_equal(a, b), (name, i)
+
+
+def test_damaged_slice_is_flagged_and_concealed():
+    F = gpu()
+    w, h, fmt = 128, 96, "yuv420p"
+    kw = dict(slices=4, gop_size=1)
+    enc = cc.Encoder("oracle", w, h, fmt, **kw)
+    f0, f1 = synth.smooth(fmt, w, h, 0), synth.smooth(fmt, w, h, 1)
+    p0, p1 = enc.encode(f0), bytearray(enc.encode(f1))
+    p1[len(p1) // 2] ^= 0x55                      # corrupt one slice -> CRC mismatch
+    ref = cc.Decoder("oracle", w, h, enc.extradata)
+    dec = F.FFV1Decoder(w, h, enc.extradata)
+    ref.decode(p0)
+    dec.decode(p0)
+    want = ref.decode(bytes(p1))
+    got = dec.decode(bytes(p1))
+    assert dec.last.damaged_slices >= 1
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b)
+
+
+def test_device_resident_batch():
+    """pictures already in HBM -> packets in HBM (the path bench.py's `value` times)"""
+    import torch
+    F = gpu()
+    w, h, fmt = 640, 360, "yuv420p10le"
+    kw = dict(slices=60, gop_size=1)
+    n = 5
+    frame_bytes, planes = F.frame_layout(fmt, w, h)
+    host = np.zeros((n, frame_bytes), np.uint8)
+    srcs = []
+    for i in range(n):
+        src = synth.testsrc2_like(fmt, w, h, i)
+        srcs.append(src)
+        for (off, pitch, rows, rb), a in zip(planes, src):
+            host[i, off:off + pitch * rows].reshape(rows, pitch)[:, :rb] = a
+    dev = torch.from_numpy(host).cuda()
+    enc = F.FFV1Encoder(w, h, fmt, max_batch=8, **kw)
+    enc.encode_device(dev.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ref = cc.Encoder("oracle", w, h, fmt, **kw)
+    pkts = [enc.device_fetch(i) for i in range(n)]
+    assert pkts == [ref.encode(s) for s in srcs]
+    # decode the batch back into device memory
+    dec = F.FFV1Decoder(w, h, enc.extradata, max_batch=8)
+    out = torch.zeros((n, frame_bytes), dtype=torch.uint8, device="cuda")
+    dec.decode_device(pkts, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    back = out.cpu().numpy()
+    for i in range(n):
+        for (off, pitch, rows, rb), a in zip(planes, srcs[i]):
+            assert np.array_equal(back[i, off:off + pitch * rows].reshape(rows, pitch)[:, :rb], a)
