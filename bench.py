@@ -1,0 +1,445 @@
+#!/usr/bin/env python3
+"""bench.py -- FFV1 encode & decode frames/s on B200 (BASELINE.json metric).
+
+A "step" is one pass of the hot path over one batch of synthetic 4K 10-bit pictures:
+the batch is encoded (pictures -> packets) and the packets are decoded again
+(packets -> pictures).  frames/s = pictures that went through BOTH directions per second.
+
+  value  : inputs already resident in HBM (ffgpu_ffv1_encode_device / _decode_device),
+           timed with CUDA events on the launching stream
+  e2e    : the same work through the reference-facing C ABI with HOST buffers
+           (send_frame/receive_packet, send_packet/receive_frame), pinned host memory,
+           H2D + D2H inside the timed region, wall clock bracketed by synchronize()
+  --impl reference : the reference's own CPU FFV1 (oracle/_ref, slice-threaded over all
+           host threads), same metric / config, bounded sample per step
+
+One process per GPU (torchrun for N > 1); pictures are partitioned across ranks
+(rank r codes pictures r, r+N, ...) with no data-path collective: "scaling": "weak".
+"""
+import argparse
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on
+    "C2": dict(desc="4K 3840x2160 yuv420p10le, -slices 1023 (33x31, reference max), range coder "
+                    "(forced by >8 bit), context 0, -g 1, slice CRC",
+               w=3840, h=2160, fmt="yuv420p10le", opts=dict(slices=1023, gop_size=1)),
+    "C3": dict(desc="4K bgr0 RCT, -coder range_tab -context 1, 2x2 slices, -g 1",
+               w=3840, h=2160, fmt="bgr0", opts=dict(coder=2, context=1, gop_size=1)),
+    "C1": dict(desc="1080p yuv420p 8-bit, default 2x2 slices, Golomb-Rice, -g 1",
+               w=1920, h=1080, fmt="yuv420p", opts=dict(gop_size=1)),
+    "small": dict(desc="640x360 yuv420p10le 60 slices (debug)", w=640, h=360, fmt="yuv420p10le",
+                  opts=dict(slices=60, gop_size=1)),
+}
+
+
+def md5(b):
+    return hashlib.md5(b).hexdigest()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_frames(wl, count, first_index=0, stride=1):
+    import synth
+    return [synth.testsrc2_like(wl["fmt"], wl["w"], wl["h"], first_index + i * stride)
+            for i in range(count)]
+
+
+def cpu_codec_kind():
+    import cpucodec as cc
+    return ("ref", "reference") if cc.available("ref") else ("oracle", "port")
+
+
+def run_cpu(wl, frames, threads, budget_s, max_frames):
+    """the reference's CPU encoder+decoder (slice threads), bounded sample"""
+    import cpucodec as cc
+    which, kind = cpu_codec_kind()
+    enc = cc.Encoder(which, wl["w"], wl["h"], wl["fmt"], threads=threads, **wl["opts"])
+    dec = cc.Decoder(which, wl["w"], wl["h"], enc.extradata, threads=threads)
+    enc.encode(frames[0])                       # first-touch of the packet buffer, untimed
+    enc.close()
+    enc = cc.Encoder(which, wl["w"], wl["h"], wl["fmt"], threads=threads, **wl["opts"])
+    enc.encode(frames[0])
+    pkts, n = [], 0
+    t0 = time.perf_counter()
+    while n < max_frames and (n < 2 or time.perf_counter() - t0 < budget_s / 2):
+        pkts.append(enc.encode(frames[n % len(frames)]))
+        n += 1
+    t_enc = time.perf_counter() - t0
+    dec.decode(pkts[0], copy=False)
+    t0 = time.perf_counter()
+    for p in pkts:
+        dec.decode(p, copy=False)
+    t_dec = time.perf_counter() - t0
+    return dict(kind=kind, frames=n, t_enc=t_enc, t_dec=t_dec,
+                enc_fps=n / t_enc, dec_fps=n / t_dec, fps=n / (t_enc + t_dec))
+
+
+def reference_arm(args, wl, rank, world):
+    """--impl reference: rank 0 alone times the reference CPU implementation"""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    frames = make_frames(wl, 4)
+    which, kind = cpu_codec_kind()
+    sample = 8
+    res = []
+    for step in range(args.warmup + args.steps):
+        r = run_cpu(wl, frames, threads, 1e9, sample)
+        if step >= args.warmup:
+            res.append(r)
+    tot_frames = sum(r["frames"] for r in res)
+    tot_t = sum(r["t_enc"] + r["t_dec"] for r in res)
+    fps = tot_frames / tot_t
+    out = {
+        "impl": "reference", "metric": "ffv1_encode_decode_fps_4k10", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_t / max(len(res), 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + wl["desc"], "frames_per_step": sample},
+        "encode_fps": tot_frames / sum(r["t_enc"] for r in res),
+        "decode_fps": tot_frames / sum(r["t_dec"] for r in res),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+                         "sample": "%d pictures encoded+decoded per step, %d steps, %d slice threads" % (
+                             sample, len(res), threads)},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="pictures per step and GPU (0 = default)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        reference_arm(args, wl, rank, world)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import ffmpeg_ffv2_b200 as F
+    import cpucodec as cc
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the FFV1 pixel path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    w, h, fmt, opts = wl["w"], wl["h"], wl["fmt"], wl["opts"]
+    frame_bytes, planes = F.frame_layout(fmt, w, h)
+    B = args.batch or (48 if args.workload == "C2" else 16)
+    distinct = min(8, B)
+
+    # ---- synthetic input: `distinct` pictures (this rank's share of the stream), cycled ----
+    srcs = make_frames(wl, distinct, first_index=rank, stride=world)
+    h_frames = torch.empty((B, frame_bytes), dtype=torch.uint8).pin_memory()
+    hf = h_frames.numpy()
+    hf[:] = 0
+    for i in range(B):
+        for (off, pitch, rows, rb), a in zip(planes, srcs[i % distinct]):
+            hf[i, off:off + pitch * rows].reshape(rows, pitch)[:, :rb] = a
+    host_planes = [[hf[i, off:off + pitch * rows].reshape(rows, pitch)[:, :rb]
+                    for (off, pitch, rows, rb) in planes] for i in range(B)]
+    d_frames = h_frames.cuda(non_blocking=False)
+    d_out = torch.zeros((B, frame_bytes), dtype=torch.uint8, device="cuda")
+    h_out = torch.empty((B, frame_bytes), dtype=torch.uint8).pin_memory()
+    ho = h_out.numpy()
+    ho[:] = 0
+
+    enc = F.FFV1Encoder(w, h, fmt, device=local, max_batch=B, pipeline_depth=3, **opts)
+    dec = F.FFV1Decoder(w, h, enc.extradata, device=local, max_batch=B, pipeline_depth=3)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- parity gate: packets byte-identical to the CPU reference, pictures restored ----
+    which, kind = cpu_codec_kind()
+    enc.encode_device(d_frames.data_ptr(), B, stream)
+    torch.cuda.synchronize()
+    pkts = [enc.device_fetch(i) for i in range(B)]
+    cpu_enc = cc.Encoder(which, w, h, fmt, threads=min(os.cpu_count() or 1, 64), **opts)
+    for i in range(min(2, distinct)):
+        want = cpu_enc.encode(srcs[i])
+        if pkts[i] != want:
+            raise SystemExit("PARITY FAILURE: GPU packet %d differs from the CPU %s" % (i, kind))
+    cpu_enc.close()
+    dec.decode_device(pkts, d_out.data_ptr(), stream)
+    torch.cuda.synchronize()
+    if not torch.equal(d_out, d_frames):
+        raise SystemExit("PARITY FAILURE: decoded pictures differ from the input")
+    pkt_bytes = sum(len(p) for p in pkts)
+    raw_bytes = sum(rb * rows for (_o, _p, rows, rb) in planes)
+
+    # ---- value: inputs resident in HBM, CUDA events on the launching stream ----
+    enc.profile(True)
+    dec.profile(True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    kern = {}
+    t_enc_ms = t_dec_ms = 0.0
+    launches0 = enc.launches + dec.launches
+    sampler = ClockSampler(local)
+    for step in range(args.warmup + args.steps):
+        if step == args.warmup:
+            barrier()
+            sampler.start()
+            launches0 = enc.launches + dec.launches
+            wall0 = time.perf_counter()
+        ev[0].record()
+        enc.encode_device(d_frames.data_ptr(), B, stream)
+        ev[1].record()
+        dec.decode_device(pkts, d_out.data_ptr(), stream)
+        ev[2].record()
+        torch.cuda.synchronize()
+        if step >= args.warmup:
+            t_enc_ms += ev[0].elapsed_time(ev[1])
+            t_dec_ms += ev[1].elapsed_time(ev[2])
+            for k, v in list(enc.kernel_ms().items()) + list(dec.kernel_ms().items()):
+                kern[k] = kern.get(k, 0.0) + v
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    gpu_launches = enc.launches + dec.launches - launches0
+    enc.profile(False)
+    dec.profile(False)
+    K = args.steps
+    dev_time = max_over_ranks(max((t_enc_ms + t_dec_ms) / 1e3, 0.0))
+    total_frames = B * K * world
+    value = total_frames / dev_time
+    enc_fps = B * K * world / max_over_ranks(t_enc_ms / 1e3)
+    dec_fps = B * K * world / max_over_ranks(t_dec_ms / 1e3)
+    for k in kern:
+        kern[k] /= K
+
+    # ---- roofline of the dominant kernel ----
+    peak, peak_src = measured_peaks()
+    dom = max(("code", "decode"), key=lambda k: kern.get(k, 0.0))
+    alg_bytes = (raw_bytes + pkt_bytes / B) * B           # raw + packet bytes per picture
+    achieved = alg_bytes / (kern[dom] / 1e3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_code_range" if dom == "code" else "k_decode",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kern[dom]}
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        # smaller launch groups, more of them in flight: H2D, kernels and D2H overlap
+        vb = max(B // 4, 1)
+        enc.close()
+        dec.close()
+        enc = F.FFV1Encoder(w, h, fmt, device=local, max_batch=vb, pipeline_depth=4, **opts)
+        dec = F.FFV1Decoder(w, h, enc.extradata, device=local, max_batch=vb, pipeline_depth=4)
+
+        def e2e_step():
+            out_pk, i = [], 0
+            while True:
+                if i < B:
+                    if enc.send_frame(host_planes[i], pts=i):
+                        i += 1
+                        continue
+                elif i == B:
+                    enc.send_frame(None)
+                    i += 1
+                r = enc.receive_packet()
+                if r == F.EOF:
+                    break
+                if r is not None:
+                    out_pk.append(r[0])
+            done, i = 0, 0
+            while True:
+                if i < B:
+                    if dec.send_packet(out_pk[i], pts=i, dst=dsts[i]):
+                        i += 1
+                        continue
+                elif i == B:
+                    dec.send_packet(None)
+                    i += 1
+                r = dec.receive_frame()
+                if r == F.EOF:
+                    break
+                if r is not None:
+                    done += 1
+            return out_pk, done
+
+        dsts = []
+        for i in range(B):
+            po = F.codec.PictureOut()
+            arrs = []
+            for k, (off, pitch, rows, rb) in enumerate(planes):
+                a = ho[i, off:off + pitch * rows].reshape(rows, pitch)[:, :rb]
+                po.data[k] = a.ctypes.data
+                po.linesize[k] = pitch
+                arrs.append(a)
+            dsts.append((po, arrs))
+        e2e_t = 0.0
+        e2e_launch0 = 0
+        for step in range(args.warmup + args.steps):
+            if step == args.warmup:
+                e2e_launch0 = enc.launches + dec.launches
+            barrier()
+            t0 = time.perf_counter()
+            out_pk, done = e2e_step()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            barrier()
+            if step >= args.warmup:
+                e2e_t += max_over_ranks(dt)
+            assert done == B and len(out_pk) == B
+        if out_pk != pkts or not np.array_equal(ho, hf):
+            raise SystemExit("PARITY FAILURE: e2e path differs from the device path / the input")
+        e2e = {"value": B * K * world / e2e_t, "unit": "frames/s",
+               "h2d_bytes_per_step": int(B * raw_bytes + pkt_bytes),
+               "d2h_bytes_per_step": int(pkt_bytes + B * raw_bytes),
+               "ms_per_step": 1e3 * e2e_t / K,
+               "api": "ffgpu_ffv1_encode_send_frame/receive_packet + "
+                      "ffgpu_ffv1_decode_send_packet/receive_frame, pinned host buffers",
+               "frames_per_launch_group": vb, "launch_groups_in_flight": 4,
+               "gpu_launches": int(enc.launches + dec.launches - e2e_launch0)}
+
+    # ---- CPU baseline beside it (rank 0, N == 1): the reference's slice-threaded CPU codec ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        r = run_cpu(wl, srcs, threads, 16.0, 400)
+        cpu = {"value": r["fps"], "unit": "frames/s", "cores": threads, "kind": r["kind"],
+               "encode_fps": r["enc_fps"], "decode_fps": r["dec_fps"],
+               "sample": "%d pictures encoded+decoded once (%.1f s), %d slice threads" % (
+                   r["frames"], r["t_enc"] + r["t_dec"], threads)}
+
+    out = {
+        "metric": "ffv1_encode_decode_fps_4k10", "value": value, "unit": "frames/s",
+        "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dev_time / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + wl["desc"], "frames_per_step_per_gpu": B,
+                   "distinct_pictures": distinct, "source": "testsrc2-like (tests/synth.py)",
+                   "l2": "inputs larger than L2 (%.0f MB per step)" % (B * frame_bytes / 1e6),
+                   "partition": "pictures round-robin over ranks, no collective"},
+        "encode_fps": enc_fps, "decode_fps": dec_fps,
+        "pixel_GBps": value * raw_bytes / 1e9,
+        "packet_bytes_per_picture": pkt_bytes / B, "raw_bytes_per_picture": raw_bytes,
+        "kernel_ms_per_step": kern, "wall_ms_per_step": 1e3 * wall / K,
+        "roofline": roofline, "gpu_launches": int(gpu_launches), "clocks": clocks,
+        "e2e": e2e, "cpu_baseline": cpu,
+    }
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    enc.close()
+    dec.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -91,6 +91,10 @@ SYMBOLS = [
                                              C.POINTER(C.c_int)]),
     ("ffgpu_ffv1_encoder_launches", C.c_uint64, [C.c_void_p]),
     ("ffgpu_ffv1_decoder_launches", C.c_uint64, [C.c_void_p]),
+    ("ffgpu_ffv1_encoder_profile", C.c_int, [C.c_void_p, C.c_int]),
+    ("ffgpu_ffv1_encoder_kernel_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
+    ("ffgpu_ffv1_decoder_profile", C.c_int, [C.c_void_p, C.c_int]),
+    ("ffgpu_ffv1_decoder_kernel_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
     ("ffgpu_last_error", C.c_char_p, []),
     ("ffgpu_abi_version", C.c_int, []),
 ]
@@ -237,6 +241,21 @@ class FFV1Encoder:
             raise FFGpuError("encode_device_fetch", r, _err())
         return self._buf[:n.value].tobytes()
 
+    ENC_KERNELS = ["symbolize", "fill_state", "code", "pack_slice_scan", "pack_frame_scan",
+                   "pack_gather"]
+
+    def profile(self, enable=True):
+        r = lib().ffgpu_ffv1_encoder_profile(self.h, int(enable))
+        if r < 0:
+            raise FFGpuError("encoder_profile", r, _err())
+
+    def kernel_ms(self):
+        ms = (C.c_float * 8)()
+        n = lib().ffgpu_ffv1_encoder_kernel_ms(self.h, ms, 8)
+        if n < 0:
+            raise FFGpuError("encoder_kernel_ms", n, _err())
+        return dict(zip(self.ENC_KERNELS, list(ms)[:n]))
+
     def device_result(self, frame):
         p = C.c_void_p()
         n = C.c_size_t()
@@ -337,6 +356,20 @@ class FFV1Decoder:
         if r < 0:
             raise FFGpuError("receive_frame", r, _err())
         return o
+
+    DEC_KERNELS = ["init_state", "decode"]
+
+    def profile(self, enable=True):
+        r = lib().ffgpu_ffv1_decoder_profile(self.h, int(enable))
+        if r < 0:
+            raise FFGpuError("decoder_profile", r, _err())
+
+    def kernel_ms(self):
+        ms = (C.c_float * 4)()
+        n = lib().ffgpu_ffv1_decoder_kernel_ms(self.h, ms, 4)
+        if n < 0:
+            raise FFGpuError("decoder_kernel_ms", n, _err())
+        return dict(zip(self.DEC_KERNELS, list(ms)[:n]))
 
     def decode_device(self, pkts, d_ptr, stream=0):
         n = len(pkts)

@@ -153,6 +153,8 @@ struct ffgpu_encoder {
     int flushing, eof;
     int64_t picture_number;
     uint64_t launches;
+    int profile;                        /* record events around every kernel of device batches */
+    void *events[FFK_ENC_KERNELS + 1];
 };
 
 static int enc_free_job(EncJob *j)
@@ -484,11 +486,23 @@ extern "C" int ffgpu_ffv1_encode_receive_packet(ffgpu_encoder *e, uint8_t *pkt, 
 {
     EncJob *j;
     int r, i;
-    if (!e || !e->dev_ready)
-        return e && e->flushing ? FFGPU_EOF : FFGPU_EAGAIN;
+    if (!e)
+        return fail(FFGPU_EINVAL, "null encoder");
+    if (!e->dev_ready) {
+        if (e->flushing) {
+            e->flushing = 0;
+            return FFGPU_EOF;
+        }
+        return FFGPU_EAGAIN;
+    }
     j = &e->jobs[e->head];
-    if (j->state == JOB_FREE || j->state == JOB_FILLING)
-        return e->flushing ? FFGPU_EOF : FFGPU_EAGAIN;
+    if (j->state == JOB_FREE || j->state == JOB_FILLING) {
+        if (e->flushing) {
+            e->flushing = 0;                       /* drained: the handle accepts pictures again */
+            return FFGPU_EOF;
+        }
+        return FFGPU_EAGAIN;
+    }
     if (j->state == JOB_RUNNING) {
         /* block only if the caller cannot make progress otherwise */
         const EncJob *f = &e->jobs[e->fill];
@@ -578,6 +592,8 @@ extern "C" int ffgpu_ffv1_encode_device(ffgpu_encoder *e, const void *d_frames, 
     e->picture_number += nframes;
     j->n = nframes;
     enc_fill_dev(e, j, (const uint8_t *)d_frames, &E);
+    if (e->profile)
+        E.events = e->events;
     CK(cudaMemcpyAsync(j->d_frame_set, j->h_frame_set, nframes, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(j->d_frame_key, j->h_frame_key, nframes, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(j->d_overflow, 0, sizeof(uint32_t), st));
@@ -631,12 +647,42 @@ extern "C" int ffgpu_ffv1_encode_device_fetch(ffgpu_encoder *e, int frame, uint8
     return 0;
 }
 
+/* profiling of the device-batch path: per-kernel CUDA-event times of the last group */
+extern "C" int ffgpu_ffv1_encoder_profile(ffgpu_encoder *e, int enable)
+{
+    int r;
+    if (!e)
+        return fail(FFGPU_EINVAL, "null encoder");
+    if ((r = enc_device_init(e)) < 0)
+        return r;
+    if (enable && !e->events[0])
+        for (int i = 0; i <= FFK_ENC_KERNELS; i++) {
+            cudaEvent_t ev;
+            CK(cudaEventCreate(&ev));
+            e->events[i] = ev;
+        }
+    e->profile = enable;
+    return 0;
+}
+
+extern "C" int ffgpu_ffv1_encoder_kernel_ms(ffgpu_encoder *e, float *ms, int n)
+{
+    if (!e || !e->profile || !e->events[0])
+        return fail(FFGPU_EINVAL, "profiling not enabled");
+    for (int i = 0; i < n && i < FFK_ENC_KERNELS; i++)
+        CK(cudaEventElapsedTime(&ms[i], (cudaEvent_t)e->events[i], (cudaEvent_t)e->events[i + 1]));
+    return FFK_ENC_KERNELS;
+}
+
 extern "C" int ffgpu_ffv1_encode_close(ffgpu_encoder *e)
 {
     if (!e)
         return 0;
     if (e->dev_ready) {
         cudaDeviceSynchronize();
+        for (int i = 0; i <= FFK_ENC_KERNELS; i++)
+            if (e->events[i])
+                cudaEventDestroy((cudaEvent_t)e->events[i]);
         for (int i = 0; i < MAX_DEPTH; i++)
             enc_free_job(&e->jobs[i]);
         cudaFree(e->d_slices); cudaFree(e->d_qt); cudaFree(e->d_tab); cudaFree(e->d_prefix);
@@ -696,6 +742,8 @@ struct ffgpu_decoder {
     DecJob jobs[MAX_DEPTH];
     int fill, head, flushing;
     uint64_t launches;
+    int profile, profile_next;
+    void *events[FFK_DEC_KERNELS + 1];
 };
 
 static void dec_free_job(DecJob *j)
@@ -907,6 +955,8 @@ static int dec_launch(ffgpu_decoder *d, DecJob *j, uint8_t *frames, cudaStream_t
     FFDecDev D;
     int r;
     dec_fill_dev(d, j, frames, &D);
+    if (d->profile_next)
+        D.events = d->events;
     CK(cudaMemcpyAsync(j->d_pkt, j->h_pkt, align_up(j->pkt_used + 64, 16), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(j->d_work, j->h_work, (size_t)j->n * d->max_slices * sizeof(FFDecSlice),
                        cudaMemcpyHostToDevice, st));
@@ -1101,11 +1151,23 @@ extern "C" int ffgpu_ffv1_decode_receive_frame(ffgpu_decoder *d, ffgpu_picture_o
 {
     DecJob *j;
     int r, i;
-    if (!d || !d->dev_ready)
-        return d && d->flushing ? FFGPU_EOF : FFGPU_EAGAIN;
+    if (!d)
+        return fail(FFGPU_EINVAL, "null decoder");
+    if (!d->dev_ready) {
+        if (d->flushing) {
+            d->flushing = 0;
+            return FFGPU_EOF;
+        }
+        return FFGPU_EAGAIN;
+    }
     j = &d->jobs[d->head];
-    if (j->state == JOB_FREE || j->state == JOB_FILLING)
-        return d->flushing ? FFGPU_EOF : FFGPU_EAGAIN;
+    if (j->state == JOB_FREE || j->state == JOB_FILLING) {
+        if (d->flushing) {
+            d->flushing = 0;                       /* drained: the handle accepts packets again */
+            return FFGPU_EOF;
+        }
+        return FFGPU_EAGAIN;
+    }
     if (j->state == JOB_RUNNING) {
         const DecJob *f = &d->jobs[d->fill];
         const int must_wait = d->flushing || f->state == JOB_RUNNING || f->state == JOB_DRAINING;
@@ -1210,16 +1272,44 @@ extern "C" int ffgpu_ffv1_decode_device(ffgpu_decoder *d, const uint8_t *const *
         }
     }
     st = cuda_stream ? (cudaStream_t)cuda_stream : j->stream;
+    d->profile_next = d->profile;
     r = dec_launch(d, j, (uint8_t *)d_frames, st, 0);
+    d->profile_next = 0;
     j->n = 0;
     j->state = JOB_FREE;
     return r;
+}
+
+extern "C" int ffgpu_ffv1_decoder_profile(ffgpu_decoder *d, int enable)
+{
+    if (!d)
+        return fail(FFGPU_EINVAL, "null decoder");
+    if (enable && !d->events[0])
+        for (int i = 0; i <= FFK_DEC_KERNELS; i++) {
+            cudaEvent_t ev;
+            CK(cudaEventCreate(&ev));
+            d->events[i] = ev;
+        }
+    d->profile = enable;
+    return 0;
+}
+
+extern "C" int ffgpu_ffv1_decoder_kernel_ms(ffgpu_decoder *d, float *ms, int n)
+{
+    if (!d || !d->profile || !d->events[0])
+        return fail(FFGPU_EINVAL, "profiling not enabled");
+    for (int i = 0; i < n && i < FFK_DEC_KERNELS; i++)
+        CK(cudaEventElapsedTime(&ms[i], (cudaEvent_t)d->events[i], (cudaEvent_t)d->events[i + 1]));
+    return FFK_DEC_KERNELS;
 }
 
 extern "C" int ffgpu_ffv1_decode_close(ffgpu_decoder *d)
 {
     if (!d)
         return 0;
+    for (int i = 0; i <= FFK_DEC_KERNELS; i++)
+        if (d->events[i])
+            cudaEventDestroy((cudaEvent_t)d->events[i]);
     if (d->dev_ready) {
         cudaDeviceSynchronize();
         for (int i = 0; i < MAX_DEPTH; i++)

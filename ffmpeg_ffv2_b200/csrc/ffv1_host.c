@@ -996,8 +996,16 @@ int ff_dec_parse_packet(FFStream *s, FFDecHostState *hs, const uint8_t *pkt, siz
             hs->damaged[i] = 1;            /* "slice CRC mismatch" */
             info->crc_damaged++;
         }
-        d->pkt_off = pkt_off + (uint32_t)(end - pkt);
-        d->size = (uint32_t)v;
+        if (i) {
+            d->pkt_off = pkt_off + (uint32_t)(end - pkt);
+            d->size = (uint32_t)v;
+        } else {
+            /* slice 0 keeps decoding with the coder that read the key-frame bit: its stream
+             * starts at the packet start and only bytestream_end moves (ffv1dec.c:927-928).
+             * In an intact packet end == pkt here. */
+            d->pkt_off = pkt_off;
+            d->size = (uint32_t)((end - pkt) + v);
+        }
         d->key_frame = info->key_frame;
     }
 

@@ -35,6 +35,12 @@ static inline int launch_ok(void)
     return cudaGetLastError() == cudaSuccess;
 }
 
+static inline void mark(void **events, int i, cudaStream_t st)
+{
+    if (events && events[i])
+        cudaEventRecord((cudaEvent_t)events[i], st);
+}
+
 /* ---------------- stage A ---------------- */
 __global__ void __launch_bounds__(SYM_THREADS)
 k_symbolize(const FFDevParams P, const FFDevSlice *__restrict__ slices,
@@ -167,6 +173,7 @@ extern "C" int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nfr
     if (nframes <= 0 || nframes > 1024 || P->nslices > 1024)
         return FFGPU_EINVAL;
 
+    mark(E->events, 0, st);
     /* stage A */
     {
         /* enough z-blocks to cover large slices; small slices get one block each */
@@ -176,6 +183,7 @@ extern "C" int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nfr
         if (z > 64) z = 64;
         dim3 grid(P->nslices, nframes, z);
         k_symbolize<<<grid, SYM_THREADS, 0, st>>>(*P, E->slices, E->frames, E->qt, E->tokens);
+        mark(E->events, FFK_SYMBOLIZE + 1, st);
         launches++;
         if (!launch_ok()) return FFGPU_EXTERNAL;
     }
@@ -190,6 +198,7 @@ extern "C" int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nfr
         k_fill_state<<<grid, 256, 0, st>>>((uint2 *)E->state, words, E->frame_key, E->state_per_frame,
                                            golomb ? FF_VLC_INIT_LO : 0x80808080u,
                                            golomb ? FF_VLC_INIT_HI : 0x80808080u);
+        mark(E->events, FFK_FILL_STATE + 1, st);
         launches++;
         if (!launch_ok()) return FFGPU_EXTERNAL;
     }
@@ -201,16 +210,20 @@ extern "C" int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nfr
             k_code_golomb<<<blocks, CODE_THREADS, 0, st>>>(*P, *E, nframes);
         else
             k_code_range<<<blocks, CODE_THREADS, 0, st>>>(*P, *E, nframes);
+        mark(E->events, FFK_CODE + 1, st);
         launches++;
         if (!launch_ok()) return FFGPU_EXTERNAL;
     }
     /* packet assembly */
     k_pack_slice_scan<<<nframes, 1024, 0, st>>>(*P, *E);
+    mark(E->events, FFK_PACK_SLICE_SCAN + 1, st);
     k_pack_frame_scan<<<1, 1024, 0, st>>>(*E, nframes);
+    mark(E->events, FFK_PACK_FRAME_SCAN + 1, st);
     {
         dim3 grid((P->nslices + CODE_THREADS - 1) / CODE_THREADS, nframes);
         k_pack_gather<<<grid, CODE_THREADS, 0, st>>>(*P, *E);
     }
+    mark(E->events, FFK_PACK_GATHER + 1, st);
     launches += 3;
     if (!launch_ok()) return FFGPU_EXTERNAL;
     return launches;
@@ -281,9 +294,12 @@ extern "C" int ffk_decode_group(const FFDevParams *P, const FFDecDev *D, int nfr
     if (nframes <= 0)
         return FFGPU_EINVAL;
     dim3 g0(D->max_slices, nframes);
+    mark(D->events, 0, st);
     k_dec_init_state<<<g0, 256, 0, st>>>(*P, *D, P->ac == FF_AC_GOLOMB);
+    mark(D->events, FFK_DEC_INIT_STATE + 1, st);
     const int total = nframes * D->max_slices;
     k_decode<<<(total + CODE_THREADS - 1) / CODE_THREADS, CODE_THREADS, 0, st>>>(*P, *D, nframes);
+    mark(D->events, FFK_DECODE + 1, st);
     if (!launch_ok()) return FFGPU_EXTERNAL;
     return 2;
 }

@@ -34,7 +34,15 @@ typedef struct FFEncDev {
     uint32_t *overflow;             /* [1] sticky flag                                  */
     uint8_t *pkt;                   /* packed output of the whole group                 */
     int state_per_frame;            /* 1: state[frame][slice] (intra), 0: state[slice]   */
+    void **events;                  /* optional cudaEvent_t[FFK_ENC_KERNELS + 1]: recorded    */
+                                    /* before the first and after every kernel (profiling)  */
 } FFEncDev;
+
+/* kernels of one encode group, in launch order */
+enum { FFK_SYMBOLIZE = 0, FFK_FILL_STATE, FFK_CODE, FFK_PACK_SLICE_SCAN, FFK_PACK_FRAME_SCAN,
+       FFK_PACK_GATHER, FFK_ENC_KERNELS };
+/* kernels of one decode group */
+enum { FFK_DEC_INIT_STATE = 0, FFK_DECODE, FFK_DEC_KERNELS };
 
 int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nframes, ffk_stream stream);
 
@@ -54,6 +62,7 @@ typedef struct FFDecDev {
     int max_slices;
     int max_ctx;                    /* contexts per set (largest quant table)           */
     int state_per_frame;
+    void **events;                  /* optional cudaEvent_t[FFK_DEC_KERNELS + 1]          */
 } FFDecDev;
 
 int ffk_decode_group(const FFDevParams *P, const FFDecDev *D, int nframes, ffk_stream stream);

@@ -110,7 +110,8 @@ int ffgpu_ffv1_encode_frame(ffgpu_encoder *enc, const ffgpu_picture *pic,
  * groups on CUDA streams; packets come back in presentation order.
  * send: pic == NULL flushes.  FFGPU_EAGAIN = queue full, call receive first.
  * receive: FFGPU_EAGAIN = nothing ready yet (send more or flush), FFGPU_EOF after a flush
- * once every packet was returned. */
+ * once every packet was returned; the EOF also ends the flush, so the handle accepts
+ * pictures again afterwards (avcodec_flush_buffers semantics). */
 int ffgpu_ffv1_encode_send_frame(ffgpu_encoder *enc, const ffgpu_picture *pic);
 int ffgpu_ffv1_encode_receive_packet(ffgpu_encoder *enc, uint8_t *pkt, size_t pkt_cap,
                                      size_t *pkt_size, int *key_frame, int64_t *pts);
@@ -197,6 +198,17 @@ size_t ffgpu_ffv1_frame_layout(const char *pix_fmt, int width, int height,
 /* launch statistics of the handle (kernels launched by this library so far) */
 uint64_t ffgpu_ffv1_encoder_launches(const ffgpu_encoder *enc);
 uint64_t ffgpu_ffv1_decoder_launches(const ffgpu_decoder *dec);
+
+/* Profiling of the *_device entry points: when enabled, CUDA events are recorded around
+ * every kernel of the launch group; *_kernel_ms() returns the elapsed times of the last
+ * group (after the stream was synchronised), in launch order:
+ *   encoder: symbolize, fill_state, code, pack_slice_scan, pack_frame_scan, pack_gather
+ *   decoder: init_state, decode
+ * and the number of kernels, or a negative error. */
+int ffgpu_ffv1_encoder_profile(ffgpu_encoder *enc, int enable);
+int ffgpu_ffv1_encoder_kernel_ms(ffgpu_encoder *enc, float *ms, int n);
+int ffgpu_ffv1_decoder_profile(ffgpu_decoder *dec, int enable);
+int ffgpu_ffv1_decoder_kernel_ms(ffgpu_decoder *dec, float *ms, int n);
 
 /* last error text of the calling thread ("" if none) */
 const char *ffgpu_last_error(void);

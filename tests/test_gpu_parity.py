@@ -206,23 +206,42 @@ def test_full_size_roundtrip_and_oracle(name, w, h, fmt, kw, nframes):
                 assert np.array_equal(a, b), (name, i)
 
 
-def test_damaged_slice_is_flagged_and_concealed():
+def _corrupt_cases(p1):
+    """(name, packet): a payload byte of slice 1 (CRC mismatch -> concealment) and a byte of a
+    size trailer (slice pointer chain shortened, ffv1dec.c:746-756)"""
+    sizes, end = [], len(p1)
+    while end > 0:
+        size = int.from_bytes(p1[end - 8:end - 5], "big")
+        sizes.append((end - 8 - size, size))
+        end -= size + 8
+    sizes = sizes[::-1]
+    a = bytearray(p1)
+    a[sizes[1][0] + sizes[1][1] // 2] ^= 0x55
+    b = bytearray(p1)
+    b[sizes[1][0] + sizes[1][1] + 1] ^= 0x55
+    return [("payload", bytes(a)), ("size-trailer", bytes(b))]
+
+
+@pytest.mark.parametrize("fmt,kw", [("yuv420p", dict(slices=4, gop_size=1)),
+                                    ("yuv420p10le", dict(slices=4, gop_size=1))])
+def test_damaged_packets_behave_like_the_reference(fmt, kw):
     F = gpu()
-    w, h, fmt = 128, 96, "yuv420p"
-    kw = dict(slices=4, gop_size=1)
+    w, h = 128, 96
     enc = cc.Encoder("oracle", w, h, fmt, **kw)
     f0, f1 = synth.smooth(fmt, w, h, 0), synth.smooth(fmt, w, h, 1)
-    p0, p1 = enc.encode(f0), bytearray(enc.encode(f1))
-    p1[len(p1) // 2] ^= 0x55                      # corrupt one slice -> CRC mismatch
-    ref = cc.Decoder("oracle", w, h, enc.extradata)
-    dec = F.FFV1Decoder(w, h, enc.extradata)
-    ref.decode(p0)
-    dec.decode(p0)
-    want = ref.decode(bytes(p1))
-    got = dec.decode(bytes(p1))
-    assert dec.last.damaged_slices >= 1
-    for a, b in zip(want, got):
-        assert np.array_equal(a, b)
+    p0, p1 = enc.encode(f0), enc.encode(f1)
+    for name, bad in _corrupt_cases(p1):
+        ref = cc.Decoder("oracle", w, h, enc.extradata)
+        dec = F.FFV1Decoder(w, h, enc.extradata)
+        ref.decode(p0)
+        dec.decode(p0)
+        want = ref.decode(bad)
+        got = dec.decode(bad)
+        if name == "payload":
+            assert dec.last.damaged_slices >= 1
+        for a, b in zip(want, got):
+            assert np.array_equal(a, b), (fmt, name)
+        dec.close()
 
 
 def test_device_resident_batch():
