@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(CODE_THREADS)
 k_code_range(const FFDevParams P, const FFEncDev E, int nframes)
 {
     __shared__ FFRacTables tab;
+    __shared__ uint32_t rows[CODE_THREADS][FF_ROW_WORDS];
     for (int i = threadIdx.x; i < (int)sizeof(FFRacTables) / 4; i += CODE_THREADS)
         ((uint32_t *)&tab)[i] = ((const uint32_t *)E.tab)[i];
     __syncthreads();
@@ -90,7 +91,7 @@ k_code_range(const FFDevParams P, const FFEncDev E, int nframes)
         sl, E.tokens + (size_t)f * P.frame_tokens + sl.tok_off,
         E.state + st_slot * P.total_ctx * FF_CONTEXT_SIZE, &tab,
         E.prefix[(size_t)E.frame_prefix_set[f] * P.nslices + s], E.prefix_bytes,
-        E.bs + (size_t)f * P.frame_bs + sl.bs_off, &ovf);
+        E.bs + (size_t)f * P.frame_bs + sl.bs_off, &ovf, rows[threadIdx.x]);
     E.slice_bytes[gid] = n;
     if (ovf)
         atomicOr(E.overflow, 1u);
@@ -261,6 +262,7 @@ __global__ void __launch_bounds__(CODE_THREADS)
 k_decode(const FFDevParams P, const FFDecDev D, int nframes)
 {
     __shared__ FFRacTables tab;
+    __shared__ uint32_t rows[CODE_THREADS][FF_ROW_WORDS];
     for (int i = threadIdx.x; i < (int)sizeof(FFRacTables) / 4; i += CODE_THREADS)
         ((uint32_t *)&tab)[i] = ((const uint32_t *)D.tab)[i];
     __syncthreads();
@@ -282,7 +284,7 @@ k_decode(const FFDevParams P, const FFDecDev D, int nframes)
             C.lines = D.lines + (size_t)gid * P.ncoded * 2 * D.line_stride;
             C.line_stride = D.line_stride;
             C.frame = D.frames + (size_t)f * P.frame_bytes;
-            ff_decode_slice(P, w, D.pkt, C, &r);
+            ff_decode_slice(P, w, D.pkt, C, &r, rows[threadIdx.x]);
         }
     }
     D.result[gid] = r;

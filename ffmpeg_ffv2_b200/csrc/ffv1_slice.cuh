@@ -203,24 +203,141 @@ FFGPU_HD void ff_enc_resume(FFRacEnc *c, const FFRacPrefix &pre, const uint8_t *
     c->run = pre.run;
 }
 
-/* returns the slice's byte count; *overflow != 0 if the arena was too small */
+/* ---- per-thread cache of the current context's 32 adaptive state bytes ----
+ * The row lives in shared memory (9-word stride: conflict-free when all lanes touch the
+ * same slot) so that the per-decision state read/update is an LDS/STS instead of a global
+ * round trip; it is written back only when the context changes. */
+#define FF_ROW_WORDS 9
+
+typedef struct
+#if defined(__CUDACC__)
+__align__(16)
+#else
+__attribute__((aligned(16)))
+#endif
+FFU128 { uint32_t x, y, z, w; } FFU128;
+
+FFGPU_HD void ff_row_load(uint32_t *row, const uint8_t *g)
+{
+    const FFU128 a = ((const FFU128 *)g)[0], b = ((const FFU128 *)g)[1];
+    row[0] = a.x; row[1] = a.y; row[2] = a.z; row[3] = a.w;
+    row[4] = b.x; row[5] = b.y; row[6] = b.z; row[7] = b.w;
+}
+
+FFGPU_HD void ff_row_store(const uint32_t *row, uint8_t *g)
+{
+    FFU128 a, b;
+    a.x = row[0]; a.y = row[1]; a.z = row[2]; a.w = row[3];
+    b.x = row[4]; b.y = row[5]; b.z = row[6]; b.w = row[7];
+    ((FFU128 *)g)[0] = a;
+    ((FFU128 *)g)[1] = b;
+}
+
+/* one renormalisation step of renorm_encoder (rangecoder.h:71-94); in the symbol loop the
+ * range can drop below 0x100 at most once per decision */
+FFGPU_HD void ffrac_enc_shift1(FFRacEnc *c)
+{
+    if (c->pending < 0) {
+        c->pending = c->low >> 8;
+    } else if (c->low <= 0xFF00) {
+        ffrac_emit(c, c->pending);
+        for (; c->run; c->run--)
+            ffrac_emit(c, 0xFF);
+        c->pending = c->low >> 8;
+    } else if (c->low >= 0x10000) {
+        ffrac_emit(c, c->pending + 1);
+        for (; c->run; c->run--)
+            ffrac_emit(c, 0x00);
+        c->pending = (c->low >> 8) & 0xFF;
+    } else {
+        c->run++;
+    }
+    c->low = (c->low & 0xFF) << 8;
+    c->range <<= 8;
+}
+
+/* Stage B, range coder.  The 32 lanes of a warp code 32 different slices, so the loop is
+ * written as ONE BINARY DECISION PER ITERATION with a small per-lane state machine
+ * (put_symbol_inline, ffv1enc.c:185-231, unrolled over `step`): a lane that is inside a
+ * large residual (2e+3 decisions) does not hold up lanes that only code zero flags.
+ *   step 0           zero flag                 state[0]
+ *   1..e             unary exponent ones       state[1 + min(i,9)]
+ *   e+1              unary terminator          state[1 + min(e,9)]
+ *   e+2..2e+1        mantissa, MSB first       state[22 + min(i,9)]
+ *   2e+2             sign                      state[11 + min(e,10)]
+ * returns the slice's byte count; *overflow != 0 if the arena was too small */
 FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *tokens,
                                         uint8_t *state, const FFRacTables *tab,
                                         const FFRacPrefix &pre, const uint8_t *pre_bytes,
-                                        uint8_t *out, uint32_t *overflow)
+                                        uint8_t *out, uint32_t *overflow, uint32_t *row)
 {
+    const uint8_t *trans = (const uint8_t *)tab;     /* one[256] followed by zero[256] */
+    uint8_t *rowb = (uint8_t *)row;
     FFRacEnc c;
-    uint32_t i, n;
+    const uint32_t n = sl.ntok;
+    uint32_t i = 0, nb;
+    uint32_t tok_next = n ? tokens[0] : 0;
+    int cur_ctx = -1;
+    int a = 0, e = 0, neg = 0, step = 0, nsteps = 0;
+
     ff_enc_resume(&c, pre, pre_bytes, out, sl.bs_cap);
-    for (i = 0; i < sl.ntok; i++) {
-        const uint32_t tok = tokens[i];
-        const int diff = (int32_t)tok >> FF_TOKEN_CTX_BITS;
-        uint8_t *st = state + (size_t)(tok & FF_TOKEN_CTX_MASK) * FF_CONTEXT_SIZE;
-        ffrac_put_symbol(&c, tab, st, diff, 1);
+    for (;;) {
+        int slot, bit, s, r1, rb;
+        if (step == nsteps) {                        /* fetch the next residual */
+            uint32_t tok;
+            int ctx, diff;
+            if (i == n)
+                break;
+            tok = tok_next;
+            i++;
+            if (i < n)
+                tok_next = tokens[i];
+            ctx = (int)(tok & FF_TOKEN_CTX_MASK);
+            diff = (int32_t)tok >> FF_TOKEN_CTX_BITS;
+            if (ctx != cur_ctx) {
+                if (cur_ctx >= 0)
+                    ff_row_store(row, state + (size_t)cur_ctx * FF_CONTEXT_SIZE);
+                ff_row_load(row, state + (size_t)ctx * FF_CONTEXT_SIZE);
+                cur_ctx = ctx;
+            }
+            a = diff < 0 ? -diff : diff;
+            neg = diff < 0;
+            e = ffrac_ilog2((uint32_t)a);
+            nsteps = a ? 2 * e + 3 : 1;
+            step = 0;
+        }
+        if (step == 0) {
+            slot = 0;
+            bit = a == 0;
+        } else if (step <= e) {
+            slot = 1 + ff_min(step - 1, 9);
+            bit = 1;
+        } else if (step == e + 1) {
+            slot = 1 + ff_min(e, 9);
+            bit = 0;
+        } else if (step <= 2 * e + 1) {
+            const int j = 2 * e + 1 - step;
+            slot = 22 + ff_min(j, 9);
+            bit = (a >> j) & 1;
+        } else {
+            slot = 11 + ff_min(e, 10);
+            bit = neg;
+        }
+        s = rowb[slot];
+        r1 = (c.range * s) >> 8;                     /* put_rac, rangecoder.h:104-121 */
+        rb = c.range - r1;
+        rowb[slot] = trans[s + (bit ? 0 : 256)];
+        c.low += bit ? rb : 0;
+        c.range = bit ? r1 : rb;
+        if (c.range < 0x100)
+            ffrac_enc_shift1(&c);
+        step++;
     }
-    n = ffrac_enc_finish(&c, tab, 1);           /* ffv1enc.c:1242 */
+    if (cur_ctx >= 0)
+        ff_row_store(row, state + (size_t)cur_ctx * FF_CONTEXT_SIZE);
+    nb = ffrac_enc_finish(&c, tab, 1);               /* ffv1enc.c:1242 */
     *overflow = c.overflow;
-    return n;
+    return nb;
 }
 
 /* ------------------------------------------------------------------ */
@@ -538,45 +655,6 @@ FFGPU_HD int ff_wrap_sample(const FFDevParams &P, int v)
     return P.use32 ? v : (int)(int16_t)v;
 }
 
-/* decode_line (range coder branch), ffv1dec_template.c:23-126.  prev/cur are the two line
- * buffers of the plane: prev holds line y-1, cur still holds line y-2 and is overwritten. */
-FFGPU_HD int ff_decode_line_range(const FFDevParams &P, FFRacDec *c, const FFDecCtx &D,
-                                  const int16_t *qt, uint8_t *state, int w,
-                                  const int32_t *prev, int32_t *cur)
-{
-    const int five = qt[FF_MAX_CTX_INPUTS * 256];
-    const uint32_t mask = (1u << P.cbits) - 1;
-    int x;
-    int T = prev[0], LT = cur[0], L = prev[0], LL = 0;
-    if (c->overread > 2)                          /* is_input_end, ffv1dec.c:96-107 */
-        return -1;
-    for (x = 0; x < w; x++) {
-        const int RT = prev[ff_min(x + 1, w - 1)];
-        int ctx, sign = 0, diff, v;
-        if (!(x & 1023) && c->overread > 2)
-            return -1;
-        ctx = qt[(L - LT) & 0xFF] + qt[256 + ((LT - T) & 0xFF)] + qt[512 + ((T - RT) & 0xFF)];
-        if (five) {
-            const int TT = cur[x];
-            ctx += qt[768 + ((LL - L) & 0xFF)] + qt[1024 + ((TT - T) & 0xFF)];
-        }
-        if (ctx < 0) {
-            ctx = -ctx;
-            sign = 1;
-        }
-        diff = ffrac_get_symbol(c, D.tab, state + (size_t)ctx * FF_CONTEXT_SIZE, 1);
-        if (sign)
-            diff = -diff;
-        v = ff_wrap_sample(P, (int)(((uint32_t)ff_median3(L, L + T - LT, T) + (uint32_t)diff) & mask));
-        cur[x] = v;
-        LL = L;
-        L = v;
-        LT = T;
-        T = RT;
-    }
-    return 0;
-}
-
 /* decode_line (Golomb branch incl. run mode), ffv1dec_template.c:70-113 */
 FFGPU_HD int ff_decode_line_golomb(const FFDevParams &P, FFBitR *br, const FFDecCtx &D,
                                    const int16_t *qt, uint2 *vstate, int w,
@@ -722,22 +800,227 @@ FFGPU_HD void ff_store_line_rgb(const FFDevParams &P, uint8_t *frame, int X0, in
     }
 }
 
-/* decode_slice after the header, ffv1dec.c:304-359 */
-FFGPU_HD void ff_decode_slice(const FFDevParams &P, const FFDecSlice &d, const uint8_t *pkt,
-                              const FFDecCtx &D, FFDecResult *res)
-{
-    const uint8_t *base = pkt + d.pkt_off;
-    FFRacDec c;
-    FFBitR br;
-    int k, y, x, err = 0;
-    const int golomb = P.ac == FF_AC_GOLOMB;
+/* line iterator over the coded lines of a slice, in coding order (YCbCr: plane after plane,
+ * RGB: G,B,R[,A] interleaved per picture line) */
+typedef struct FFLineIt {
+    int k, y;          /* current coded plane / line */
+    int w, h;          /* geometry of plane k        */
+} FFLineIt;
 
-    c.buf = base;
+FFGPU_HD int ff_line_first(const FFDevParams &P, const FFDecSlice &d, FFLineIt *it)
+{
+    it->k = 0;
+    it->y = 0;
+    it->w = ff_crshift(d.w, P.cp[0].hs);
+    it->h = ff_crshift(d.h, P.cp[0].vs);
+    return it->w > 0 && it->h > 0;
+}
+
+FFGPU_HD int ff_line_next(const FFDevParams &P, const FFDecSlice &d, FFLineIt *it)
+{
+    if (P.colorspace == 0) {
+        if (++it->y < it->h)
+            return 1;
+        if (++it->k >= P.ncoded)
+            return 0;
+        it->y = 0;
+        it->w = ff_crshift(d.w, P.cp[it->k].hs);
+        it->h = ff_crshift(d.h, P.cp[it->k].vs);
+        return 1;
+    }
+    if (++it->k < P.ncoded)
+        return 1;
+    it->k = 0;
+    return ++it->y < it->h;
+}
+
+/* decode_slice after the header for the range coder, ffv1dec.c:304-359 with decode_line
+ * (ffv1dec_template.c:23-126) and get_symbol_inline (ffv1dec.c:42-64) flattened to one
+ * binary decision per loop iteration, for the same reason as in the encoder: the lanes of
+ * a warp decode different slices and must not wait for each other's long residuals. */
+FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, const uint8_t *pkt,
+                                    const FFDecCtx &D, FFDecResult *res, uint32_t *row)
+{
+    enum { PH_NEW = 0, PH_ZERO, PH_UNARY, PH_MANT, PH_SIGN };
+    const uint8_t *trans = (const uint8_t *)D.tab;
+    uint8_t *rowb = (uint8_t *)row;
+    const uint32_t mask = (1u << P.cbits) - 1;
+    FFRacDec c;
+    FFLineIt it;
+    int x, err = 0, phase = PH_NEW, cur_ctx = -1;
+    int w = 0, five = 0, sign = 0, e = 0, mi = 0;
+    uint32_t a = 0;
+    int T = 0, LT = 0, L = 0, LL = 0, RT = 0;
+    const int16_t *qt = D.qt_all;
+    int32_t *cur = D.lines;
+    const int32_t *prev = D.lines;
+    size_t sbase = 0;
+    int live;
+
+    c.buf = pkt + d.pkt_off;
     c.low = d.low;
     c.range = d.range;
     c.pos = d.pos;
     c.end = d.size;
     c.overread = d.overread;
+
+    for (int k = 0; k < P.ncoded; k++)
+        for (x = 0; x < 2 * D.line_stride; x++)
+            D.lines[(size_t)k * 2 * D.line_stride + x] = 0;
+
+    live = ff_line_first(P, d, &it);
+    x = -1;                                          /* -1: the line has to be set up */
+    while (live) {
+        int slot, s, r1, bit;
+        if (phase == PH_NEW) {
+            int ctx;
+            if (x < 0 || x == w) {
+                if (x == w) {                        /* a line is complete */
+                    if (P.colorspace != 0 && it.k == P.ncoded - 1) {
+                        const int o = (it.y & 1) ? D.line_stride : 0;
+                        ff_store_line_rgb(P, D.frame, d.x, d.y + it.y, d.w,
+                                          D.lines + o, D.lines + 2 * D.line_stride + o,
+                                          D.lines + 4 * D.line_stride + o,
+                                          P.ncoded > 3 ? D.lines + 6 * D.line_stride + o : (const int32_t *)0);
+                    }
+                    if (!ff_line_next(P, d, &it)) {
+                        live = 0;
+                        break;
+                    }
+                }
+                {
+                    const FFDevPlane cp = P.cp[it.k];
+                    int32_t *l0 = D.lines + (size_t)it.k * 2 * D.line_stride;
+                    cur = (it.y & 1) ? l0 + D.line_stride : l0;
+                    prev = (it.y & 1) ? l0 : l0 + D.line_stride;
+                    w = P.colorspace == 0 ? it.w : d.w;
+                    qt = D.qt_all + (size_t)d.qidx[cp.set] * FF_QT_STRIDE;
+                    five = qt[FF_MAX_CTX_INPUTS * 256];
+                    sbase = (size_t)P.set_base[cp.set];
+                }
+                x = 0;
+                T = prev[0];
+                LT = cur[0];
+                L = prev[0];
+                LL = 0;
+                if (c.overread > 2) {                /* is_input_end at line start */
+                    err = 1;
+                    break;
+                }
+            } else if (!(x & 1023) && c.overread > 2) {
+                err = 1;
+                break;
+            }
+            RT = prev[ff_min(x + 1, w - 1)];
+            ctx = qt[(L - LT) & 0xFF] + qt[256 + ((LT - T) & 0xFF)] + qt[512 + ((T - RT) & 0xFF)];
+            if (five)
+                ctx += qt[768 + ((LL - L) & 0xFF)] + qt[1024 + ((cur[x] - T) & 0xFF)];
+            sign = ctx < 0;
+            ctx = (int)sbase + (sign ? -ctx : ctx);
+            if (ctx != cur_ctx) {
+                if (cur_ctx >= 0)
+                    ff_row_store(row, D.rstate + (size_t)cur_ctx * FF_CONTEXT_SIZE);
+                ff_row_load(row, D.rstate + (size_t)ctx * FF_CONTEXT_SIZE);
+                cur_ctx = ctx;
+            }
+            phase = PH_ZERO;
+            e = 0;
+        }
+        slot = phase == PH_ZERO ? 0 : phase == PH_UNARY ? 1 + ff_min(e, 9) :
+               phase == PH_MANT ? 22 + ff_min(mi, 9) : 11 + ff_min(e, 10);
+        s = rowb[slot];
+        r1 = (c.range * s) >> 8;                     /* get_rac, rangecoder.h:136-152 */
+        c.range -= r1;
+        bit = c.low >= c.range;
+        rowb[slot] = trans[s + (bit ? 0 : 256)];
+        if (bit) {
+            c.low -= c.range;
+            c.range = r1;
+        }
+        if (c.range < 0x100) {                       /* refill */
+            c.range <<= 8;
+            c.low <<= 8;
+            if (c.pos < c.end)
+                c.low += c.buf[c.pos++];
+            else
+                c.overread++;
+        }
+        {
+            int done = 0, diff = 0;
+            if (phase == PH_ZERO) {
+                if (bit)
+                    done = 1;
+                else
+                    phase = PH_UNARY;
+            } else if (phase == PH_UNARY) {
+                if (bit) {
+                    if (++e > 31) {                  /* get_symbol returns AVERROR_INVALIDDATA */
+                        diff = FFRAC_SYMBOL_ERROR;
+                        done = 1;
+                    }
+                } else {
+                    a = 1;
+                    mi = e - 1;
+                    phase = e ? PH_MANT : PH_SIGN;
+                }
+            } else if (phase == PH_MANT) {
+                a += a + (uint32_t)bit;
+                if (--mi < 0)
+                    phase = PH_SIGN;
+            } else {
+                diff = bit ? -(int)a : (int)a;
+                done = 1;
+            }
+            if (done) {
+                int v;
+                if (sign)
+                    diff = -diff;
+                v = ff_wrap_sample(P, (int)(((uint32_t)ff_median3(L, L + T - LT, T) + (uint32_t)diff) & mask));
+                cur[x] = v;
+                if (P.colorspace == 0) {             /* decode_plane's store, ffv1dec.c:142-161 */
+                    const FFDevPlane cp = P.cp[it.k];
+                    uint8_t *p = D.frame + P.plane_off[cp.mem] +
+                                 (size_t)((d.y >> cp.vs) + it.y) * P.pitch[cp.mem] +
+                                 (size_t)((d.x >> cp.hs) + x) * cp.step + cp.off;
+                    if (P.sbits <= 8) {
+                        p[0] = (uint8_t)v;
+                    } else {
+                        const uint32_t o = P.packed_lsb ? (uint32_t)v & 0xFFFF
+                            : (uint32_t)((v << (16 - P.sbits)) | ((v & 0xFFFF) >> (2 * P.sbits - 16))) & 0xFFFF;
+                        p[0] = (uint8_t)o;
+                        p[1] = (uint8_t)(o >> 8);
+                    }
+                }
+                LL = L;
+                L = v;
+                LT = T;
+                T = RT;
+                x++;
+                phase = PH_NEW;
+            }
+        }
+    }
+    if (cur_ctx >= 0)
+        ff_row_store(row, D.rstate + (size_t)cur_ctx * FF_CONTEXT_SIZE);
+    /* end-of-slice check, ffv1dec.c:351-359 */
+    if (P.version > 2) {
+        uint8_t term = 129;
+        ffrac_get(&c, D.tab, &term);
+    }
+    res->end_pos = c.pos;
+    res->overread = c.overread;
+    res->error = err;
+    res->pad = 0;
+}
+
+/* decode_slice after the header, Golomb-Rice streams (ffv1dec.c:304-350) */
+FFGPU_HD void ff_decode_slice_golomb(const FFDevParams &P, const FFDecSlice &d, const uint8_t *pkt,
+                                     const FFDecCtx &D, FFDecResult *res)
+{
+    const uint8_t *base = pkt + d.pkt_off;
+    FFBitR br;
+    int k, y, x, err = 0;
+
     br.buf = base + d.golomb_start;
     br.size_bits = (int64_t)(d.size - d.golomb_start) * 8;
     br.pos = 0;
@@ -759,12 +1042,7 @@ FFGPU_HD void ff_decode_slice(const FFDevParams &P, const FFDecSlice &d, const u
             for (y = 0; y < h; y++) {
                 int32_t *cur = (y & 1) ? l1 : l0;
                 const int32_t *prev = (y & 1) ? l0 : l1;
-                int r;
-                if (golomb)
-                    r = ff_decode_line_golomb(P, &br, D, qt, D.vstate + sbase, w, prev, cur, &run_index);
-                else
-                    r = ff_decode_line_range(P, &c, D, qt, D.rstate + sbase * FF_CONTEXT_SIZE, w, prev, cur);
-                if (r < 0) {
+                if (ff_decode_line_golomb(P, &br, D, qt, D.vstate + sbase, w, prev, cur, &run_index) < 0) {
                     err = 1;
                     break;                       /* decode_plane returns, next plane still runs */
                 }
@@ -782,12 +1060,7 @@ FFGPU_HD void ff_decode_slice(const FFDevParams &P, const FFDecSlice &d, const u
                 int32_t *l1 = l0 + D.line_stride;
                 int32_t *cur = (y & 1) ? l1 : l0;
                 const int32_t *prev = (y & 1) ? l0 : l1;
-                int r;
-                if (golomb)
-                    r = ff_decode_line_golomb(P, &br, D, qt, D.vstate + sbase, d.w, prev, cur, &run_index);
-                else
-                    r = ff_decode_line_range(P, &c, D, qt, D.rstate + sbase * FF_CONTEXT_SIZE, d.w, prev, cur);
-                if (r < 0) {
+                if (ff_decode_line_golomb(P, &br, D, qt, D.vstate + sbase, d.w, prev, cur, &run_index) < 0) {
                     err = 1;
                     break;
                 }
@@ -801,15 +1074,19 @@ FFGPU_HD void ff_decode_slice(const FFDevParams &P, const FFDecSlice &d, const u
             }
         }
     }
-    /* end-of-slice check, ffv1dec.c:351-359 */
-    if (!golomb && P.version > 2) {
-        uint8_t term = 129;
-        ffrac_get(&c, D.tab, &term);
-    }
-    res->end_pos = c.pos;
-    res->overread = c.overread;
+    res->end_pos = d.pos;
+    res->overread = d.overread;
     res->error = err;
     res->pad = 0;
+}
+
+FFGPU_HD void ff_decode_slice(const FFDevParams &P, const FFDecSlice &d, const uint8_t *pkt,
+                              const FFDecCtx &D, FFDecResult *res, uint32_t *row)
+{
+    if (P.ac == FF_AC_GOLOMB)
+        ff_decode_slice_golomb(P, d, pkt, D, res);
+    else
+        ff_decode_slice_range(P, d, pkt, D, res, row);
 }
 
 #endif /* FFGPU_FFV1_SLICE_CUH */

@@ -25,6 +25,15 @@ def pytest_configure(config):
                        check=True, stdout=subprocess.DEVNULL)
 
 
+    # the product library and the CPU emulation of its device functions: rebuild when stale
+    import shutil
+    if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+        from ffmpeg_ffv2_b200 import build as b
+        b.build(force=False)
+    subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "emul")], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+
+
 def pytest_collection_modifyitems(config, items):
     try:
         import torch

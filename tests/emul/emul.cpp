@@ -114,6 +114,7 @@ extern "C" int ffv1emul_encode(void *h, const uint8_t *const planes[4], const in
     for (int i = 0; i < P.nslices; i++) {
         FFSliceRect r = { e->sl[i].x, e->sl[i].y, e->sl[i].w, e->sl[i].h };
         uint32_t ovf = 0;
+        alignas(16) uint32_t row[FF_ROW_WORDS];
         int rc = ff_enc_slice_prefix(&e->s, i, &r, keyf, 3, 0, 1, &pre[i], &e->prebytes[(size_t)i * 2048], 2048);
         if (rc < 0) return rc;
         pre[i].byte_off = (uint32_t)i * 2048;
@@ -124,7 +125,7 @@ extern "C" int ffv1emul_encode(void *h, const uint8_t *const planes[4], const in
         else
             bytes[i] = ff_encode_slice_range(e->sl[i], &e->tokens[e->sl[i].tok_off],
                                              &e->rstate[(size_t)i * P.total_ctx * FF_CONTEXT_SIZE], &e->s.cur_tab,
-                                             pre[i], e->prebytes.data(), &e->bs[e->sl[i].bs_off], &ovf);
+                                             pre[i], e->prebytes.data(), &e->bs[e->sl[i].bs_off], &ovf, row);
         if (ovf) return FFGPU_INVALIDDATA;
     }
     /* pack */
@@ -223,7 +224,8 @@ extern "C" int ffv1emul_decode(void *h, const uint8_t *pkt_in, int size, uint8_t
         FFDecCtx D;
         D.qt_all = d->qt.data(); D.tab = &d->s.cur_tab; D.rstate = rs; D.vstate = vs;
         D.lines = d->lines.data(); D.line_stride = line_stride; D.frame = frame;
-        ff_decode_slice(P, work[i], pkt.data(), D, &res[i]);
+        alignas(16) uint32_t row[FF_ROW_WORDS];
+        ff_decode_slice(P, work[i], pkt.data(), D, &res[i], row);
         if (P.ac != FF_AC_GOLOMB && P.version > 2) {
             int v = (int)work[i].size - (int)res[i].end_pos - 2 - 5 * P.ec;
             if (v) d->hs.damaged[i] = 1;          /* "bytestream end mismatching by %d" */

@@ -233,8 +233,11 @@ def test_damaged_packets_behave_like_the_reference(fmt, kw):
     for name, bad in _corrupt_cases(p1):
         ref = cc.Decoder("oracle", w, h, enc.extradata)
         dec = F.FFV1Decoder(w, h, enc.extradata)
-        ref.decode(p0)
-        dec.decode(p0)
+        if name == "payload":
+            # concealment needs a previous picture; in the other case the rectangles no slice
+            # covers are unspecified in the reference (uninitialised buffer): start from zero
+            ref.decode(p0)
+            dec.decode(p0)
         want = ref.decode(bad)
         got = dec.decode(bad)
         if name == "payload":
