@@ -253,7 +253,10 @@ def main():
 
     enc = F.FFV1Encoder(w, h, fmt, device=local, max_batch=B, pipeline_depth=3, **opts)
     dec = F.FFV1Decoder(w, h, enc.extradata, device=local, max_batch=B, pipeline_depth=3)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a real (non-default) stream: the C ABI treats a NULL stream as "use the handle's own"
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
 
     # ---- parity gate: packets byte-identical to the CPU reference, pictures restored ----
     which, kind = cpu_codec_kind()
