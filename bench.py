@@ -189,6 +189,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="pictures per step and GPU (0 = default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-groups", type=int, default=4, help="launch groups a step's pictures are split into")
+    ap.add_argument("--e2e-depth", type=int, default=4, help="launch groups in flight (e2e leg)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
 
@@ -251,8 +253,9 @@ def main():
     ho = h_out.numpy()
     ho[:] = 0
 
-    enc = F.FFV1Encoder(w, h, fmt, device=local, max_batch=B, pipeline_depth=3, **opts)
-    dec = F.FFV1Decoder(w, h, enc.extradata, device=local, max_batch=B, pipeline_depth=3)
+    # the device-resident path uses one launch group at a time: depth 1 keeps memory for big batches
+    enc = F.FFV1Encoder(w, h, fmt, device=local, max_batch=B, pipeline_depth=1, **opts)
+    dec = F.FFV1Decoder(w, h, enc.extradata, device=local, max_batch=B, pipeline_depth=1)
     # a real (non-default) stream: the C ABI treats a NULL stream as "use the handle's own"
     tstream = torch.cuda.Stream()
     torch.cuda.set_stream(tstream)
@@ -337,11 +340,11 @@ def main():
     e2e = None
     if not args.no_e2e:
         # smaller launch groups, more of them in flight: H2D, kernels and D2H overlap
-        vb = max(B // 4, 1)
+        vb = max(B // args.e2e_groups, 1)
         enc.close()
         dec.close()
-        enc = F.FFV1Encoder(w, h, fmt, device=local, max_batch=vb, pipeline_depth=4, **opts)
-        dec = F.FFV1Decoder(w, h, enc.extradata, device=local, max_batch=vb, pipeline_depth=4)
+        enc = F.FFV1Encoder(w, h, fmt, device=local, max_batch=vb, pipeline_depth=args.e2e_depth, **opts)
+        dec = F.FFV1Decoder(w, h, enc.extradata, device=local, max_batch=vb, pipeline_depth=args.e2e_depth)
 
         def e2e_step():
             out_pk, i = [], 0
@@ -406,7 +409,7 @@ def main():
                "ms_per_step": 1e3 * e2e_t / K,
                "api": "ffgpu_ffv1_encode_send_frame/receive_packet + "
                       "ffgpu_ffv1_decode_send_packet/receive_frame, pinned host buffers",
-               "frames_per_launch_group": vb, "launch_groups_in_flight": 4,
+               "frames_per_launch_group": vb, "launch_groups_in_flight": args.e2e_depth,
                "gpu_launches": int(enc.launches + dec.launches - e2e_launch0)}
 
     # ---- CPU baseline beside it (rank 0, N == 1): the reference's slice-threaded CPU codec ----

@@ -241,8 +241,8 @@ class FFV1Encoder:
             raise FFGpuError("encode_device_fetch", r, _err())
         return self._buf[:n.value].tobytes()
 
-    ENC_KERNELS = ["symbolize", "fill_state", "code", "pack_slice_scan", "pack_frame_scan",
-                   "pack_gather"]
+    ENC_KERNELS = ["symbolize", "fill_state", "sort", "code", "pack_slice_scan",
+                   "pack_frame_scan", "pack_gather"]
 
     def profile(self, enable=True):
         r = lib().ffgpu_ffv1_encoder_profile(self.h, int(enable))
@@ -357,7 +357,7 @@ class FFV1Decoder:
             raise FFGpuError("receive_frame", r, _err())
         return o
 
-    DEC_KERNELS = ["init_state", "decode"]
+    DEC_KERNELS = ["init_state", "sort", "decode"]
 
     def profile(self, enable=True):
         r = lib().ffgpu_ffv1_decoder_profile(self.h, int(enable))

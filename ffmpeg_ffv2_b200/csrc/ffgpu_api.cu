@@ -115,6 +115,10 @@ struct EncJob {
     uint32_t *d_slice_bytes, *d_slice_off, *d_pkt_size, *d_pkt_off, *d_overflow;
     uint8_t *d_pkt;
     uint8_t *d_frame_set, *d_frame_key;
+    uint32_t *d_weight, *d_weight_sorted, *d_order;
+    void *d_sort_tmp;
+    size_t sort_tmp_bytes;
+    int pkt_owned;
     /* pinned host */
     uint8_t *h_frame_set, *h_frame_key;
     uint32_t *h_pkt_size, *h_pkt_off, *h_overflow;
@@ -146,6 +150,7 @@ struct ffgpu_encoder {
     FFRacTables *d_tab;
     FFRacPrefix *d_prefix;
     uint8_t *d_prefix_bytes;
+    uint32_t *d_iota;           /* 0,1,2,... values for the slice sort */
     uint8_t *d_state_shared;    /* carried-state streams: one arena for all groups */
     PrefixSet sets[NPREFIX_SETS];
     EncJob jobs[MAX_DEPTH];
@@ -161,8 +166,11 @@ static int enc_free_job(EncJob *j)
 {
     cudaFree(j->d_frames); cudaFree(j->d_tokens); cudaFree(j->d_state); cudaFree(j->d_bs);
     cudaFree(j->d_slice_bytes); cudaFree(j->d_slice_off); cudaFree(j->d_pkt_size);
-    cudaFree(j->d_pkt_off); cudaFree(j->d_overflow); cudaFree(j->d_pkt);
+    cudaFree(j->d_pkt_off); cudaFree(j->d_overflow);
+    if (j->pkt_owned)
+        cudaFree(j->d_pkt);
     cudaFree(j->d_frame_set); cudaFree(j->d_frame_key);
+    cudaFree(j->d_weight); cudaFree(j->d_weight_sorted); cudaFree(j->d_order); cudaFree(j->d_sort_tmp);
     cudaFreeHost(j->h_frame_set); cudaFreeHost(j->h_frame_key); cudaFreeHost(j->h_pkt_size);
     cudaFreeHost(j->h_pkt_off); cudaFreeHost(j->h_overflow); cudaFreeHost(j->h_pkt);
     free(j->pts); free(j->key);
@@ -201,6 +209,17 @@ static int enc_device_init(ffgpu_encoder *e)
     if (!e->intra) {
         CK(cudaMalloc(&e->d_state_shared, state_frame));
     }
+    {
+        const size_t n = (size_t)e->max_batch * P->nslices;
+        uint32_t *iota = (uint32_t *)malloc(n * sizeof(uint32_t));
+        if (!iota)
+            return fail(FFGPU_ENOMEM, "out of memory");
+        for (size_t i = 0; i < n; i++)
+            iota[i] = (uint32_t)i;
+        CK(cudaMalloc(&e->d_iota, n * sizeof(uint32_t)));
+        CK(cudaMemcpy(e->d_iota, iota, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        free(iota);
+    }
     for (int i = 0; i < e->depth; i++) {
         EncJob *j = &e->jobs[i];
         const size_t B = (size_t)e->max_batch;
@@ -216,7 +235,19 @@ static int enc_device_init(ffgpu_encoder *e)
         CK(cudaMalloc(&j->d_pkt_size, B * sizeof(uint32_t)));
         CK(cudaMalloc(&j->d_pkt_off, (B + 1) * sizeof(uint32_t)));
         CK(cudaMalloc(&j->d_overflow, sizeof(uint32_t)));
-        CK(cudaMalloc(&j->d_pkt, B * P->pkt_stride));
+        /* the packed output reuses the token array: tokens are dead once stage B has run,
+         * and a frame's tokens (4 bytes per sample) are larger than its bitstream arena */
+        if (P->frame_tokens * sizeof(uint32_t) >= P->pkt_stride) {
+            j->d_pkt = (uint8_t *)j->d_tokens;
+        } else {                                    /* tiny slices / 17-bit samples */
+            CK(cudaMalloc(&j->d_pkt, B * P->pkt_stride));
+            j->pkt_owned = 1;
+        }
+        CK(cudaMalloc(&j->d_weight, B * P->nslices * sizeof(uint32_t)));
+        CK(cudaMalloc(&j->d_weight_sorted, B * P->nslices * sizeof(uint32_t)));
+        CK(cudaMalloc(&j->d_order, B * P->nslices * sizeof(uint32_t)));
+        j->sort_tmp_bytes = ffk_sort_tmp_bytes((int)(B * P->nslices));
+        CK(cudaMalloc(&j->d_sort_tmp, j->sort_tmp_bytes));
         CK(cudaMalloc(&j->d_frame_set, B));
         CK(cudaMalloc(&j->d_frame_key, B));
         CK(cudaHostAlloc(&j->h_frame_set, B, cudaHostAllocDefault));
@@ -268,10 +299,11 @@ extern "C" int ffgpu_ffv1_encode_init(ffgpu_encoder **penc, const ffgpu_enc_opti
     e->prefix_stride = e->s.version > 2 ? 64 : 4096;
     if (e->intra) {
         /* enough pictures per group for ~48k resident slice coders, bounded by memory */
-        const size_t per_frame = e->P.frame_bytes + e->P.frame_tokens * 4 + e->P.frame_bs + e->P.pkt_stride +
+        const size_t per_frame = e->P.frame_bytes + e->P.frame_tokens * 4 + e->P.frame_bs +
                                  (size_t)e->P.nslices * e->P.total_ctx * FF_CONTEXT_SIZE;
-        int b = opt->max_batch > 0 ? opt->max_batch : (49152 + e->P.nslices - 1) / e->P.nslices;
-        size_t cap = ((size_t)12 << 30) / (per_frame ? per_frame : 1);
+        /* enough pictures per group to keep ~64k slice coders (2k warps) resident */
+        int b = opt->max_batch > 0 ? opt->max_batch : (65536 + e->P.nslices - 1) / e->P.nslices;
+        size_t cap = ((size_t)16 << 30) / (per_frame ? per_frame : 1);
         if (b > 256) b = 256;
         if (opt->max_batch <= 0 && (size_t)b > cap) b = (int)cap;
         if (b < 1) b = 1;
@@ -384,6 +416,12 @@ static void enc_fill_dev(const ffgpu_encoder *e, const EncJob *j, const uint8_t 
     E->overflow = j->d_overflow;
     E->pkt = j->d_pkt;
     E->state_per_frame = e->intra;
+    E->weight = j->d_weight;
+    E->weight_sorted = j->d_weight_sorted;
+    E->iota = e->d_iota;
+    E->order = j->d_order;
+    E->sort_tmp = j->d_sort_tmp;
+    E->sort_tmp_bytes = j->sort_tmp_bytes;
 }
 
 /* enqueue the kernel chain + result download of a filled group */
@@ -686,7 +724,7 @@ extern "C" int ffgpu_ffv1_encode_close(ffgpu_encoder *e)
         for (int i = 0; i < MAX_DEPTH; i++)
             enc_free_job(&e->jobs[i]);
         cudaFree(e->d_slices); cudaFree(e->d_qt); cudaFree(e->d_tab); cudaFree(e->d_prefix);
-        cudaFree(e->d_prefix_bytes); cudaFree(e->d_state_shared);
+        cudaFree(e->d_prefix_bytes); cudaFree(e->d_state_shared); cudaFree(e->d_iota);
     }
     free(e->h_slices);
     free(e->extradata);
@@ -720,6 +758,9 @@ struct DecJob {
     int32_t *d_lines;
     uint8_t *d_frames;
     FFDecResult *d_result, *h_result;
+    uint32_t *d_weight, *d_weight_sorted, *d_order;
+    void *d_sort_tmp;
+    size_t sort_tmp_bytes;
     DecFrameMeta *meta;
 };
 
@@ -738,6 +779,7 @@ struct ffgpu_decoder {
     uint8_t *d_initial;
     uint8_t *d_state_shared;
     uint8_t *d_prev;            /* last output picture, for concealment */
+    uint32_t *d_iota;
     int have_prev;
     DecJob jobs[MAX_DEPTH];
     int fill, head, flushing;
@@ -751,6 +793,7 @@ static void dec_free_job(DecJob *j)
     cudaFreeHost(j->h_pkt); cudaFree(j->d_pkt); cudaFreeHost(j->h_work); cudaFree(j->d_work);
     cudaFreeHost(j->h_nslices); cudaFree(j->d_nslices); cudaFree(j->d_state); cudaFree(j->d_lines);
     cudaFree(j->d_frames); cudaFree(j->d_result); cudaFreeHost(j->h_result);
+    cudaFree(j->d_weight); cudaFree(j->d_weight_sorted); cudaFree(j->d_order); cudaFree(j->d_sort_tmp);
     free(j->meta);
     if (j->done) cudaEventDestroy(j->done);
     if (j->stream) cudaStreamDestroy(j->stream);
@@ -782,8 +825,8 @@ static int dec_setup_stream(ffgpu_decoder *d)
     d->intra = d->s.version > 2 && d->s.intra;
     if (d->intra) {
         const size_t per_frame = d->P.frame_bytes * 2 + (size_t)d->max_slices * d->P.total_ctx * FF_CONTEXT_SIZE;
-        int b = d->opt.max_batch > 0 ? d->opt.max_batch : (49152 + d->max_slices - 1) / d->max_slices;
-        size_t cap = ((size_t)12 << 30) / (per_frame ? per_frame : 1);
+        int b = d->opt.max_batch > 0 ? d->opt.max_batch : (65536 + d->max_slices - 1) / d->max_slices;
+        size_t cap = ((size_t)16 << 30) / (per_frame ? per_frame : 1);
         if (b > 256) b = 256;
         if (d->opt.max_batch <= 0 && (size_t)b > cap) b = (int)cap;
         if (b < 1) b = 1;
@@ -839,6 +882,17 @@ static int dec_device_init(ffgpu_decoder *d)
         CK(cudaMalloc(&d->d_state_shared, state_frame));
     CK(cudaMalloc(&d->d_prev, P->frame_bytes));
     CK(cudaMemset(d->d_prev, 0, P->frame_bytes));
+    {
+        const size_t n = (size_t)d->max_batch * d->max_slices;
+        uint32_t *iota = (uint32_t *)malloc(n * sizeof(uint32_t));
+        if (!iota)
+            return fail(FFGPU_ENOMEM, "out of memory");
+        for (size_t i = 0; i < n; i++)
+            iota[i] = (uint32_t)i;
+        CK(cudaMalloc(&d->d_iota, n * sizeof(uint32_t)));
+        CK(cudaMemcpy(d->d_iota, iota, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        free(iota);
+    }
     for (int i = 0; i < d->depth; i++) {
         DecJob *j = &d->jobs[i];
         const size_t B = (size_t)d->max_batch;
@@ -858,6 +912,11 @@ static int dec_device_init(ffgpu_decoder *d)
         CK(cudaMemset(j->d_frames, 0, B * P->frame_bytes));
         CK(cudaMalloc(&j->d_result, B * d->max_slices * sizeof(FFDecResult)));
         CK(cudaHostAlloc(&j->h_result, B * d->max_slices * sizeof(FFDecResult), cudaHostAllocDefault));
+        CK(cudaMalloc(&j->d_weight, B * d->max_slices * sizeof(uint32_t)));
+        CK(cudaMalloc(&j->d_weight_sorted, B * d->max_slices * sizeof(uint32_t)));
+        CK(cudaMalloc(&j->d_order, B * d->max_slices * sizeof(uint32_t)));
+        j->sort_tmp_bytes = ffk_sort_tmp_bytes((int)(B * d->max_slices));
+        CK(cudaMalloc(&j->d_sort_tmp, j->sort_tmp_bytes));
         j->meta = (DecFrameMeta *)calloc(B, sizeof(DecFrameMeta));
         if (!j->meta)
             return fail(FFGPU_ENOMEM, "out of memory");
@@ -933,6 +992,13 @@ static void dec_fill_dev(const ffgpu_decoder *d, const DecJob *j, uint8_t *frame
     D->max_slices = d->max_slices;
     D->max_ctx = d->max_ctx;
     D->state_per_frame = d->intra;
+    D->qt_count = d->s.qt_count;
+    D->weight = j->d_weight;
+    D->weight_sorted = j->d_weight_sorted;
+    D->iota = d->d_iota;
+    D->order = j->d_order;
+    D->sort_tmp = j->d_sort_tmp;
+    D->sort_tmp_bytes = j->sort_tmp_bytes;
 }
 
 static int download_picture(const ffgpu_decoder *d, const uint8_t *d_frame, const ffgpu_picture_out *dst,
@@ -1315,7 +1381,7 @@ extern "C" int ffgpu_ffv1_decode_close(ffgpu_decoder *d)
         for (int i = 0; i < MAX_DEPTH; i++)
             dec_free_job(&d->jobs[i]);
         cudaFree(d->d_qt); cudaFree(d->d_tab); cudaFree(d->d_initial); cudaFree(d->d_state_shared);
-        cudaFree(d->d_prev);
+        cudaFree(d->d_prev); cudaFree(d->d_iota);
     }
     free(d->h_slices);
     ff_stream_free(&d->s);

@@ -785,10 +785,11 @@ int ff_fill_dev_params(const FFStream *s, int encoder, FFDevParams *P, FFDevSlic
         d->tok_off = tok;
         d->ntok = samples;
         tok += samples;
-        /* slice bitstream arena: 3x the raw size of the coded samples plus room for the
-         * header prefix; an overflow is reported as "encoded frame too large" */
+        /* slice bitstream arena: twice the information content of the coded samples
+         * (cbits per sample) plus room for the header prefix; an overflow is reported as
+         * "encoded frame too large" like the reference's own guard */
         d->bs_off = bs;
-        d->bs_cap = (uint32_t)((((uint64_t)samples * ((P->cbits + 7) / 8) * 3 + 4096 + 15) & ~15ULL));
+        d->bs_cap = (uint32_t)(((((uint64_t)samples * P->cbits + 7) / 8) * 2 + 2048 + 15) & ~15ULL);
         bs += d->bs_cap;
     }
     P->frame_tokens = tok;

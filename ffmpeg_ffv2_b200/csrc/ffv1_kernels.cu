@@ -21,13 +21,15 @@
  *               packet of the group
  */
 #include <cuda_runtime.h>
+#include <cub/block/block_reduce.cuh>
 #include <cub/block/block_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 
 #include "../../include/ffgpu.h"
 #include "ffv1_launch.h"
 #include "ffv1_slice.cuh"
 
-#define CODE_THREADS 128
+#define CODE_THREADS FF_CODE_THREADS
 #define SYM_THREADS  256
 
 static inline int launch_ok(void)
@@ -45,13 +47,22 @@ static inline void mark(void **events, int i, cudaStream_t st)
 __global__ void __launch_bounds__(SYM_THREADS)
 k_symbolize(const FFDevParams P, const FFDevSlice *__restrict__ slices,
             const uint8_t *__restrict__ frames, const int16_t *__restrict__ qt,
-            uint32_t *__restrict__ tokens)
+            uint32_t *__restrict__ tokens, uint32_t *__restrict__ weight)
 {
+    typedef cub::BlockReduce<uint32_t, SYM_THREADS> Reduce;
+    __shared__ typename Reduce::TempStorage tmp;
     const FFDevSlice sl = slices[blockIdx.x];
     const uint8_t *frame = frames + (size_t)blockIdx.y * P.frame_bytes;
     uint32_t *tok = tokens + (size_t)blockIdx.y * P.frame_tokens + sl.tok_off;
-    for (uint32_t i = blockIdx.z * SYM_THREADS + threadIdx.x; i < sl.ntok; i += gridDim.z * SYM_THREADS)
-        tok[i] = ff_symbolize_index(P, sl, frame, qt, i);
+    uint32_t wsum = 0;
+    for (uint32_t i = blockIdx.z * SYM_THREADS + threadIdx.x; i < sl.ntok; i += gridDim.z * SYM_THREADS) {
+        const uint32_t t = ff_symbolize_index(P, sl, frame, qt, i);
+        tok[i] = t;
+        wsum += ff_token_weight(t);
+    }
+    wsum = Reduce(tmp).Sum(wsum);
+    if (threadIdx.x == 0 && weight)
+        atomicAdd(&weight[(size_t)blockIdx.y * P.nslices + blockIdx.x], wsum);
 }
 
 /* ---------------- adaptive state reset ---------------- */
@@ -75,23 +86,22 @@ __global__ void k_fill_state(uint2 *__restrict__ state, size_t words_per_frame,
 __global__ void __launch_bounds__(CODE_THREADS)
 k_code_range(const FFDevParams P, const FFEncDev E, int nframes)
 {
-    __shared__ FFRacTables tab;
-    __shared__ uint32_t rows[CODE_THREADS][FF_ROW_WORDS];
     for (int i = threadIdx.x; i < (int)sizeof(FFRacTables) / 4; i += CODE_THREADS)
-        ((uint32_t *)&tab)[i] = ((const uint32_t *)E.tab)[i];
+        ((uint32_t *)&ff_s_tab)[i] = ((const uint32_t *)E.tab)[i];
     __syncthreads();
-    const int gid = blockIdx.x * CODE_THREADS + threadIdx.x;
-    if (gid >= nframes * P.nslices)
+    const int tid = blockIdx.x * CODE_THREADS + threadIdx.x;
+    if (tid >= nframes * P.nslices)
         return;
+    const int gid = E.order ? (int)E.order[tid] : tid;      /* heaviest slices first */
     const int f = gid / P.nslices, s = gid - f * P.nslices;
     const FFDevSlice sl = E.slices[s];
     const size_t st_slot = (size_t)(E.state_per_frame ? f : 0) * P.nslices + s;
     uint32_t ovf = 0;
     const uint32_t n = ff_encode_slice_range(
         sl, E.tokens + (size_t)f * P.frame_tokens + sl.tok_off,
-        E.state + st_slot * P.total_ctx * FF_CONTEXT_SIZE, &tab,
+        E.state + st_slot * P.total_ctx * FF_CONTEXT_SIZE, &ff_s_tab,
         E.prefix[(size_t)E.frame_prefix_set[f] * P.nslices + s], E.prefix_bytes,
-        E.bs + (size_t)f * P.frame_bs + sl.bs_off, &ovf, rows[threadIdx.x]);
+        E.bs + (size_t)f * P.frame_bs + sl.bs_off, &ovf, 0);
     E.slice_bytes[gid] = n;
     if (ovf)
         atomicOr(E.overflow, 1u);
@@ -100,9 +110,10 @@ k_code_range(const FFDevParams P, const FFEncDev E, int nframes)
 __global__ void __launch_bounds__(CODE_THREADS)
 k_code_golomb(const FFDevParams P, const FFEncDev E, int nframes)
 {
-    const int gid = blockIdx.x * CODE_THREADS + threadIdx.x;
-    if (gid >= nframes * P.nslices)
+    const int tid = blockIdx.x * CODE_THREADS + threadIdx.x;
+    if (tid >= nframes * P.nslices)
         return;
+    const int gid = E.order ? (int)E.order[tid] : tid;
     const int f = gid / P.nslices, s = gid - f * P.nslices;
     const FFDevSlice sl = E.slices[s];
     const size_t st_slot = (size_t)(E.state_per_frame ? f : 0) * P.nslices + s;
@@ -183,7 +194,9 @@ extern "C" int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nfr
         if (z < 1) z = 1;
         if (z > 64) z = 64;
         dim3 grid(P->nslices, nframes, z);
-        k_symbolize<<<grid, SYM_THREADS, 0, st>>>(*P, E->slices, E->frames, E->qt, E->tokens);
+        if (E->weight)
+            cudaMemsetAsync(E->weight, 0, sizeof(uint32_t) * (size_t)nframes * P->nslices, st);
+        k_symbolize<<<grid, SYM_THREADS, 0, st>>>(*P, E->slices, E->frames, E->qt, E->tokens, E->weight);
         mark(E->events, FFK_SYMBOLIZE + 1, st);
         launches++;
         if (!launch_ok()) return FFGPU_EXTERNAL;
@@ -203,6 +216,13 @@ extern "C" int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nfr
         launches++;
         if (!launch_ok()) return FFGPU_EXTERNAL;
     }
+    /* longest slices first: sort (decision count, slice id) descending */
+    if (E->weight && E->order) {
+        size_t tmp = E->sort_tmp_bytes;
+        cub::DeviceRadixSort::SortPairsDescending(E->sort_tmp, tmp, E->weight, E->weight_sorted, E->iota,
+                                                  E->order, nframes * P->nslices, 0, 32, st);
+    }
+    mark(E->events, FFK_SORT + 1, st);
     /* stage B */
     {
         const int total = nframes * P->nslices;
@@ -258,17 +278,31 @@ __global__ void k_dec_init_state(const FFDevParams P, const FFDecDev D, int golo
     }
 }
 
+/* sort key of a decode work item: its byte count (0 for absent / skipped slices) */
+__global__ void k_dec_keys(const FFDecDev D, int nframes)
+{
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= nframes * D.max_slices)
+        return;
+    const int f = gid / D.max_slices, s = gid - f * D.max_slices;
+    uint32_t k = 0;
+    if (s < D.nslices[f] && !D.work[gid].skip)
+        k = D.work[gid].size;
+    D.weight[gid] = k;
+}
+
 __global__ void __launch_bounds__(CODE_THREADS)
 k_decode(const FFDevParams P, const FFDecDev D, int nframes)
 {
-    __shared__ FFRacTables tab;
-    __shared__ uint32_t rows[CODE_THREADS][FF_ROW_WORDS];
     for (int i = threadIdx.x; i < (int)sizeof(FFRacTables) / 4; i += CODE_THREADS)
-        ((uint32_t *)&tab)[i] = ((const uint32_t *)D.tab)[i];
+        ((uint32_t *)&ff_s_tab)[i] = ((const uint32_t *)D.tab)[i];
+    for (int i = threadIdx.x; i < D.qt_count * FF_QT_STRIDE / 2; i += CODE_THREADS)
+        ((uint32_t *)ff_s_qt)[i] = ((const uint32_t *)D.qt)[i];
     __syncthreads();
-    const int gid = blockIdx.x * CODE_THREADS + threadIdx.x;
-    if (gid >= nframes * D.max_slices)
+    const int tid = blockIdx.x * CODE_THREADS + threadIdx.x;
+    if (tid >= nframes * D.max_slices)
         return;
+    const int gid = D.order ? (int)D.order[tid] : tid;       /* largest slices first */
     const int f = gid / D.max_slices, s = gid - f * D.max_slices;
     FFDecResult r;
     r.end_pos = 0; r.overread = 0; r.error = 0; r.pad = 1;      /* pad=1: not decoded */
@@ -278,16 +312,24 @@ k_decode(const FFDevParams P, const FFDecDev D, int nframes)
             const size_t slot = (size_t)(D.state_per_frame ? f : 0) * D.max_slices + s;
             FFDecCtx C;
             C.qt_all = D.qt;
-            C.tab = &tab;
+            C.tab = &ff_s_tab;
             C.rstate = D.state + slot * P.total_ctx * FF_CONTEXT_SIZE;
             C.vstate = (uint2 *)D.state + slot * P.total_ctx;
             C.lines = D.lines + (size_t)gid * P.ncoded * 2 * D.line_stride;
             C.line_stride = D.line_stride;
             C.frame = D.frames + (size_t)f * P.frame_bytes;
-            ff_decode_slice(P, w, D.pkt, C, &r, rows[threadIdx.x]);
+            ff_decode_slice(P, w, D.pkt, C, &r, 0);
         }
     }
     D.result[gid] = r;
+}
+
+extern "C" size_t ffk_sort_tmp_bytes(int n)
+{
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairsDescending((void *)0, bytes, (const uint32_t *)0, (uint32_t *)0,
+                                              (const uint32_t *)0, (uint32_t *)0, n);
+    return bytes + 256;
 }
 
 extern "C" int ffk_decode_group(const FFDevParams *P, const FFDecDev *D, int nframes, ffk_stream stream)
@@ -300,10 +342,18 @@ extern "C" int ffk_decode_group(const FFDevParams *P, const FFDecDev *D, int nfr
     k_dec_init_state<<<g0, 256, 0, st>>>(*P, *D, P->ac == FF_AC_GOLOMB);
     mark(D->events, FFK_DEC_INIT_STATE + 1, st);
     const int total = nframes * D->max_slices;
-    k_decode<<<(total + CODE_THREADS - 1) / CODE_THREADS, CODE_THREADS, 0, st>>>(*P, *D, nframes);
+    if (D->weight && D->order) {
+        size_t tmp = D->sort_tmp_bytes;
+        k_dec_keys<<<(total + 255) / 256, 256, 0, st>>>(*D, nframes);
+        cub::DeviceRadixSort::SortPairsDescending(D->sort_tmp, tmp, D->weight, D->weight_sorted, D->iota,
+                                                  D->order, total, 0, 32, st);
+    }
+    mark(D->events, FFK_DEC_SORT + 1, st);
+    k_decode<<<(total + CODE_THREADS - 1) / CODE_THREADS, CODE_THREADS,
+               (size_t)D->qt_count * FF_QT_STRIDE * sizeof(int16_t), st>>>(*P, *D, nframes);
     mark(D->events, FFK_DECODE + 1, st);
     if (!launch_ok()) return FFGPU_EXTERNAL;
-    return 2;
+    return 3;
 }
 
 /* ---------------- concealment ---------------- */

@@ -34,15 +34,25 @@ typedef struct FFEncDev {
     uint32_t *overflow;             /* [1] sticky flag                                  */
     uint8_t *pkt;                   /* packed output of the whole group                 */
     int state_per_frame;            /* 1: state[frame][slice] (intra), 0: state[slice]   */
+    /* longest-first scheduling of stage B: per-slice decision counts from stage A, sorted */
+    uint32_t *weight;               /* [nframes][nslices]                               */
+    uint32_t *weight_sorted;        /* scratch                                          */
+    const uint32_t *iota;           /* 0,1,2,...                                        */
+    uint32_t *order;                /* [nframes*nslices] slice ids, heaviest first      */
+    void *sort_tmp;
+    size_t sort_tmp_bytes;
     void **events;                  /* optional cudaEvent_t[FFK_ENC_KERNELS + 1]: recorded    */
                                     /* before the first and after every kernel (profiling)  */
 } FFEncDev;
 
+/* temp bytes cub's radix sort needs for n (key,value) pairs */
+size_t ffk_sort_tmp_bytes(int n);
+
 /* kernels of one encode group, in launch order */
-enum { FFK_SYMBOLIZE = 0, FFK_FILL_STATE, FFK_CODE, FFK_PACK_SLICE_SCAN, FFK_PACK_FRAME_SCAN,
-       FFK_PACK_GATHER, FFK_ENC_KERNELS };
+enum { FFK_SYMBOLIZE = 0, FFK_FILL_STATE, FFK_SORT, FFK_CODE, FFK_PACK_SLICE_SCAN,
+       FFK_PACK_FRAME_SCAN, FFK_PACK_GATHER, FFK_ENC_KERNELS };
 /* kernels of one decode group */
-enum { FFK_DEC_INIT_STATE = 0, FFK_DECODE, FFK_DEC_KERNELS };
+enum { FFK_DEC_INIT_STATE = 0, FFK_DEC_SORT, FFK_DECODE, FFK_DEC_KERNELS };
 
 int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nframes, ffk_stream stream);
 
@@ -62,6 +72,13 @@ typedef struct FFDecDev {
     int max_slices;
     int max_ctx;                    /* contexts per set (largest quant table)           */
     int state_per_frame;
+    int qt_count;                   /* quant table sets of the stream                   */
+    uint32_t *weight;               /* [nframes*max_slices] slice byte counts            */
+    uint32_t *weight_sorted;
+    const uint32_t *iota;
+    uint32_t *order;                /* work items, largest slice first                  */
+    void *sort_tmp;
+    size_t sort_tmp_bytes;
     void **events;                  /* optional cudaEvent_t[FFK_DEC_KERNELS + 1]          */
 } FFDecDev;
 

@@ -208,6 +208,26 @@ FFGPU_HD void ff_enc_resume(FFRacEnc *c, const FFRacPrefix &pre, const uint8_t *
  * same slot) so that the per-decision state read/update is an LDS/STS instead of a global
  * round trip; it is written back only when the context changes. */
 #define FF_ROW_WORDS 9
+#define FF_CODE_THREADS 128      /* threads per block of the slice-coder kernels */
+
+#if defined(__CUDACC__)
+/* statically named shared memory, so that the device code below addresses it with LDS/STS
+ * and immediate offsets instead of generic pointers */
+static __shared__ FFRacTables ff_s_tab;
+static __shared__ uint32_t ff_s_rows[FF_CODE_THREADS * FF_ROW_WORDS];
+extern __shared__ int16_t ff_s_qt[];             /* decoder: qt_count quant table sets */
+#endif
+#if defined(__CUDA_ARCH__)
+#define FF_TAB(i)   (((const uint8_t *)&ff_s_tab)[i])
+#define FF_ROWB(i)  (((uint8_t *)ff_s_rows)[threadIdx.x * (FF_ROW_WORDS * 4) + (i)])
+#define FF_ROWW     (&ff_s_rows[threadIdx.x * FF_ROW_WORDS])
+#define FF_QT(set_off, i) (ff_s_qt[(set_off) + (i)])
+#else
+#define FF_TAB(i)   (((const uint8_t *)tab_)[i])
+#define FF_ROWB(i)  (((uint8_t *)row_)[i])
+#define FF_ROWW     (row_)
+#define FF_QT(set_off, i) (qt_all_[(set_off) + (i)])
+#endif
 
 typedef struct
 #if defined(__CUDACC__)
@@ -267,37 +287,38 @@ FFGPU_HD void ffrac_enc_shift1(FFRacEnc *c)
  *   2e+2             sign                      state[11 + min(e,10)]
  * returns the slice's byte count; *overflow != 0 if the arena was too small */
 FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *tokens,
-                                        uint8_t *state, const FFRacTables *tab,
+                                        uint8_t *state, const FFRacTables *tab_,
                                         const FFRacPrefix &pre, const uint8_t *pre_bytes,
-                                        uint8_t *out, uint32_t *overflow, uint32_t *row)
+                                        uint8_t *out, uint32_t *overflow, uint32_t *row_)
 {
-    const uint8_t *trans = (const uint8_t *)tab;     /* one[256] followed by zero[256] */
-    uint8_t *rowb = (uint8_t *)row;
     FFRacEnc c;
     const uint32_t n = sl.ntok;
     uint32_t i = 0, nb;
-    uint32_t tok_next = n ? tokens[0] : 0;
+    /* two tokens of look-ahead hide the L1/L2 latency of the token stream */
+    uint32_t tok_a = n > 0 ? tokens[0] : 0, tok_b = n > 1 ? tokens[1] : 0;
     int cur_ctx = -1;
     int a = 0, e = 0, neg = 0, step = 0, nsteps = 0;
+    (void)tab_; (void)row_;
 
     ff_enc_resume(&c, pre, pre_bytes, out, sl.bs_cap);
     for (;;) {
-        int slot, bit, s, r1, rb;
+        int slot, bit, s, r1, rb, um, mm;
         if (step == nsteps) {                        /* fetch the next residual */
             uint32_t tok;
             int ctx, diff;
             if (i == n)
                 break;
-            tok = tok_next;
+            tok = tok_a;
+            tok_a = tok_b;
             i++;
-            if (i < n)
-                tok_next = tokens[i];
+            if (i + 1 < n)
+                tok_b = tokens[i + 1];
             ctx = (int)(tok & FF_TOKEN_CTX_MASK);
             diff = (int32_t)tok >> FF_TOKEN_CTX_BITS;
             if (ctx != cur_ctx) {
                 if (cur_ctx >= 0)
-                    ff_row_store(row, state + (size_t)cur_ctx * FF_CONTEXT_SIZE);
-                ff_row_load(row, state + (size_t)ctx * FF_CONTEXT_SIZE);
+                    ff_row_store(FF_ROWW, state + (size_t)cur_ctx * FF_CONTEXT_SIZE);
+                ff_row_load(FF_ROWW, state + (size_t)ctx * FF_CONTEXT_SIZE);
                 cur_ctx = ctx;
             }
             a = diff < 0 ? -diff : diff;
@@ -306,27 +327,17 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
             nsteps = a ? 2 * e + 3 : 1;
             step = 0;
         }
-        if (step == 0) {
-            slot = 0;
-            bit = a == 0;
-        } else if (step <= e) {
-            slot = 1 + ff_min(step - 1, 9);
-            bit = 1;
-        } else if (step == e + 1) {
-            slot = 1 + ff_min(e, 9);
-            bit = 0;
-        } else if (step <= 2 * e + 1) {
-            const int j = 2 * e + 1 - step;
-            slot = 22 + ff_min(j, 9);
-            bit = (a >> j) & 1;
-        } else {
-            slot = 11 + ff_min(e, 10);
-            bit = neg;
-        }
-        s = rowb[slot];
+        /* (slot, bit) of decision `step`, branch-free */
+        um = ff_min(step - 1, 9);                    /* unary index, steps 1..e+1      */
+        mm = 2 * e + 1 - step;                       /* mantissa bit, steps e+2..2e+1  */
+        slot = step == 0 ? 0 : step <= e + 1 ? 1 + um : step <= 2 * e + 1 ? 22 + ff_min(mm, 9)
+                                                                          : 11 + ff_min(e, 10);
+        bit = step == 0 ? (a == 0) : step <= e ? 1 : step == e + 1 ? 0
+                                 : step <= 2 * e + 1 ? ((a >> (mm & 31)) & 1) : neg;
+        s = FF_ROWB(slot);
         r1 = (c.range * s) >> 8;                     /* put_rac, rangecoder.h:104-121 */
         rb = c.range - r1;
-        rowb[slot] = trans[s + (bit ? 0 : 256)];
+        FF_ROWB(slot) = FF_TAB(s + (bit ? 0 : 256));
         c.low += bit ? rb : 0;
         c.range = bit ? r1 : rb;
         if (c.range < 0x100)
@@ -334,10 +345,19 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
         step++;
     }
     if (cur_ctx >= 0)
-        ff_row_store(row, state + (size_t)cur_ctx * FF_CONTEXT_SIZE);
-    nb = ffrac_enc_finish(&c, tab, 1);               /* ffv1enc.c:1242 */
+        ff_row_store(FF_ROWW, state + (size_t)cur_ctx * FF_CONTEXT_SIZE);
+    nb = ffrac_enc_finish(&c, tab_, 1);              /* ffv1enc.c:1242 */
     *overflow = c.overflow;
     return nb;
+}
+
+/* number of binary decisions the range coder spends on a token: the slice's total is its
+ * serial cost and drives the longest-first scheduling of stage B */
+FFGPU_HD uint32_t ff_token_weight(uint32_t tok)
+{
+    const int diff = (int32_t)tok >> FF_TOKEN_CTX_BITS;
+    const uint32_t a = (uint32_t)(diff < 0 ? -diff : diff);
+    return a ? 2u * (uint32_t)ffrac_ilog2(a) + 3u : 1u;
 }
 
 /* ------------------------------------------------------------------ */
@@ -839,11 +859,11 @@ FFGPU_HD int ff_line_next(const FFDevParams &P, const FFDecSlice &d, FFLineIt *i
  * binary decision per loop iteration, for the same reason as in the encoder: the lanes of
  * a warp decode different slices and must not wait for each other's long residuals. */
 FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, const uint8_t *pkt,
-                                    const FFDecCtx &D, FFDecResult *res, uint32_t *row)
+                                    const FFDecCtx &D, FFDecResult *res, uint32_t *row_)
 {
     enum { PH_NEW = 0, PH_ZERO, PH_UNARY, PH_MANT, PH_SIGN };
-    const uint8_t *trans = (const uint8_t *)D.tab;
-    uint8_t *rowb = (uint8_t *)row;
+    const FFRacTables *tab_ = D.tab;
+    const int16_t *qt_all_ = D.qt_all;
     const uint32_t mask = (1u << P.cbits) - 1;
     FFRacDec c;
     FFLineIt it;
@@ -851,11 +871,12 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
     int w = 0, five = 0, sign = 0, e = 0, mi = 0;
     uint32_t a = 0;
     int T = 0, LT = 0, L = 0, LL = 0, RT = 0;
-    const int16_t *qt = D.qt_all;
+    int qo = 0;                                      /* offset of the line's quant table set */
     int32_t *cur = D.lines;
     const int32_t *prev = D.lines;
     size_t sbase = 0;
     int live;
+    (void)tab_; (void)row_; (void)qt_all_;
 
     c.buf = pkt + d.pkt_off;
     c.low = d.low;
@@ -894,8 +915,8 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
                     cur = (it.y & 1) ? l0 + D.line_stride : l0;
                     prev = (it.y & 1) ? l0 : l0 + D.line_stride;
                     w = P.colorspace == 0 ? it.w : d.w;
-                    qt = D.qt_all + (size_t)d.qidx[cp.set] * FF_QT_STRIDE;
-                    five = qt[FF_MAX_CTX_INPUTS * 256];
+                    qo = d.qidx[cp.set] * FF_QT_STRIDE;
+                    five = FF_QT(qo, FF_MAX_CTX_INPUTS * 256);
                     sbase = (size_t)P.set_base[cp.set];
                 }
                 x = 0;
@@ -912,15 +933,16 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
                 break;
             }
             RT = prev[ff_min(x + 1, w - 1)];
-            ctx = qt[(L - LT) & 0xFF] + qt[256 + ((LT - T) & 0xFF)] + qt[512 + ((T - RT) & 0xFF)];
+            ctx = FF_QT(qo, (L - LT) & 0xFF) + FF_QT(qo, 256 + ((LT - T) & 0xFF)) +
+                  FF_QT(qo, 512 + ((T - RT) & 0xFF));
             if (five)
-                ctx += qt[768 + ((LL - L) & 0xFF)] + qt[1024 + ((cur[x] - T) & 0xFF)];
+                ctx += FF_QT(qo, 768 + ((LL - L) & 0xFF)) + FF_QT(qo, 1024 + ((cur[x] - T) & 0xFF));
             sign = ctx < 0;
             ctx = (int)sbase + (sign ? -ctx : ctx);
             if (ctx != cur_ctx) {
                 if (cur_ctx >= 0)
-                    ff_row_store(row, D.rstate + (size_t)cur_ctx * FF_CONTEXT_SIZE);
-                ff_row_load(row, D.rstate + (size_t)ctx * FF_CONTEXT_SIZE);
+                    ff_row_store(FF_ROWW, D.rstate + (size_t)cur_ctx * FF_CONTEXT_SIZE);
+                ff_row_load(FF_ROWW, D.rstate + (size_t)ctx * FF_CONTEXT_SIZE);
                 cur_ctx = ctx;
             }
             phase = PH_ZERO;
@@ -928,11 +950,11 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
         }
         slot = phase == PH_ZERO ? 0 : phase == PH_UNARY ? 1 + ff_min(e, 9) :
                phase == PH_MANT ? 22 + ff_min(mi, 9) : 11 + ff_min(e, 10);
-        s = rowb[slot];
+        s = FF_ROWB(slot);
         r1 = (c.range * s) >> 8;                     /* get_rac, rangecoder.h:136-152 */
         c.range -= r1;
         bit = c.low >= c.range;
-        rowb[slot] = trans[s + (bit ? 0 : 256)];
+        FF_ROWB(slot) = FF_TAB(s + (bit ? 0 : 256));
         if (bit) {
             c.low -= c.range;
             c.range = r1;
@@ -1001,7 +1023,7 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
         }
     }
     if (cur_ctx >= 0)
-        ff_row_store(row, D.rstate + (size_t)cur_ctx * FF_CONTEXT_SIZE);
+        ff_row_store(FF_ROWW, D.rstate + (size_t)cur_ctx * FF_CONTEXT_SIZE);
     /* end-of-slice check, ffv1dec.c:351-359 */
     if (P.version > 2) {
         uint8_t term = 129;

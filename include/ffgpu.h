@@ -202,8 +202,8 @@ uint64_t ffgpu_ffv1_decoder_launches(const ffgpu_decoder *dec);
 /* Profiling of the *_device entry points: when enabled, CUDA events are recorded around
  * every kernel of the launch group; *_kernel_ms() returns the elapsed times of the last
  * group (after the stream was synchronised), in launch order:
- *   encoder: symbolize, fill_state, code, pack_slice_scan, pack_frame_scan, pack_gather
- *   decoder: init_state, decode
+ *   encoder: symbolize, fill_state, sort, code, pack_slice_scan, pack_frame_scan, pack_gather
+ *   decoder: init_state, sort, decode
  * and the number of kernels, or a negative error. */
 int ffgpu_ffv1_encoder_profile(ffgpu_encoder *enc, int enable);
 int ffgpu_ffv1_encoder_kernel_ms(ffgpu_encoder *enc, float *ms, int n);
