@@ -782,9 +782,9 @@ int ff_fill_dev_params(const FFStream *s, int encoder, FFDevParams *P, FFDevSlic
             d->nseg = 1;
             samples = (uint32_t)r.w * r.h * n;
         }
-        d->tok_off = tok;
+        d->tok_off = tok;                     /* 16-byte aligned: stage B streams 4 tokens per cp.async */
         d->ntok = samples;
-        tok += samples;
+        tok += (samples + 3) & ~3u;
         /* slice bitstream arena: twice the information content of the coded samples
          * (cbits per sample) plus room for the header prefix; an overflow is reported as
          * "encoded frame too large" like the reference's own guard */

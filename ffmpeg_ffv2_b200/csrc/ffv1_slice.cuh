@@ -208,6 +208,31 @@ FFGPU_HD void ff_enc_resume(FFRacEnc *c, const FFRacPrefix &pre, const uint8_t *
  * same slot) so that the per-decision state read/update is an LDS/STS instead of a global
  * round trip; it is written back only when the context changes. */
 #define FF_ROW_WORDS 9
+
+typedef struct
+#if defined(__CUDACC__)
+__align__(16)
+#else
+__attribute__((aligned(16)))
+#endif
+FFU128 { uint32_t x, y, z, w; } FFU128;
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ void ff_cp_async16(void *smem, const void *gmem)
+{
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void ff_cp_async_commit(void)
+{
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void ff_cp_async_wait(void)
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+#endif
 #define FF_CODE_THREADS 128      /* threads per block of the slice-coder kernels */
 
 #if defined(__CUDACC__)
@@ -216,6 +241,11 @@ FFGPU_HD void ff_enc_resume(FFRacEnc *c, const FFRacPrefix &pre, const uint8_t *
 static __shared__ FFRacTables ff_s_tab;
 static __shared__ uint32_t ff_s_rows[FF_CODE_THREADS * FF_ROW_WORDS];
 extern __shared__ int16_t ff_s_qt[];             /* decoder: qt_count quant table sets */
+/* stage B token stream: per lane a ring of 16-byte chunks filled by cp.async (LDGSTS) six
+ * chunks ahead of the read position, so a lane's DRAM/L2 miss never stalls its warp */
+#define FF_TOK_CHUNKS 8
+#define FF_TOK_AHEAD  6
+static __shared__ FFU128 ff_s_tok[FF_TOK_CHUNKS * FF_CODE_THREADS];
 #endif
 #if defined(__CUDA_ARCH__)
 #define FF_TAB(i)   (((const uint8_t *)&ff_s_tab)[i])
@@ -229,13 +259,7 @@ extern __shared__ int16_t ff_s_qt[];             /* decoder: qt_count quant tabl
 #define FF_QT(set_off, i) (qt_all_[(set_off) + (i)])
 #endif
 
-typedef struct
-#if defined(__CUDACC__)
-__align__(16)
-#else
-__attribute__((aligned(16)))
-#endif
-FFU128 { uint32_t x, y, z, w; } FFU128;
+
 
 FFGPU_HD void ff_row_load(uint32_t *row, const uint8_t *g)
 {
@@ -294,12 +318,18 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
     FFRacEnc c;
     const uint32_t n = sl.ntok;
     uint32_t i = 0, nb;
-    /* two tokens of look-ahead hide the L1/L2 latency of the token stream */
-    uint32_t tok_a = n > 0 ? tokens[0] : 0, tok_b = n > 1 ? tokens[1] : 0;
     int cur_ctx = -1;
     int a = 0, e = 0, neg = 0, step = 0, nsteps = 0;
     (void)tab_; (void)row_;
 
+#if defined(__CUDA_ARCH__)
+    const uint32_t nchunks = (n + 3) >> 2;
+    for (uint32_t ch = 0; ch < FF_TOK_AHEAD; ch++) {
+        if (ch < nchunks)
+            ff_cp_async16(&ff_s_tok[ch * FF_CODE_THREADS + threadIdx.x], tokens + 4 * ch);
+        ff_cp_async_commit();
+    }
+#endif
     ff_enc_resume(&c, pre, pre_bytes, out, sl.bs_cap);
     for (;;) {
         int slot, bit, s, r1, rb, um, mm;
@@ -308,11 +338,21 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
             int ctx, diff;
             if (i == n)
                 break;
-            tok = tok_a;
-            tok_a = tok_b;
+#if defined(__CUDA_ARCH__)
+            if ((i & 3) == 0) {                      /* entering chunk i/4: issue chunk i/4 + AHEAD */
+                const uint32_t ch = (i >> 2) + FF_TOK_AHEAD;
+                if (ch < nchunks)
+                    ff_cp_async16(&ff_s_tok[(ch & (FF_TOK_CHUNKS - 1)) * FF_CODE_THREADS + threadIdx.x],
+                                  tokens + 4 * ch);
+                ff_cp_async_commit();
+                ff_cp_async_wait<FF_TOK_AHEAD>();
+            }
+            tok = ((const uint32_t *)&ff_s_tok[((i >> 2) & (FF_TOK_CHUNKS - 1)) * FF_CODE_THREADS +
+                                               threadIdx.x])[i & 3];
+#else
+            tok = tokens[i];
+#endif
             i++;
-            if (i + 1 < n)
-                tok_b = tokens[i + 1];
             ctx = (int)(tok & FF_TOKEN_CTX_MASK);
             diff = (int32_t)tok >> FF_TOKEN_CTX_BITS;
             if (ctx != cur_ctx) {
@@ -871,6 +911,7 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
     int w = 0, five = 0, sign = 0, e = 0, mi = 0;
     uint32_t a = 0;
     int T = 0, LT = 0, L = 0, LL = 0, RT = 0;
+    int q0 = 0, q1 = 0, q2 = 0, q3 = 0;
     int qo = 0;                                      /* offset of the line's quant table set */
     int32_t *cur = D.lines;
     const int32_t *prev = D.lines;
@@ -924,6 +965,11 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
                 LT = cur[0];
                 L = prev[0];
                 LL = 0;
+                /* look-ahead on the previous line: q0..q3 = prev[min(x+1..x+4, w-1)] */
+                q0 = prev[ff_min(1, w - 1)];
+                q1 = prev[ff_min(2, w - 1)];
+                q2 = prev[ff_min(3, w - 1)];
+                q3 = prev[ff_min(4, w - 1)];
                 if (c.overread > 2) {                /* is_input_end at line start */
                     err = 1;
                     break;
@@ -932,7 +978,11 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
                 err = 1;
                 break;
             }
-            RT = prev[ff_min(x + 1, w - 1)];
+            RT = q0;
+            q0 = q1;
+            q1 = q2;
+            q2 = q3;
+            q3 = prev[ff_min(x + 5, w - 1)];
             ctx = FF_QT(qo, (L - LT) & 0xFF) + FF_QT(qo, 256 + ((LT - T) & 0xFF)) +
                   FF_QT(qo, 512 + ((T - RT) & 0xFF));
             if (five)
