@@ -234,7 +234,7 @@ def main():
 
     w, h, fmt, opts = wl["w"], wl["h"], wl["fmt"], wl["opts"]
     frame_bytes, planes = F.frame_layout(fmt, w, h)
-    B = args.batch or (48 if args.workload == "C2" else 16)
+    B = args.batch or (192 if args.workload == "C2" else 16)
     distinct = min(8, B)
 
     # ---- synthetic input: `distinct` pictures (this rank's share of the stream), cycled ----

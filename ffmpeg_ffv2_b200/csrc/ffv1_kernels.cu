@@ -65,6 +65,98 @@ k_symbolize(const FFDevParams P, const FFDevSlice *__restrict__ slices,
         atomicAdd(&weight[(size_t)blockIdx.y * P.nslices + blockIdx.x], wsum);
 }
 
+/* Stage A for the planar YCbCr / gray (+alpha) layouts: one CTA per slice, one warp per
+ * sample row, 32 consecutive samples per step.  Every lane loads its own sample and the one
+ * above it (two coalesced row reads); the left / top-left / top-right neighbours come from
+ * the adjacent lanes by warp shuffle, only the lanes at a 32-sample seam or at the slice
+ * border issue an extra load.  The context quantiser lives in shared memory. */
+__global__ void __launch_bounds__(SYM_THREADS)
+k_symbolize_planar(const FFDevParams P, const FFDevSlice *__restrict__ slices,
+                   const uint8_t *__restrict__ frames, const int16_t *__restrict__ qt,
+                   uint32_t *__restrict__ tokens, uint32_t *__restrict__ weight)
+{
+    typedef cub::BlockReduce<uint32_t, SYM_THREADS> Reduce;
+    __shared__ typename Reduce::TempStorage tmp;
+    __shared__ int16_t sq[FF_QT_STRIDE];
+    {
+        const uint32_t *src = (const uint32_t *)(qt + (size_t)P.set_qidx[0] * FF_QT_STRIDE);
+        for (int i = threadIdx.x; i < FF_QT_STRIDE / 2; i += SYM_THREADS)
+            ((uint32_t *)sq)[i] = src[i];
+    }
+    __syncthreads();
+    const FFDevSlice sl = slices[blockIdx.x];
+    const uint8_t *frame = frames + (size_t)blockIdx.y * P.frame_bytes;
+    uint32_t *tok = tokens + (size_t)blockIdx.y * P.frame_tokens + sl.tok_off;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nrows_step = (SYM_THREADS / 32) * gridDim.z;
+    const int five = sq[FF_MAX_CTX_INPUTS * 256];
+    const int wide = P.sbits > 8;
+    const int shift = P.packed_lsb ? 0 : 16 - P.sbits;
+    const int cbits = P.cbits;
+    uint32_t wsum = 0, base = 0;
+
+#define SAMPLE(rowp, xx) ((int)(int16_t)(wide ? (*(const uint16_t *)((rowp) + 2 * (size_t)(xx)) >> shift) \
+                                              : (rowp)[(size_t)(xx) * step]))
+    for (int k = 0; k < P.ncoded; k++) {
+        const int mem = P.cp[k].mem, step = P.cp[k].step;
+        const int w = sl.seg_w[k], h = sl.seg_lines[k];
+        const int ctx_base = P.set_base[P.cp[k].set];
+        const size_t pitch = (size_t)P.pitch[mem];
+        const uint8_t *pbase = frame + P.plane_off[mem] + (size_t)(sl.y >> P.cp[k].vs) * pitch +
+                               (size_t)(sl.x >> P.cp[k].hs) * step + P.cp[k].off;
+        for (int y = blockIdx.z * (SYM_THREADS / 32) + warp; y < h; y += nrows_step) {
+            const uint8_t *r0 = pbase + (size_t)y * pitch;
+            const uint8_t *r1 = r0 - pitch, *r2 = r1 - pitch;
+            for (int x0 = 0; x0 < w; x0 += 32) {
+                const int x = x0 + lane;
+                const bool valid = x < w;
+                const int cur = valid ? SAMPLE(r0, x) : 0;
+                const int T = (valid && y >= 1) ? SAMPLE(r1, x) : 0;
+                int L = __shfl_up_sync(0xffffffffu, cur, 1);
+                int LT = __shfl_up_sync(0xffffffffu, T, 1);
+                int RT = __shfl_down_sync(0xffffffffu, T, 1);
+                int LL = __shfl_up_sync(0xffffffffu, cur, 2);
+                if (!valid)
+                    continue;
+                if (x == 0) {                       /* left border: ffv1enc.c:287 */
+                    L = T;
+                    LT = y >= 2 ? SAMPLE(r2, 0) : 0;
+                } else if (lane == 0) {             /* seam between two 32-sample steps */
+                    L = SAMPLE(r0, x - 1);
+                    LT = y >= 1 ? SAMPLE(r1, x - 1) : 0;
+                }
+                if (x + 1 >= w)                     /* right border: ffv1enc.c:288 */
+                    RT = T;
+                else if (lane == 31)
+                    RT = y >= 1 ? SAMPLE(r1, x + 1) : 0;
+                int ctx = sq[(L - LT) & 0xFF] + sq[256 + ((LT - T) & 0xFF)] + sq[512 + ((T - RT) & 0xFF)];
+                if (five) {
+                    if (x < 2)
+                        LL = x == 1 ? (y >= 1 ? SAMPLE(r1, 0) : 0) : 0;
+                    else if (lane < 2)
+                        LL = SAMPLE(r0, x - 2);
+                    const int TT = y >= 2 ? SAMPLE(r2, x) : 0;
+                    ctx += sq[768 + ((LL - L) & 0xFF)] + sq[1024 + ((TT - T) & 0xFF)];
+                }
+                int diff = cur - ff_median3(L, L + T - LT, T);
+                if (ctx < 0) {
+                    ctx = -ctx;
+                    diff = -diff;
+                }
+                diff = ff_fold(diff, cbits);
+                const uint32_t t = ((uint32_t)diff << FF_TOKEN_CTX_BITS) | (uint32_t)(ctx_base + ctx);
+                tok[base + (uint32_t)y * w + x] = t;
+                wsum += ff_token_weight(t);
+            }
+        }
+        base += (uint32_t)w * h;
+    }
+#undef SAMPLE
+    wsum = Reduce(tmp).Sum(wsum);
+    if (threadIdx.x == 0 && weight)
+        atomicAdd(&weight[(size_t)blockIdx.y * P.nslices + blockIdx.x], wsum);
+}
+
 /* ---------------- adaptive state reset ---------------- */
 /* fills the state arenas of the frames flagged as key frames with a 64-bit pattern
  * (range coder: 128 in every byte; Golomb: {drift 0, error_sum 4, bias 0, count 1}) */
@@ -196,7 +288,17 @@ extern "C" int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nfr
         dim3 grid(P->nslices, nframes, z);
         if (E->weight)
             cudaMemsetAsync(E->weight, 0, sizeof(uint32_t) * (size_t)nframes * P->nslices, st);
-        k_symbolize<<<grid, SYM_THREADS, 0, st>>>(*P, E->slices, E->frames, E->qt, E->tokens, E->weight);
+        if (P->colorspace == 0) {
+            /* rows of the largest plane per z-block: 8 warps take 8 rows per pass */
+            int zr = (P->height / P->nv + 63) / 64;
+            if (zr < 1) zr = 1;
+            if (zr > 32) zr = 32;
+            dim3 g2(P->nslices, nframes, zr);
+            k_symbolize_planar<<<g2, SYM_THREADS, 0, st>>>(*P, E->slices, E->frames, E->qt, E->tokens,
+                                                           E->weight);
+        } else {
+            k_symbolize<<<grid, SYM_THREADS, 0, st>>>(*P, E->slices, E->frames, E->qt, E->tokens, E->weight);
+        }
         mark(E->events, FFK_SYMBOLIZE + 1, st);
         launches++;
         if (!launch_ok()) return FFGPU_EXTERNAL;
@@ -291,6 +393,20 @@ __global__ void k_dec_keys(const FFDecDev D, int nframes)
     D.weight[gid] = k;
 }
 
+/* whole-arena reset for streams without initial-state tables: every key frame's slices get
+ * the same 16-byte pattern */
+__global__ void k_dec_fill_state(uint4 *__restrict__ state, size_t vec_per_frame, const FFDecDev D,
+                                 uint4 pattern)
+{
+    const int f = blockIdx.y;
+    if (!D.work[(size_t)f * D.max_slices].key_frame)
+        return;
+    uint4 *p = state + (D.state_per_frame ? (size_t)f * vec_per_frame : 0);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < vec_per_frame;
+         i += (size_t)gridDim.x * blockDim.x)
+        p[i] = pattern;
+}
+
 __global__ void __launch_bounds__(CODE_THREADS)
 k_decode(const FFDevParams P, const FFDecDev D, int nframes)
 {
@@ -339,7 +455,19 @@ extern "C" int ffk_decode_group(const FFDevParams *P, const FFDecDev *D, int nfr
         return FFGPU_EINVAL;
     dim3 g0(D->max_slices, nframes);
     mark(D->events, 0, st);
-    k_dec_init_state<<<g0, 256, 0, st>>>(*P, *D, P->ac == FF_AC_GOLOMB);
+    if (!D->initial &&
+        ((size_t)D->max_slices * P->total_ctx * (P->ac == FF_AC_GOLOMB ? 8 : FF_CONTEXT_SIZE)) % 16 == 0) {
+        const int golomb = P->ac == FF_AC_GOLOMB;
+        const size_t vec = (size_t)D->max_slices * P->total_ctx * (golomb ? 8 : FF_CONTEXT_SIZE) / 16;
+        int bx = (int)((vec + 255) / 256);
+        if (bx > 1024) bx = 1024;
+        dim3 g1(bx, nframes);
+        const uint4 pat = golomb ? make_uint4(FF_VLC_INIT_LO, FF_VLC_INIT_HI, FF_VLC_INIT_LO, FF_VLC_INIT_HI)
+                                 : make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+        k_dec_fill_state<<<g1, 256, 0, st>>>((uint4 *)D->state, vec, *D, pat);
+    } else {
+        k_dec_init_state<<<g0, 256, 0, st>>>(*P, *D, P->ac == FF_AC_GOLOMB);
+    }
     mark(D->events, FFK_DEC_INIT_STATE + 1, st);
     const int total = nframes * D->max_slices;
     if (D->weight && D->order) {

@@ -901,22 +901,27 @@ FFGPU_HD int ff_line_next(const FFDevParams &P, const FFDecSlice &d, FFLineIt *i
 FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, const uint8_t *pkt,
                                     const FFDecCtx &D, FFDecResult *res, uint32_t *row_)
 {
-    enum { PH_NEW = 0, PH_ZERO, PH_UNARY, PH_MANT, PH_SIGN };
     const FFRacTables *tab_ = D.tab;
     const int16_t *qt_all_ = D.qt_all;
     const uint32_t mask = (1u << P.cbits) - 1;
+    const int use32 = P.use32;
+    /* how a finished sample reaches the picture: 0 at the end of the line (RGB), 1 one byte,
+     * 2 one little-endian u16, 3 u16 with the MSB-aligned replication of ffv1dec.c:158 */
+    const int smode = P.colorspace ? 0 : P.sbits <= 8 ? 1 : P.packed_lsb ? 2 : 3;
+    const int shl = 16 - P.sbits, shr = 2 * P.sbits - 16;
     FFRacDec c;
     FFLineIt it;
-    int x, err = 0, phase = PH_NEW, cur_ctx = -1;
-    int w = 0, five = 0, sign = 0, e = 0, mi = 0;
+    int x, err = 0, cur_ctx = -1, need_new = 1;
+    int w = 0, five = 0, sign = 0, e = 0, mi = 0, slot = 0;
     uint32_t a = 0;
     int T = 0, LT = 0, L = 0, LL = 0, RT = 0;
     int q0 = 0, q1 = 0, q2 = 0, q3 = 0;
     int qo = 0;                                      /* offset of the line's quant table set */
     int32_t *cur = D.lines;
     const int32_t *prev = D.lines;
-    size_t sbase = 0;
-    int live;
+    uint8_t *outp = D.frame;
+    int ostep = 0;
+    int sbase = 0;
     (void)tab_; (void)row_; (void)qt_all_;
 
     c.buf = pkt + d.pkt_off;
@@ -930,40 +935,46 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
         for (x = 0; x < 2 * D.line_stride; x++)
             D.lines[(size_t)k * 2 * D.line_stride + x] = 0;
 
-    live = ff_line_first(P, d, &it);
+    if (!ff_line_first(P, d, &it))
+        goto finish;
     x = -1;                                          /* -1: the line has to be set up */
-    while (live) {
-        int slot, s, r1, bit;
-        if (phase == PH_NEW) {
+    for (;;) {
+        int s, r1, bit, done, diff;
+        if (need_new) {
             int ctx;
             if (x < 0 || x == w) {
                 if (x == w) {                        /* a line is complete */
-                    if (P.colorspace != 0 && it.k == P.ncoded - 1) {
+                    if (smode == 0 && it.k == P.ncoded - 1) {
                         const int o = (it.y & 1) ? D.line_stride : 0;
                         ff_store_line_rgb(P, D.frame, d.x, d.y + it.y, d.w,
                                           D.lines + o, D.lines + 2 * D.line_stride + o,
                                           D.lines + 4 * D.line_stride + o,
                                           P.ncoded > 3 ? D.lines + 6 * D.line_stride + o : (const int32_t *)0);
                     }
-                    if (!ff_line_next(P, d, &it)) {
-                        live = 0;
+                    if (!ff_line_next(P, d, &it))
                         break;
-                    }
                 }
                 {
+                    /* everything that is constant along the line is computed here once */
                     const FFDevPlane cp = P.cp[it.k];
                     int32_t *l0 = D.lines + (size_t)it.k * 2 * D.line_stride;
                     cur = (it.y & 1) ? l0 + D.line_stride : l0;
                     prev = (it.y & 1) ? l0 : l0 + D.line_stride;
-                    w = P.colorspace == 0 ? it.w : d.w;
+                    w = smode ? it.w : d.w;
                     qo = d.qidx[cp.set] * FF_QT_STRIDE;
                     five = FF_QT(qo, FF_MAX_CTX_INPUTS * 256);
-                    sbase = (size_t)P.set_base[cp.set];
+                    sbase = P.set_base[cp.set];
+                    if (smode) {
+                        outp = D.frame + P.plane_off[cp.mem] +
+                               (size_t)((d.y >> cp.vs) + it.y) * P.pitch[cp.mem] +
+                               (size_t)(d.x >> cp.hs) * cp.step + cp.off;
+                        ostep = cp.step;
+                    }
                 }
                 x = 0;
                 T = prev[0];
                 LT = cur[0];
-                L = prev[0];
+                L = T;
                 LL = 0;
                 /* look-ahead on the previous line: q0..q3 = prev[min(x+1..x+4, w-1)] */
                 q0 = prev[ff_min(1, w - 1)];
@@ -988,28 +999,25 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
             if (five)
                 ctx += FF_QT(qo, 768 + ((LL - L) & 0xFF)) + FF_QT(qo, 1024 + ((cur[x] - T) & 0xFF));
             sign = ctx < 0;
-            ctx = (int)sbase + (sign ? -ctx : ctx);
+            ctx = sbase + (sign ? -ctx : ctx);
             if (ctx != cur_ctx) {
                 if (cur_ctx >= 0)
                     ff_row_store(FF_ROWW, D.rstate + (size_t)cur_ctx * FF_CONTEXT_SIZE);
                 ff_row_load(FF_ROWW, D.rstate + (size_t)ctx * FF_CONTEXT_SIZE);
                 cur_ctx = ctx;
             }
-            phase = PH_ZERO;
-            e = 0;
+            need_new = 0;
+            slot = 0;
         }
-        slot = phase == PH_ZERO ? 0 : phase == PH_UNARY ? 1 + ff_min(e, 9) :
-               phase == PH_MANT ? 22 + ff_min(mi, 9) : 11 + ff_min(e, 10);
+        /* one binary decision: get_rac + refill, rangecoder.h:123-152 */
         s = FF_ROWB(slot);
-        r1 = (c.range * s) >> 8;                     /* get_rac, rangecoder.h:136-152 */
+        r1 = (c.range * s) >> 8;
         c.range -= r1;
         bit = c.low >= c.range;
         FF_ROWB(slot) = FF_TAB(s + (bit ? 0 : 256));
-        if (bit) {
-            c.low -= c.range;
-            c.range = r1;
-        }
-        if (c.range < 0x100) {                       /* refill */
+        c.low -= bit ? c.range : 0;
+        c.range = bit ? r1 : c.range;
+        if (c.range < 0x100) {
             c.range <<= 8;
             c.low <<= 8;
             if (c.pos < c.end)
@@ -1017,61 +1025,60 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
             else
                 c.overread++;
         }
-        {
-            int done = 0, diff = 0;
-            if (phase == PH_ZERO) {
-                if (bit)
-                    done = 1;
-                else
-                    phase = PH_UNARY;
-            } else if (phase == PH_UNARY) {
-                if (bit) {
-                    if (++e > 31) {                  /* get_symbol returns AVERROR_INVALIDDATA */
-                        diff = FFRAC_SYMBOL_ERROR;
-                        done = 1;
-                    }
-                } else {
-                    a = 1;
-                    mi = e - 1;
-                    phase = e ? PH_MANT : PH_SIGN;
-                }
-            } else if (phase == PH_MANT) {
-                a += a + (uint32_t)bit;
-                if (--mi < 0)
-                    phase = PH_SIGN;
-            } else {
-                diff = bit ? -(int)a : (int)a;
+        /* get_symbol_inline (ffv1dec.c:42-64) as a walk over the state slots:
+         * 0 zero flag | 1..10 unary exponent | 22..31 mantissa | 11..21 sign */
+        done = 0;
+        diff = 0;
+        if (slot == 0) {
+            if (bit)
                 done = 1;
+            else {
+                slot = 1;
+                e = 0;
             }
-            if (done) {
-                int v;
-                if (sign)
-                    diff = -diff;
-                v = ff_wrap_sample(P, (int)(((uint32_t)ff_median3(L, L + T - LT, T) + (uint32_t)diff) & mask));
-                cur[x] = v;
-                if (P.colorspace == 0) {             /* decode_plane's store, ffv1dec.c:142-161 */
-                    const FFDevPlane cp = P.cp[it.k];
-                    uint8_t *p = D.frame + P.plane_off[cp.mem] +
-                                 (size_t)((d.y >> cp.vs) + it.y) * P.pitch[cp.mem] +
-                                 (size_t)((d.x >> cp.hs) + x) * cp.step + cp.off;
-                    if (P.sbits <= 8) {
-                        p[0] = (uint8_t)v;
-                    } else {
-                        const uint32_t o = P.packed_lsb ? (uint32_t)v & 0xFFFF
-                            : (uint32_t)((v << (16 - P.sbits)) | ((v & 0xFFFF) >> (2 * P.sbits - 16))) & 0xFFFF;
-                        p[0] = (uint8_t)o;
-                        p[1] = (uint8_t)(o >> 8);
-                    }
+        } else if (slot < 11) {
+            if (bit) {
+                if (++e > 31) {                      /* get_symbol returns AVERROR_INVALIDDATA */
+                    diff = FFRAC_SYMBOL_ERROR;
+                    done = 1;
                 }
-                LL = L;
-                L = v;
-                LT = T;
-                T = RT;
-                x++;
-                phase = PH_NEW;
+                slot = 1 + ff_min(e, 9);
+            } else {
+                a = 1;
+                mi = e - 1;
+                slot = e ? 22 + ff_min(mi, 9) : 11;
             }
+        } else if (slot >= 22) {
+            a += a + (uint32_t)bit;
+            mi--;
+            slot = mi < 0 ? 11 + ff_min(e, 10) : 22 + ff_min(mi, 9);
+        } else {
+            diff = bit ? -(int)a : (int)a;
+            done = 1;
+        }
+        if (done) {
+            int v;
+            diff = sign ? -diff : diff;
+            v = (int)(((uint32_t)ff_median3(L, L + T - LT, T) + (uint32_t)diff) & mask);
+            v = use32 ? v : (int)(int16_t)v;
+            cur[x] = v;
+            if (smode == 1) {                        /* decode_plane's store, ffv1dec.c:142-161 */
+                *outp = (uint8_t)v;
+            } else if (smode == 2) {
+                *(uint16_t *)outp = (uint16_t)v;
+            } else if (smode == 3) {
+                *(uint16_t *)outp = (uint16_t)((v << shl) | ((v & 0xFFFF) >> shr));
+            }
+            outp += ostep;
+            LL = L;
+            L = v;
+            LT = T;
+            T = RT;
+            x++;
+            need_new = 1;
         }
     }
+finish:
     if (cur_ctx >= 0)
         ff_row_store(FF_ROWW, D.rstate + (size_t)cur_ctx * FF_CONTEXT_SIZE);
     /* end-of-slice check, ffv1dec.c:351-359 */
