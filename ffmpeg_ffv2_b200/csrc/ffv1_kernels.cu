@@ -31,6 +31,7 @@
 
 #define CODE_THREADS FF_CODE_THREADS
 #define SYM_THREADS  256
+#define SYM_ROWS     4      /* rows a warp symbolizes per step (stage A, planar) */
 
 static inline int launch_ok(void)
 {
@@ -97,6 +98,9 @@ k_symbolize_planar(const FFDevParams P, const FFDevSlice *__restrict__ slices,
 
 #define SAMPLE(rowp, xx) ((int)(int16_t)(wide ? (*(const uint16_t *)((rowp) + 2 * (size_t)(xx)) >> shift) \
                                               : (rowp)[(size_t)(xx) * step]))
+    /* each warp takes groups of SYM_ROWS consecutive rows: the SYM_ROWS + 1 row loads of a
+     * step are independent and all in flight together (memory-level parallelism), and the
+     * row above a sample is the previous row of the same group */
     for (int k = 0; k < P.ncoded; k++) {
         const int mem = P.cp[k].mem, step = P.cp[k].step;
         const int w = sl.seg_w[k], h = sl.seg_lines[k];
@@ -104,49 +108,63 @@ k_symbolize_planar(const FFDevParams P, const FFDevSlice *__restrict__ slices,
         const size_t pitch = (size_t)P.pitch[mem];
         const uint8_t *pbase = frame + P.plane_off[mem] + (size_t)(sl.y >> P.cp[k].vs) * pitch +
                                (size_t)(sl.x >> P.cp[k].hs) * step + P.cp[k].off;
-        for (int y = blockIdx.z * (SYM_THREADS / 32) + warp; y < h; y += nrows_step) {
-            const uint8_t *r0 = pbase + (size_t)y * pitch;
-            const uint8_t *r1 = r0 - pitch, *r2 = r1 - pitch;
+        const int ngroups = (h + SYM_ROWS - 1) / SYM_ROWS;
+        for (int g = blockIdx.z * (SYM_THREADS / 32) + warp; g < ngroups; g += nrows_step) {
+            const int y0 = g * SYM_ROWS;
             for (int x0 = 0; x0 < w; x0 += 32) {
                 const int x = x0 + lane;
                 const bool valid = x < w;
-                const int cur = valid ? SAMPLE(r0, x) : 0;
-                const int T = (valid && y >= 1) ? SAMPLE(r1, x) : 0;
-                int L = __shfl_up_sync(0xffffffffu, cur, 1);
-                int LT = __shfl_up_sync(0xffffffffu, T, 1);
-                int RT = __shfl_down_sync(0xffffffffu, T, 1);
-                int LL = __shfl_up_sync(0xffffffffu, cur, 2);
-                if (!valid)
-                    continue;
-                if (x == 0) {                       /* left border: ffv1enc.c:287 */
-                    L = T;
-                    LT = y >= 2 ? SAMPLE(r2, 0) : 0;
-                } else if (lane == 0) {             /* seam between two 32-sample steps */
-                    L = SAMPLE(r0, x - 1);
-                    LT = y >= 1 ? SAMPLE(r1, x - 1) : 0;
+                int v[SYM_ROWS + 1];                 /* rows y0-1 .. y0+SYM_ROWS-1 at column x */
+#pragma unroll
+                for (int j = 0; j <= SYM_ROWS; j++) {
+                    const int yy = y0 - 1 + j;
+                    v[j] = (valid && yy >= 0 && yy < h) ? SAMPLE(pbase + (size_t)yy * pitch, x) : 0;
                 }
-                if (x + 1 >= w)                     /* right border: ffv1enc.c:288 */
-                    RT = T;
-                else if (lane == 31)
-                    RT = y >= 1 ? SAMPLE(r1, x + 1) : 0;
-                int ctx = sq[(L - LT) & 0xFF] + sq[256 + ((LT - T) & 0xFF)] + sq[512 + ((T - RT) & 0xFF)];
-                if (five) {
-                    if (x < 2)
-                        LL = x == 1 ? (y >= 1 ? SAMPLE(r1, 0) : 0) : 0;
-                    else if (lane < 2)
-                        LL = SAMPLE(r0, x - 2);
-                    const int TT = y >= 2 ? SAMPLE(r2, x) : 0;
-                    ctx += sq[768 + ((LL - L) & 0xFF)] + sq[1024 + ((TT - T) & 0xFF)];
+#pragma unroll
+                for (int j = 1; j <= SYM_ROWS; j++) {
+                    const int y = y0 + j - 1;
+                    if (y >= h)
+                        break;
+                    const uint8_t *r0 = pbase + (size_t)y * pitch;
+                    const uint8_t *r1 = r0 - pitch, *r2 = r1 - pitch;
+                    const int cur = v[j], T = v[j - 1];
+                    int L = __shfl_up_sync(0xffffffffu, cur, 1);
+                    int LT = __shfl_up_sync(0xffffffffu, T, 1);
+                    int RT = __shfl_down_sync(0xffffffffu, T, 1);
+                    int LL = __shfl_up_sync(0xffffffffu, cur, 2);
+                    if (valid) {
+                        if (x == 0) {                /* left border: ffv1enc.c:287 */
+                            L = T;
+                            LT = y >= 2 ? SAMPLE(r2, 0) : 0;
+                        } else if (lane == 0) {      /* seam between two 32-sample steps */
+                            L = SAMPLE(r0, x - 1);
+                            LT = y >= 1 ? SAMPLE(r1, x - 1) : 0;
+                        }
+                        if (x + 1 >= w)              /* right border: ffv1enc.c:288 */
+                            RT = T;
+                        else if (lane == 31)
+                            RT = y >= 1 ? SAMPLE(r1, x + 1) : 0;
+                        int ctx = sq[(L - LT) & 0xFF] + sq[256 + ((LT - T) & 0xFF)] +
+                                  sq[512 + ((T - RT) & 0xFF)];
+                        if (five) {
+                            if (x < 2)
+                                LL = x == 1 ? (y >= 1 ? SAMPLE(r1, 0) : 0) : 0;
+                            else if (lane < 2)
+                                LL = SAMPLE(r0, x - 2);
+                            const int TT = y >= 2 ? SAMPLE(r2, x) : 0;
+                            ctx += sq[768 + ((LL - L) & 0xFF)] + sq[1024 + ((TT - T) & 0xFF)];
+                        }
+                        int diff = cur - ff_median3(L, L + T - LT, T);
+                        if (ctx < 0) {
+                            ctx = -ctx;
+                            diff = -diff;
+                        }
+                        diff = ff_fold(diff, cbits);
+                        const uint32_t t = ((uint32_t)diff << FF_TOKEN_CTX_BITS) | (uint32_t)(ctx_base + ctx);
+                        tok[base + (uint32_t)y * w + x] = t;
+                        wsum += ff_token_weight(t);
+                    }
                 }
-                int diff = cur - ff_median3(L, L + T - LT, T);
-                if (ctx < 0) {
-                    ctx = -ctx;
-                    diff = -diff;
-                }
-                diff = ff_fold(diff, cbits);
-                const uint32_t t = ((uint32_t)diff << FF_TOKEN_CTX_BITS) | (uint32_t)(ctx_base + ctx);
-                tok[base + (uint32_t)y * w + x] = t;
-                wsum += ff_token_weight(t);
             }
         }
         base += (uint32_t)w * h;
@@ -290,9 +308,10 @@ extern "C" int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nfr
             cudaMemsetAsync(E->weight, 0, sizeof(uint32_t) * (size_t)nframes * P->nslices, st);
         if (P->colorspace == 0) {
             /* rows of the largest plane per z-block: 8 warps take 8 rows per pass */
-            int zr = (P->height / P->nv + 63) / 64;
+            /* one pass: 8 warps x SYM_ROWS rows per z-block */
+            int zr = (P->height / P->nv + 8 * SYM_ROWS - 1) / (8 * SYM_ROWS);
             if (zr < 1) zr = 1;
-            if (zr > 32) zr = 32;
+            if (zr > 64) zr = 64;
             dim3 g2(P->nslices, nframes, zr);
             k_symbolize_planar<<<g2, SYM_THREADS, 0, st>>>(*P, E->slices, E->frames, E->qt, E->tokens,
                                                            E->weight);
