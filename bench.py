@@ -347,35 +347,45 @@ def main():
         dec = F.FFV1Decoder(w, h, enc.extradata, device=local, max_batch=vb, pipeline_depth=args.e2e_depth)
 
         def e2e_step():
-            out_pk, i = [], 0
-            while True:
-                if i < B:
-                    if enc.send_frame(host_planes[i], pts=i):
-                        i += 1
+            """encoder and decoder run concurrently, like a transcode pipeline: packets are fed
+            to the decoder as soon as the encoder returns them, so H2D of pictures, kernels of
+            both directions and D2H of decoded pictures overlap"""
+            out_pk = []
+            sent = dec_sent = dec_got = 0
+            enc_done = False
+            while dec_got < B:
+                if sent < B and enc.send_frame(host_planes[sent], pts=sent):
+                    sent += 1
+                    if sent == B:
+                        enc.send_frame(None)
+                while True:
+                    if dec_sent < len(out_pk):
+                        if not dec.send_packet(out_pk[dec_sent], pts=dec_sent, dst=dsts[dec_sent]):
+                            break
+                        dec_sent += 1
+                        if dec_sent == B:
+                            dec.send_packet(None)
                         continue
-                elif i == B:
-                    enc.send_frame(None)
-                    i += 1
-                r = enc.receive_packet()
-                if r == F.EOF:
-                    break
-                if r is not None:
+                    if enc_done:
+                        break
+                    r = enc.receive_packet()
+                    if r == F.EOF:
+                        enc_done = True
+                        break
+                    if r is None:
+                        break
                     out_pk.append(r[0])
-            done, i = 0, 0
-            while True:
-                if i < B:
-                    if dec.send_packet(out_pk[i], pts=i, dst=dsts[i]):
-                        i += 1
-                        continue
-                elif i == B:
-                    dec.send_packet(None)
-                    i += 1
-                r = dec.receive_frame()
-                if r == F.EOF:
-                    break
-                if r is not None:
-                    done += 1
-            return out_pk, done
+                while True:
+                    r = dec.receive_frame()
+                    if r is None or r == F.EOF:
+                        break
+                    dec_got += 1
+            # leave both handles drained and reusable
+            while not enc_done and enc.receive_packet() != F.EOF:
+                pass
+            while dec.receive_frame() != F.EOF:
+                pass
+            return out_pk, dec_got
 
         dsts = []
         for i in range(B):
@@ -412,6 +422,26 @@ def main():
                "frames_per_launch_group": vb, "launch_groups_in_flight": args.e2e_depth,
                "gpu_launches": int(enc.launches + dec.launches - e2e_launch0)}
 
+    # ---- PCIe context: plain pinned copies of 1 GiB, both directions ----
+    pcie = None
+    try:
+        nb = 1 << 30
+        hp = torch.empty(nb, dtype=torch.uint8).pin_memory()
+        dp = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        dp.copy_(hp, non_blocking=True)
+        torch.cuda.synchronize()
+        e0.record()
+        dp.copy_(hp, non_blocking=True)
+        e1.record()
+        hp.copy_(dp, non_blocking=True)
+        e2.record()
+        torch.cuda.synchronize()
+        pcie = {"h2d_GBps": nb / e0.elapsed_time(e1) / 1e6, "d2h_GBps": nb / e1.elapsed_time(e2) / 1e6}
+        del hp, dp
+    except Exception:
+        pcie = None
+
     # ---- CPU baseline beside it (rank 0, N == 1): the reference's slice-threaded CPU codec ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -436,7 +466,7 @@ def main():
         "packet_bytes_per_picture": pkt_bytes / B, "raw_bytes_per_picture": raw_bytes,
         "kernel_ms_per_step": kern, "wall_ms_per_step": 1e3 * wall / K,
         "roofline": roofline, "gpu_launches": int(gpu_launches), "clocks": clocks,
-        "e2e": e2e, "cpu_baseline": cpu,
+        "e2e": e2e, "cpu_baseline": cpu, "pcie": pcie,
     }
     if rank == 0:
         print(json.dumps(out), flush=True)

@@ -824,7 +824,14 @@ static int dec_setup_stream(ffgpu_decoder *d)
         d->line_stride = d->s.width + 8;
     d->intra = d->s.version > 2 && d->s.intra;
     if (d->intra) {
-        const size_t per_frame = d->P.frame_bytes * 2 + (size_t)d->max_slices * d->P.total_ctx * FF_CONTEXT_SIZE;
+        /* the arena is sized later from the tables the stream uses (dec_size_states): budget
+         * with the smallest table here */
+        int min_ctx = d->s.ctx_count[0];
+        for (int i = 1; i < d->s.qt_count; i++)
+            if (d->s.ctx_count[i] < min_ctx)
+                min_ctx = d->s.ctx_count[i];
+        const size_t per_frame = d->P.frame_bytes * 2 +
+                                 (size_t)d->max_slices * d->P.nsets * min_ctx * FF_CONTEXT_SIZE;
         int b = d->opt.max_batch > 0 ? d->opt.max_batch : (65536 + d->max_slices - 1) / d->max_slices;
         size_t cap = ((size_t)16 << 30) / (per_frame ? per_frame : 1);
         if (b > 256) b = 256;
@@ -839,6 +846,34 @@ static int dec_setup_stream(ffgpu_decoder *d)
     if (d->depth > MAX_DEPTH)
         d->depth = MAX_DEPTH;
     d->have_params = 1;
+    return 0;
+}
+
+/* The adaptive-state arena is sized for the quant tables the stream really uses (the slice
+ * headers name them), not for the largest table of the global header: -context 0 streams
+ * carry the 7563-context table too but never touch it. */
+static int dec_size_states(ffgpu_decoder *d, const uint8_t *pkt, size_t size)
+{
+    FFDecHostState hs = d->hs;
+    FFDecFrameInfo info;
+    FFDecSlice *tmp = (FFDecSlice *)calloc((size_t)d->max_slices, sizeof(FFDecSlice));
+    int n, need = 1;
+    if (!tmp)
+        return fail(FFGPU_ENOMEM, "out of memory");
+    n = ff_dec_parse_packet(&d->s, &hs, pkt, size, 0, tmp, &info);
+    if (n < 0) {
+        free(tmp);
+        return fail(n, "invalid packet (%d)", n);
+    }
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < d->P.nsets && !tmp[i].skip; k++)
+            if (d->s.ctx_count[tmp[i].qidx[k]] > need)
+                need = d->s.ctx_count[tmp[i].qidx[k]];
+    free(tmp);
+    d->max_ctx = need;
+    d->P.total_ctx = d->P.nsets * need;
+    for (int k = 0; k < d->P.nsets; k++)
+        d->P.set_base[k] = k * need;
     return 0;
 }
 
@@ -873,7 +908,8 @@ static int dec_device_init(ffgpu_decoder *d)
         memset(tmp, 128, per * FF_MAX_QUANT_TABLES);
         for (int i = 0; i < d->s.qt_count; i++)
             if (d->s.initial[i])
-                memcpy(tmp + per * i, d->s.initial[i], (size_t)d->s.ctx_count[i] * FF_CONTEXT_SIZE);
+                memcpy(tmp + per * i, d->s.initial[i],
+                       (size_t)(d->s.ctx_count[i] < d->max_ctx ? d->s.ctx_count[i] : d->max_ctx) * FF_CONTEXT_SIZE);
         CK(cudaMalloc(&d->d_initial, per * FF_MAX_QUANT_TABLES));
         CK(cudaMemcpy(d->d_initial, tmp, per * FF_MAX_QUANT_TABLES, cudaMemcpyHostToDevice));
         free(tmp);
@@ -1067,6 +1103,12 @@ static int dec_add_packet(ffgpu_decoder *d, DecJob *j, const uint8_t *pkt, size_
                             j->h_work + (size_t)j->n * d->max_slices, &m->info);
     if (n < 0)
         return fail(n, "invalid packet (%d)", n);
+    for (int i = 0; i < n; i++) {
+        const FFDecSlice *w = &j->h_work[(size_t)j->n * d->max_slices + i];
+        for (int k = 0; k < d->P.nsets && !w->skip; k++)
+            if (d->s.ctx_count[w->qidx[k]] > d->max_ctx)
+                return fail(FFGPU_ENOSYS, "slice switches to a larger quant table mid-stream");
+    }
     m->nslices = n;
     m->pts = pts;
     memcpy(m->damaged, d->hs.damaged, sizeof(m->damaged));
@@ -1183,6 +1225,8 @@ extern "C" int ffgpu_ffv1_decode_send_packet(ffgpu_decoder *d, const uint8_t *pk
                 return r;
             d->hs.max_slices = d->max_slices;
         }
+        if ((r = dec_size_states(d, pkt, size)) < 0)
+            return r;
         if ((r = dec_device_init(d)) < 0)
             return r;
     }
@@ -1320,6 +1364,8 @@ extern "C" int ffgpu_ffv1_decode_device(ffgpu_decoder *d, const uint8_t *const *
                 return r;
             d->hs.max_slices = d->max_slices;
         }
+        if ((r = dec_size_states(d, pkts[0], sizes[0])) < 0)
+            return r;
         if ((r = dec_device_init(d)) < 0)
             return r;
     }
