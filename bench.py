@@ -352,8 +352,12 @@ def main():
             both directions and D2H of decoded pictures overlap"""
             out_pk = []
             sent = dec_sent = dec_got = 0
-            enc_done = False
+            enc_done = dec_done = False
+            deadline = time.perf_counter() + 120.0
             while dec_got < B:
+                if time.perf_counter() > deadline:
+                    raise SystemExit("e2e pipeline stalled: sent %d, packets %d, decoded %d" % (
+                        sent, len(out_pk), dec_got))
                 if sent < B and enc.send_frame(host_planes[sent], pts=sent):
                     sent += 1
                     if sent == B:
@@ -375,16 +379,19 @@ def main():
                     if r is None:
                         break
                     out_pk.append(r[0])
-                while True:
+                while not dec_done:
                     r = dec.receive_frame()
-                    if r is None or r == F.EOF:
+                    if r == F.EOF:
+                        dec_done = True
+                        break
+                    if r is None:
                         break
                     dec_got += 1
-            # leave both handles drained and reusable
-            while not enc_done and enc.receive_packet() != F.EOF:
-                pass
-            while dec.receive_frame() != F.EOF:
-                pass
+            # leave both handles drained and reusable (the EOF ends the flush)
+            while not enc_done:
+                enc_done = enc.receive_packet() == F.EOF
+            while not dec_done:
+                dec_done = dec.receive_frame() == F.EOF
             return out_pk, dec_got
 
         dsts = []
