@@ -870,6 +870,7 @@ static int dec_size_states(ffgpu_decoder *d, const uint8_t *pkt, size_t size)
             if (d->s.ctx_count[tmp[i].qidx[k]] > need)
                 need = d->s.ctx_count[tmp[i].qidx[k]];
     free(tmp);
+    d->hs.device_parse = 1;            /* from now on only slice 0 is parsed on the host */
     d->max_ctx = need;
     d->P.total_ctx = d->P.nsets * need;
     for (int k = 0; k < d->P.nsets; k++)
@@ -1029,6 +1030,11 @@ static void dec_fill_dev(const ffgpu_decoder *d, const DecJob *j, uint8_t *frame
     D->max_ctx = d->max_ctx;
     D->state_per_frame = d->intra;
     D->qt_count = d->s.qt_count;
+    D->hdr.micro_version = d->s.micro_version;
+    D->hdr.qt_count = d->s.qt_count;
+    D->hdr.ctx_cap = d->max_ctx;
+    for (int i = 0; i < FF_MAX_QUANT_TABLES; i++)
+        D->hdr.ctx_count[i] = i < d->s.qt_count ? d->s.ctx_count[i] : 0;
     D->weight = j->d_weight;
     D->weight_sorted = j->d_weight_sorted;
     D->iota = d->d_iota;
@@ -1105,7 +1111,7 @@ static int dec_add_packet(ffgpu_decoder *d, DecJob *j, const uint8_t *pkt, size_
         return fail(n, "invalid packet (%d)", n);
     for (int i = 0; i < n; i++) {
         const FFDecSlice *w = &j->h_work[(size_t)j->n * d->max_slices + i];
-        for (int k = 0; k < d->P.nsets && !w->skip; k++)
+        for (int k = 0; k < d->P.nsets && !w->skip && !w->parse; k++)
             if (d->s.ctx_count[w->qidx[k]] > d->max_ctx)
                 return fail(FFGPU_ENOSYS, "slice switches to a larger quant table mid-stream");
     }
@@ -1133,8 +1139,17 @@ static int dec_finish_frame(ffgpu_decoder *d, DecJob *j, int i, ffgpu_picture_ou
     for (int s = 0; s < m->nslices; s++) {
         const FFDecSlice *w = &j->h_work[(size_t)i * d->max_slices + s];
         const FFDecResult *res = &j->h_result[(size_t)i * d->max_slices + s];
-        if (!w->skip && P->ac != FF_AC_GOLOMB && P->version > 2) {
-            const int v = (int)w->size - (int)res->end_pos - 2 - 5 * P->ec;
+        if (w->parse) {
+            /* CRC, header and rectangle were established on the device */
+            if (res->flags & (FF_RES_CRC_BAD | FF_RES_HDR_BAD)) {
+                m->damaged[s] = 1;
+                d->hs.damaged[s] = 1;
+            }
+            m->rect[s].x = res->x; m->rect[s].y = res->y;
+            m->rect[s].w = res->w; m->rect[s].h = res->h;
+        }
+        if (!(res->flags & FF_RES_NOT_DECODED) && P->ac != FF_AC_GOLOMB && P->version > 2) {
+            const int v = (int)res->size - (int)res->end_pos - 2 - 5 * P->ec;
             if (v) {
                 m->damaged[s] = 1;                 /* "bytestream end mismatching by %d" */
                 d->hs.damaged[s] = 1;

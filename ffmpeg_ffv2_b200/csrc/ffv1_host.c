@@ -993,7 +993,7 @@ int ff_dec_parse_packet(FFStream *s, FFDecHostState *hs, const uint8_t *pkt, siz
         end -= v;
         if (info->key_frame)
             hs->damaged[i] = 0;
-        if (s->ec && ff_crc32(0, end, (size_t)v)) {
+        if (s->ec && !(hs->device_parse && i && s->version > 2) && ff_crc32(0, end, (size_t)v)) {
             hs->damaged[i] = 1;            /* "slice CRC mismatch" */
             info->crc_damaged++;
         }
@@ -1023,6 +1023,15 @@ int ff_dec_parse_packet(FFStream *s, FFDecHostState *hs, const uint8_t *pkt, siz
         FFSliceRect rc;
         int j;
 
+        if (i && hs->device_parse && s->version > 2) {
+            /* the decode kernel checks the CRC, parses the slice header and positions the
+             * coder itself (ff_dec_slice_header); until it reports back the rectangle of
+             * the regular grid stands in */
+            d->parse = 1;
+            ff_slice_rect(s, i, &rc);
+            hs->rect[i] = rc;
+            continue;
+        }
         if (i == 0) {
             c = c0;
             c.end = d->size;               /* fs->c.bytestream_end = buf_p + v */

@@ -58,6 +58,7 @@ typedef struct FFDecHostState {
     int key_frame_ok;
     int max_slices;
     int slice_count;                    /* of the last key frame */
+    int device_parse;                   /* slices 1..n-1: CRC + header are left to the device */
     uint8_t damaged[FF_MAX_SLICES];     /* CRC / header damage of the current packet */
     FFSliceRect rect[FF_MAX_SLICES];    /* geometry of the current packet's slices   */
 } FFDecHostState;

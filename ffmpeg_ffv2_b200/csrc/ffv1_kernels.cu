@@ -433,6 +433,9 @@ k_decode(const FFDevParams P, const FFDecDev D, int nframes)
         ((uint32_t *)&ff_s_tab)[i] = ((const uint32_t *)D.tab)[i];
     for (int i = threadIdx.x; i < D.qt_count * FF_QT_STRIDE / 2; i += CODE_THREADS)
         ((uint32_t *)ff_s_qt)[i] = ((const uint32_t *)D.qt)[i];
+    __shared__ uint32_t s_crc[256];
+    for (int i = threadIdx.x; i < 256; i += CODE_THREADS)
+        s_crc[i] = ff_crc_table_entry(i);
     __syncthreads();
     const int tid = blockIdx.x * CODE_THREADS + threadIdx.x;
     if (tid >= nframes * D.max_slices)
@@ -440,10 +443,18 @@ k_decode(const FFDevParams P, const FFDecDev D, int nframes)
     const int gid = D.order ? (int)D.order[tid] : tid;       /* largest slices first */
     const int f = gid / D.max_slices, s = gid - f * D.max_slices;
     FFDecResult r;
-    r.end_pos = 0; r.overread = 0; r.error = 0; r.pad = 1;      /* pad=1: not decoded */
+    r.end_pos = 0; r.overread = 0; r.error = 0; r.flags = FF_RES_NOT_DECODED;
+    r.x = r.y = r.w = r.h = 0; r.size = 0; r.pad[0] = r.pad[1] = r.pad[2] = 0;
     if (s < D.nslices[f]) {
-        const FFDecSlice w = D.work[gid];
+        FFDecSlice w = D.work[gid];
+        r.x = w.x; r.y = w.y; r.w = w.w; r.h = w.h;
+        if (w.parse && !w.skip) {
+            ff_dec_slice_header(P, D.hdr, &w, D.pkt, &ff_s_tab, s_crc, &r);
+            r.x = w.x; r.y = w.y; r.w = w.w; r.h = w.h;
+        }
+        r.size = w.size;
         if (!w.skip) {
+            r.flags &= ~FF_RES_NOT_DECODED;
             const size_t slot = (size_t)(D.state_per_frame ? f : 0) * D.max_slices + s;
             FFDecCtx C;
             C.qt_all = D.qt;

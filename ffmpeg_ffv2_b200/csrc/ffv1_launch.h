@@ -73,6 +73,7 @@ typedef struct FFDecDev {
     int max_ctx;                    /* contexts per set (largest quant table)           */
     int state_per_frame;
     int qt_count;                   /* quant table sets of the stream                   */
+    FFDecHdr hdr;                   /* constants for device-side slice header parsing   */
     uint32_t *weight;               /* [nframes*max_slices] slice byte counts            */
     uint32_t *weight_sorted;
     const uint32_t *iota;

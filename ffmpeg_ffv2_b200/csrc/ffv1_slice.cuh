@@ -860,6 +860,80 @@ FFGPU_HD void ff_store_line_rgb(const FFDevParams &P, uint8_t *frame, int X0, in
     }
 }
 
+/* ff_init_range_decoder + decode_slice_header (ffv1dec.c:167-244) + the Golomb hand-over
+ * (ffv1dec.c:312-319) + the slice CRC check (ffv1dec.c:905-922) for slices the host left to
+ * the device.  Fills the coder state / rectangle / quant table indices of the work item. */
+FFGPU_HD void ff_dec_slice_header(const FFDevParams &P, const FFDecHdr &H, FFDecSlice *w,
+                                  const uint8_t *pkt, const FFRacTables *tab,
+                                  const uint32_t *crc_tab, FFDecResult *res)
+{
+    const uint8_t *base = pkt + w->pkt_off;
+    FFRacDec c;
+    uint8_t st[FF_CONTEXT_SIZE];
+    int i, bad = 0;
+    if (P.ec) {
+        uint32_t r = 0;
+        for (uint32_t j = 0; j < w->size; j++)
+            r = (r << 8) ^ crc_tab[(r >> 24) ^ base[j]];
+        if (r)
+            res->flags |= FF_RES_CRC_BAD;
+    }
+    if (w->size < 2) {
+        w->skip = 1;
+        res->flags |= FF_RES_HDR_BAD;
+        return;
+    }
+    ffrac_dec_init(&c, base, w->size);
+    for (i = 0; i < FF_CONTEXT_SIZE; i++)
+        st[i] = 128;
+    {
+        const unsigned sx = (unsigned)ffrac_get_symbol(&c, tab, st, 0) * (unsigned)P.width;
+        const unsigned sy = (unsigned)ffrac_get_symbol(&c, tab, st, 0) * (unsigned)P.height;
+        const unsigned sw = ((unsigned)ffrac_get_symbol(&c, tab, st, 0) + 1U) * (unsigned)P.width + sx;
+        const unsigned sh = ((unsigned)ffrac_get_symbol(&c, tab, st, 0) + 1U) * (unsigned)P.height + sy;
+        w->x = (int)sx / P.nh;
+        w->y = (int)sy / P.nv;
+        w->w = (int)sw / P.nh - w->x;
+        w->h = (int)sh / P.nv - w->y;
+        if ((unsigned)w->w > (unsigned)P.width || (unsigned)w->h > (unsigned)P.height)
+            bad = 1;
+        else if ((unsigned)w->x + (uint64_t)w->w > (unsigned)P.width ||
+                 (unsigned)w->y + (uint64_t)w->h > (unsigned)P.height)
+            bad = 1;
+    }
+    for (i = 0; i < P.nsets && !bad; i++) {
+        const int idx = ffrac_get_symbol(&c, tab, st, 0);
+        if ((unsigned)idx >= (unsigned)H.qt_count || H.ctx_count[idx & 7] > H.ctx_cap)
+            bad = 1;                       /* "quant_table_index out of range" / arena too small */
+        else
+            w->qidx[i] = idx;
+    }
+    if (bad) {
+        w->x = w->y = w->w = w->h = 0;
+        w->skip = 1;
+        res->flags |= FF_RES_HDR_BAD;
+        return;
+    }
+    ffrac_get_symbol(&c, tab, st, 0);      /* picture structure: the frame takes slice 0's */
+    ffrac_get_symbol(&c, tab, st, 0);      /* sample aspect ratio                          */
+    ffrac_get_symbol(&c, tab, st, 0);
+    if (P.ac == FF_AC_GOLOMB) {
+        if ((P.version == 3 && H.micro_version > 1) || P.version > 3) {
+            uint8_t term = 129;
+            ffrac_get(&c, tab, &term);
+        }
+        w->golomb_start = c.pos - 1;       /* version > 2 here */
+    }
+    w->low = c.low;
+    w->range = c.range;
+    w->pos = c.pos;
+    w->overread = c.overread;
+    if (c.end < w->size)
+        w->size = c.end;
+    if (!w->w || !w->h)
+        w->skip = 1;
+}
+
 /* line iterator over the coded lines of a slice, in coding order (YCbCr: plane after plane,
  * RGB: G,B,R[,A] interleaved per picture line) */
 typedef struct FFLineIt {
@@ -1089,7 +1163,7 @@ finish:
     res->end_pos = c.pos;
     res->overread = c.overread;
     res->error = err;
-    res->pad = 0;
+
 }
 
 /* decode_slice after the header, Golomb-Rice streams (ffv1dec.c:304-350) */
@@ -1156,7 +1230,7 @@ FFGPU_HD void ff_decode_slice_golomb(const FFDevParams &P, const FFDecSlice &d, 
     res->end_pos = d.pos;
     res->overread = d.overread;
     res->error = err;
-    res->pad = 0;
+
 }
 
 FFGPU_HD void ff_decode_slice(const FFDevParams &P, const FFDecSlice &d, const uint8_t *pkt,

@@ -146,13 +146,30 @@ typedef struct FFDecSlice {
     int key_frame;          /* reset the adaptive states first                       */
     int skip;               /* header invalid: leave the rectangle untouched         */
     uint32_t golomb_start;  /* Golomb: bit reader starts here (ac_byte_count)        */
+    int parse;              /* 1: the device checks the CRC and parses the slice     */
+                            /* header itself (slices 1..n-1 of v3 packets)           */
 } FFDecSlice;
+
+#define FF_RES_NOT_DECODED 1  /* absent or skipped work item                             */
+#define FF_RES_CRC_BAD     2  /* slice CRC mismatch (ffv1dec.c:905-922)                  */
+#define FF_RES_HDR_BAD     4  /* decode_slice_header failed (ffv1dec.c:296-300)          */
 
 typedef struct FFDecResult {
     uint32_t end_pos;       /* range coder: bytestream position after the terminator */
     int32_t  overread;
     int32_t  error;         /* decode_line returned AVERROR_INVALIDDATA              */
-    int32_t  pad;
+    int32_t  flags;         /* FF_RES_*                                              */
+    int32_t  x, y, w, h;    /* rectangle from the slice header (device-parsed slices) */
+    uint32_t size;          /* bytestream_end - bytestream_start actually used       */
+    uint32_t pad[3];
 } FFDecResult;
+
+/* stream constants the device-side slice header parser needs */
+typedef struct FFDecHdr {
+    int micro_version;
+    int qt_count;
+    int ctx_cap;            /* contexts per set the state arena was sized for        */
+    int ctx_count[FF_MAX_QUANT_TABLES];
+} FFDecHdr;
 
 #endif

@@ -190,6 +190,7 @@ extern "C" int ffv1emul_decode(void *h, const uint8_t *pkt_in, int size, uint8_t
     memcpy(pkt.data(), pkt_in, size);
     std::vector<FFDecSlice> work(FF_MAX_SLICES);
     FFDecFrameInfo info;
+    d->hs.device_parse = 1;                 /* exercise the device-side header parser too */
     int n = ff_dec_parse_packet(&d->s, &d->hs, pkt.data(), size, 0, work.data(), &info);
     if (n < 0) return n;
     if (!d->have_params || info.key_frame) {
@@ -207,7 +208,19 @@ extern "C" int ffv1emul_decode(void *h, const uint8_t *pkt_in, int size, uint8_t
     const int line_stride = P.width + 8;
     d->lines.resize((size_t)P.ncoded * 2 * line_stride);
     std::vector<FFDecResult> res(n);
+    std::vector<uint32_t> crc(256);
+    for (int i = 0; i < 256; i++) crc[i] = ff_crc_table_entry(i);
+    FFDecHdr H;
+    H.micro_version = d->s.micro_version; H.qt_count = d->s.qt_count; H.ctx_cap = P.total_ctx / P.nsets;
+    for (int i = 0; i < FF_MAX_QUANT_TABLES; i++) H.ctx_count[i] = i < d->s.qt_count ? d->s.ctx_count[i] : 0;
     for (int i = 0; i < n; i++) {
+        memset(&res[i], 0, sizeof(res[i]));
+        if (work[i].parse && !work[i].skip) {
+            ff_dec_slice_header(P, H, &work[i], pkt.data(), &d->s.cur_tab, crc.data(), &res[i]);
+            if (res[i].flags & (FF_RES_CRC_BAD | FF_RES_HDR_BAD)) d->hs.damaged[i] = 1;
+            FFSliceRect rc = { work[i].x, work[i].y, work[i].w, work[i].h };
+            d->hs.rect[i] = rc;
+        }
         if (work[i].skip) continue;
         uint8_t *rs = &d->rstate[(size_t)i * P.total_ctx * FF_CONTEXT_SIZE];
         uint2 *vs = &d->vstate[(size_t)i * P.total_ctx];
