@@ -287,6 +287,7 @@ class FFV1Decoder:
             raise FFGpuError("decode_init", r, _err())
         self.width, self.height = width, height
         self._pending = []
+        self._idle = (PictureOut(), [])
 
     @property
     def pix_fmt(self):
@@ -332,8 +333,8 @@ class FFV1Decoder:
             return False
         if r < 0:
             raise FFGpuError("send_packet", r, _err())
-        if dst is not None and pkt is not None:
-            self._pending.append(dst)
+        if pkt is not None:
+            self._pending.append(dst)          # None: destination supplied at receive time
         return True
 
     def alloc_picture(self, fmt=None):
@@ -341,14 +342,15 @@ class FFV1Decoder:
 
     def receive_frame(self, out=None):
         """returns (PictureOut, arrays) | None on EAGAIN | EOF"""
-        if out is None and self._pending:
-            o = self._pending[0]
-            r = lib().ffgpu_ffv1_decode_receive_frame(self.h, C.byref(o[0]))
-            if r == 0:
-                self._pending.pop(0)
-        else:
+        if self._pending and self._pending[0] is not None:
+            o = self._pending[0]               # decoded straight into the picture given at send
+        elif self._pending:
             o = out if out is not None else self._alloc_out(self.pix_fmt)
-            r = lib().ffgpu_ffv1_decode_receive_frame(self.h, C.byref(o[0]))
+        else:
+            o = self._idle                     # nothing in flight: only EAGAIN / EOF can come back
+        r = lib().ffgpu_ffv1_decode_receive_frame(self.h, C.byref(o[0]))
+        if r == 0 and self._pending:
+            self._pending.pop(0)
         if r == EAGAIN:
             return None
         if r == EOF:

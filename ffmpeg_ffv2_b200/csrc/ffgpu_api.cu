@@ -51,6 +51,53 @@ extern "C" int ffgpu_abi_version(void) { return FFGPU_ABI_VERSION; }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+/* FFGPU_TRACE=1: per launch group, when it was enqueued (host clock) and when its kernels
+ * started / finished on the device, relative to the handle's first group */
+#include <time.h>
+static int trace_on(void)
+{
+    static int v = -1;
+    if (v < 0)
+        v = getenv("FFGPU_TRACE") != NULL;
+    return v;
+}
+static double host_ms(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec / 1e6;
+}
+struct Trace {
+    cudaEvent_t base, k0, k1;
+    double host_base;
+    int have_base;
+};
+static void trace_begin(Trace *t, cudaEvent_t *k0, cudaStream_t st, const char *what, int n)
+{
+    if (!trace_on())
+        return;
+    if (!t->have_base) {
+        cudaEventCreate(&t->base);
+        cudaEventRecord(t->base, st);
+        t->host_base = host_ms();
+        t->have_base = 1;
+    }
+    cudaEventCreate(k0);
+    cudaEventRecord(*k0, st);
+    fprintf(stderr, "[ffgpu] %s group of %d enqueued at host %+.2f ms\n", what, n, host_ms() - t->host_base);
+}
+static void trace_end(Trace *t, cudaEvent_t k0, cudaEvent_t done, const char *what)
+{
+    float a = 0, b = 0;
+    if (!trace_on() || !t->have_base || !k0)
+        return;
+    cudaEventSynchronize(done);
+    cudaEventElapsedTime(&a, t->base, k0);
+    cudaEventElapsedTime(&b, t->base, done);
+    fprintf(stderr, "[ffgpu] %s group: device work %.2f .. %.2f ms (%.2f), seen by host at %+.2f ms\n", what, a, b,
+            b - a, host_ms() - t->host_base);
+}
+
 extern "C" size_t ffgpu_ffv1_frame_layout(const char *pix_fmt, int width, int height,
                                           size_t plane_offset[4], int plane_pitch[4],
                                           int plane_rows[4], int plane_rowbytes[4])
@@ -108,6 +155,7 @@ struct EncJob {
     cudaStream_t stream;
     cudaEvent_t done;
     int n, state, drained, fetched;
+    cudaEvent_t tk0;
     uint8_t *d_frames;
     uint32_t *d_tokens;
     uint8_t *d_state;
@@ -160,6 +208,7 @@ struct ffgpu_encoder {
     uint64_t launches;
     int profile;                        /* record events around every kernel of device batches */
     void *events[FFK_ENC_KERNELS + 1];
+    Trace trace;
 };
 
 static int enc_free_job(EncJob *j)
@@ -224,7 +273,7 @@ static int enc_device_init(ffgpu_encoder *e)
         EncJob *j = &e->jobs[i];
         const size_t B = (size_t)e->max_batch;
         CK(cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&j->done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&j->done, trace_on() ? cudaEventDefault : cudaEventDisableTiming));
         CK(cudaMalloc(&j->d_frames, B * P->frame_bytes));
         CK(cudaMalloc(&j->d_tokens, B * P->frame_tokens * sizeof(uint32_t)));
         if (e->intra)
@@ -433,6 +482,7 @@ static int enc_launch(ffgpu_encoder *e, EncJob *j)
     CK(cudaMemcpyAsync(j->d_frame_set, j->h_frame_set, j->n, cudaMemcpyHostToDevice, j->stream));
     CK(cudaMemcpyAsync(j->d_frame_key, j->h_frame_key, j->n, cudaMemcpyHostToDevice, j->stream));
     CK(cudaMemsetAsync(j->d_overflow, 0, sizeof(uint32_t), j->stream));
+    trace_begin(&e->trace, &j->tk0, j->stream, "encode", j->n);
     r = ffk_encode_group(&e->P, &E, j->n, j->stream);
     if (r < 0)
         return fail(r, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -455,6 +505,7 @@ static int enc_fetch(ffgpu_encoder *e, EncJob *j)
     if (j->fetched)
         return 0;
     CK(cudaEventSynchronize(j->done));
+    trace_end(&e->trace, j->tk0, j->done, "encode");
     if (*j->h_overflow)
         return fail(FFGPU_INVALIDDATA, "encoded frame too large");   /* ffv1enc_template.c:34-44 */
     total = j->h_pkt_off[j->n];
@@ -749,7 +800,8 @@ struct DecFrameMeta {
 struct DecJob {
     cudaStream_t stream;
     cudaEvent_t done;
-    int n, state, drained, fetched;
+    cudaEvent_t tk0;
+    int n, state, drained, fetched, traced;
     uint8_t *h_pkt, *d_pkt;
     size_t pkt_cap, pkt_used;
     FFDecSlice *h_work, *d_work;
@@ -786,6 +838,7 @@ struct ffgpu_decoder {
     uint64_t launches;
     int profile, profile_next;
     void *events[FFK_DEC_KERNELS + 1];
+    Trace trace;
 };
 
 static void dec_free_job(DecJob *j)
@@ -934,7 +987,7 @@ static int dec_device_init(ffgpu_decoder *d)
         DecJob *j = &d->jobs[i];
         const size_t B = (size_t)d->max_batch;
         CK(cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&j->done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&j->done, trace_on() ? cudaEventDefault : cudaEventDisableTiming));
         j->pkt_cap = align_up(B * (P->frame_bytes / 2 + 65536) + 256, 4096);
         CK(cudaHostAlloc(&j->h_pkt, j->pkt_cap, cudaHostAllocDefault));
         CK(cudaMalloc(&j->d_pkt, j->pkt_cap));
@@ -1191,7 +1244,10 @@ static int dec_finish_frame(ffgpu_decoder *d, DecJob *j, int i, ffgpu_picture_ou
 
 static int dec_launch_group(ffgpu_decoder *d, DecJob *j)
 {
-    int r = dec_launch(d, j, j->d_frames, j->stream, 1);
+    int r;
+    trace_begin(&d->trace, &j->tk0, j->stream, "decode", j->n);
+    j->traced = 0;
+    r = dec_launch(d, j, j->d_frames, j->stream, 1);
     if (r < 0)
         return r;
     CK(cudaEventRecord(j->done, j->stream));
@@ -1300,6 +1356,10 @@ extern "C" int ffgpu_ffv1_decode_receive_frame(ffgpu_decoder *d, ffgpu_picture_o
             return FFGPU_EAGAIN;
         CK(cudaEventSynchronize(j->done));
         j->state = JOB_DRAINING;
+    }
+    if (!j->traced) {
+        trace_end(&d->trace, j->tk0, j->done, "decode");
+        j->traced = 1;
     }
     i = j->drained;
     if (!j->meta[i].has_dst) {
