@@ -1270,10 +1270,6 @@ FFV1OEncoder *ffv1o_encoder_open(const FFV1OOptions *o, int *err)
         *err = FFV1O_INVALIDDATA;
         goto fail;
     }
-    if (!pf) {
-        *err = FFV1O_ENOSYS;                 /* "format not supported" */
-        goto fail;
-    }
     s->pf = pf;
     s->width = o->width;
     s->height = o->height;
@@ -1313,6 +1309,10 @@ FFV1OEncoder *ffv1o_encoder_open(const FFV1OOptions *o, int *err)
         ac = AC_DEFAULT;
 
     /* pixel format, ffv1enc.c:572-699 */
+    if (!pf) {
+        *err = FFV1O_ENOSYS;                 /* "format not supported" */
+        goto fail;
+    }
     if (pf->layout == LAY_PLANAR || pf->layout == LAY_YA8) {
         s->colorspace = 0;
         s->chroma_planes = pf->chroma;

@@ -1,0 +1,87 @@
+"""The product's __host__ __device__ slice functions (csrc/ffv1_slice.cuh: symbolize, range /
+Golomb coders, packet assembly, slice header parser, decoder) compiled for the CPU by
+tests/emul and checked bit-exactly against the oracle.  This is how the device logic is
+verified in the GPU-less build container; the CUDA kernels wrap the same functions and are
+checked again on the B200 by test_gpu_parity.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cpucodec as cc
+import synth
+
+pytestmark = pytest.mark.skipif(not cc.available("emul"), reason="tests/emul not built")
+
+FORMATS = ["yuv420p", "yuv410p", "gray", "ya8", "yuva420p", "yuv420p10le", "yuv444p16le", "gray16le",
+           "yuva444p10le", "bgr0", "bgra", "gbrp10le", "gbrp16le", "gbrap12le", "rgb48le"]
+OPTIONS = [dict(), dict(slices=4), dict(slices=9, coder=2), dict(slices=4, coder=-2, context=1),
+           dict(level=3, coder=0, context=1), dict(level=1, coder=1),
+           dict(level=3, slicecrc=0, gop_size=1, slices=12)]
+
+
+@pytest.mark.parametrize("fmt", FORMATS)
+def test_device_functions_match_oracle(fmt):
+    w, h = 64, 48
+    for kw in OPTIONS:
+        try:
+            orc = cc.Encoder("oracle", w, h, fmt, **kw)
+        except cc.CodecError as e:
+            with pytest.raises(cc.CodecError) as ei:
+                cc.Encoder("emul", w, h, fmt, **kw)
+            assert ei.value.code == e.code
+            continue
+        emu = cc.Encoder("emul", w, h, fmt, **kw)
+        assert emu.info == orc.info and emu.extradata == orc.extradata
+        do = cc.Decoder("oracle", w, h, orc.extradata)
+        de = cc.Decoder("emul", w, h, orc.extradata)
+        for i, kind in enumerate(("smooth", "noise", "extremes", "testsrc2", "smooth")):
+            planes = synth.GENERATORS[kind](fmt, w, h, i)
+            po, pe = orc.encode(planes), emu.encode(planes)
+            assert po == pe, (fmt, kw, kind)
+            fo, fe = do.decode(po), de.decode(po)
+            assert do.pix_fmt == de.pix_fmt
+            for a, b in zip(fo, fe):
+                assert np.array_equal(a, b), (fmt, kw, kind)
+
+
+def test_msb_aligned_sample_depth():
+    """bits_per_raw_sample below the container depth in a 16-bit format (ffv1dec.c:158)"""
+    w, h, fmt = 48, 32, "gray16le"
+    orc = cc.Encoder("oracle", w, h, fmt, bits_per_raw_sample=11)
+    emu = cc.Encoder("emul", w, h, fmt, bits_per_raw_sample=11)
+    planes = synth.noise(fmt, w, h, 0)
+    po = orc.encode(planes)
+    assert po == emu.encode(planes)
+    a = cc.Decoder("oracle", w, h).decode(po)
+    b = cc.Decoder("emul", w, h).decode(po)
+    assert np.array_equal(a[0], b[0])
+
+
+def test_damaged_packets():
+    w, h = 128, 96
+    for fmt in ("yuv420p", "yuv420p10le"):
+        enc = cc.Encoder("oracle", w, h, fmt, slices=4, gop_size=1)
+        p0 = enc.encode(synth.smooth(fmt, w, h, 0))
+        p1 = enc.encode(synth.smooth(fmt, w, h, 1))
+        sizes, end = [], len(p1)
+        while end > 0:
+            size = int.from_bytes(p1[end - 8:end - 5], "big")
+            sizes.append((end - 8 - size, size))
+            end -= size + 8
+        sizes = sizes[::-1]
+        for off, prev in ((sizes[1][0] + sizes[1][1] // 2, True), (sizes[1][0] + sizes[1][1] + 1, False),
+                          (sizes[2][0] + 3, True)):
+            bad = bytearray(p1)
+            bad[off] ^= 0x55
+            out = {}
+            for which in ("oracle", "emul"):
+                d = cc.Decoder(which, w, h, enc.extradata)
+                if prev:
+                    d.decode(p0)
+                fn = getattr(cc.api(which).lib, cc.PATHS[which][1] + "decoder_damaged")
+                frames = d.decode(bytes(bad))
+                out[which] = (frames, fn(C.c_void_p(d.h)))
+            assert out["oracle"][1] == out["emul"][1]
+            for a, b in zip(out["oracle"][0], out["emul"][0]):
+                assert np.array_equal(a, b)
