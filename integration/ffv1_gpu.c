@@ -1,0 +1,313 @@
+/*
+ * integration/ffv1_gpu.c -- the libavcodec side of the drop-in: two AVCodec objects that
+ * keep FFV1's init/encode2/decode/close callbacks and AVOptions and forward the slice
+ * pixel path to libffgpu.so (include/ffgpu.h).  A maintainer adds this one file to
+ * libavcodec/ (see INTEGRATION.md); nothing else in FFmpeg changes.
+ *
+ * It replaces, callback for callback:
+ *   ff_ffv1_encoder  libavcodec/ffv1enc.c:1323-1360  (encode_init :517, encode_frame :1122,
+ *                                                     encode_close :1283, options :1291-1307)
+ *   ff_ffv1_decoder  libavcodec/ffv1dec.c:1087-1101  (decode_init :818, decode_frame :837)
+ *
+ * The codecs are registered under the names "ffv1_gpu" (and can be renamed "ffv1" for a
+ * literal drop-in); the bitstream is FFV1, so any FFV1 decoder reads the encoder's output
+ * and the decoder reads any FFV1 v0/v1/v3 stream.
+ */
+#include "libavutil/avassert.h"
+#include "libavutil/imgutils.h"
+#include "libavutil/opt.h"
+#include "libavutil/pixdesc.h"
+#include "avcodec.h"
+#include "internal.h"
+
+#include "ffgpu.h"
+
+#define GPU_FIFO 1024
+
+typedef struct FFV1GpuContext {
+    AVClass *class;            /* first member: avcodec_open2 applies the AVOptions (utils.c:630-639) */
+    /* AVOptions with the names, ranges and defaults of ffv1enc.c:1291-1307 */
+    int ec;
+    int ac;
+    int context_model;
+    /* new: placement */
+    int gpu;
+    int max_batch;
+    int depth;
+    ffgpu_encoder *enc;
+    ffgpu_decoder *dec;
+    /* decoder: pictures handed to the GPU, waiting to come back in order */
+    AVFrame *fifo[GPU_FIFO];
+    int fifo_head, fifo_count;
+} FFV1GpuContext;
+
+/* exported so that a test harness without libavutil/opt.c can set the private options */
+void ff_ffv1_gpu_set_options(void *priv, int slicecrc, int coder, int context)
+{
+    FFV1GpuContext *s = priv;
+    s->ec = slicecrc;
+    s->ac = coder;
+    s->context_model = context;
+}
+
+static av_cold int gpu_encode_init(AVCodecContext *avctx)
+{
+    FFV1GpuContext *s = avctx->priv_data;
+    ffgpu_enc_options o = { 0 };
+    const uint8_t *ex;
+    int ret, n;
+
+    o.width  = avctx->width;
+    o.height = avctx->height;
+    o.pix_fmt = av_get_pix_fmt_name(avctx->pix_fmt);
+    o.slices = avctx->slices;
+    o.level  = avctx->level;
+    o.gop_size = avctx->gop_size;
+    o.coder  = s->ac;
+    o.context = s->context_model;
+    o.slicecrc = s->ec;
+    o.strict_std_compliance = avctx->strict_std_compliance;
+    o.bits_per_raw_sample = avctx->bits_per_raw_sample;
+    o.device = s->gpu;
+    o.max_batch = s->max_batch;
+    o.pipeline_depth = s->depth;
+    if (avctx->flags & (AV_CODEC_FLAG_PASS1 | AV_CODEC_FLAG_PASS2)) {
+        avpriv_report_missing_feature(avctx, "2-pass statistics on the GPU path");
+        return AVERROR_PATCHWELCOME;
+    }
+    if ((ret = ffgpu_ffv1_encode_init(&s->enc, &o)) < 0) {
+        av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
+        return ret;                            /* same AVERROR values as encode_init */
+    }
+    n = ffgpu_ffv1_encoder_extradata(s->enc, &ex);
+    if (n > 0) {
+        avctx->extradata = av_mallocz(n + AV_INPUT_BUFFER_PADDING_SIZE);
+        if (!avctx->extradata)
+            return AVERROR(ENOMEM);
+        memcpy(avctx->extradata, ex, n);
+        avctx->extradata_size = n;
+    }
+    {
+        int info[8];
+        ffgpu_ffv1_encoder_info(s->enc, info);
+        avctx->bits_per_raw_sample = info[6];
+    }
+#if FF_API_CODED_FRAME
+FF_DISABLE_DEPRECATION_WARNINGS
+    avctx->coded_frame->pict_type = AV_PICTURE_TYPE_I;
+FF_ENABLE_DEPRECATION_WARNINGS
+#endif
+    return 0;
+}
+
+/* AVCodec.send_frame / receive_packet (avcodec.h:3654-3662): the encoder sets
+ * AV_CODEC_CAP_DELAY like ffv1enc.c:1332, pictures go into the launch-group pipeline and
+ * packets come back in presentation order as groups finish; a NULL frame drains it.
+ * AVERROR(EAGAIN) / AVERROR_EOF have the meaning libavcodec/encode.c expects. */
+static int gpu_send_frame(AVCodecContext *avctx, const AVFrame *pict)
+{
+    FFV1GpuContext *s = avctx->priv_data;
+    ffgpu_picture p = { { 0 } };
+    int ret, i;
+
+    if (!pict)
+        return ffgpu_ffv1_encode_send_frame(s->enc, NULL);
+    for (i = 0; i < 4; i++) {
+        p.data[i] = pict->data[i];
+        p.linesize[i] = pict->linesize[i];
+    }
+    p.interlaced_frame = pict->interlaced_frame;
+    p.top_field_first = pict->top_field_first;
+    p.sar_num = pict->sample_aspect_ratio.num;
+    p.sar_den = pict->sample_aspect_ratio.den;
+    p.pts = pict->pts;
+    ret = ffgpu_ffv1_encode_send_frame(s->enc, &p);   /* FFGPU_EAGAIN == AVERROR(EAGAIN) */
+    if (ret < 0 && ret != AVERROR(EAGAIN))
+        av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
+    return ret;
+}
+
+static int gpu_receive_packet(AVCodecContext *avctx, AVPacket *pkt)
+{
+    FFV1GpuContext *s = avctx->priv_data;
+    size_t size = 0;
+    int key = 0, ret;
+    int64_t pts = AV_NOPTS_VALUE;
+
+    if ((ret = ff_alloc_packet2(avctx, pkt, ffgpu_ffv1_encoder_max_packet(s->enc), 0)) < 0)
+        return ret;
+    ret = ffgpu_ffv1_encode_receive_packet(s->enc, pkt->data, pkt->size, &size, &key, &pts);
+    if (ret < 0) {                             /* EAGAIN, EOF ("encoded frame too large", ...) */
+        if (ret != AVERROR(EAGAIN) && ret != AVERROR_EOF)
+            av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
+        av_packet_unref(pkt);
+        return ret;
+    }
+    pkt->size = size;
+    pkt->pts = pkt->dts = pts;
+    if (key)
+        pkt->flags |= AV_PKT_FLAG_KEY;
+    return 0;
+}
+
+static av_cold int gpu_close(AVCodecContext *avctx)
+{
+    FFV1GpuContext *s = avctx->priv_data;
+    int i;
+    ffgpu_ffv1_encode_close(s->enc);
+    ffgpu_ffv1_decode_close(s->dec);
+    s->enc = NULL;
+    s->dec = NULL;
+    for (i = 0; i < GPU_FIFO; i++)
+        av_frame_free(&s->fifo[i]);
+    return 0;
+}
+
+static av_cold int gpu_decode_init(AVCodecContext *avctx)
+{
+    FFV1GpuContext *s = avctx->priv_data;
+    ffgpu_dec_options o = { 0 };
+    const char *name;
+    int ret;
+
+    o.width = avctx->width;
+    o.height = avctx->height;
+    o.extradata = avctx->extradata;
+    o.extradata_size = avctx->extradata_size;
+    o.device = s->gpu;
+    o.max_batch = s->max_batch;
+    o.pipeline_depth = s->depth;
+    if ((ret = ffgpu_ffv1_decode_init(&s->dec, &o)) < 0) {
+        av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
+        return ret;
+    }
+    if ((name = ffgpu_ffv1_decoder_pix_fmt(s->dec))) {
+        int info[8];
+        avctx->pix_fmt = av_get_pix_fmt(name);
+        ffgpu_ffv1_decoder_info(s->dec, info);
+        avctx->bits_per_raw_sample = info[6];
+    }
+    return 0;
+}
+
+/* AVCodec.decode: synchronous form (one packet in, one picture out).  The pipelined
+ * send_packet/receive_frame entry points of the C ABI map onto AVCodec.receive_frame in the
+ * same way the encoder above maps onto encode2; see INTEGRATION.md. */
+static int gpu_decode_frame(AVCodecContext *avctx, void *data, int *got_frame, AVPacket *avpkt)
+{
+    FFV1GpuContext *s = avctx->priv_data;
+    AVFrame *frame = data;
+    ffgpu_picture_out out = { { 0 } };
+    const char *name;
+    int ret, i;
+
+    /* v0/v1 streams announce their format in the first key frame: decode it into a picture
+     * only once the format is known (the library parses the header before it needs planes) */
+    if (!(name = ffgpu_ffv1_decoder_pix_fmt(s->dec))) {
+        ret = ffgpu_ffv1_decode_frame(s->dec, avpkt->data, avpkt->size, &out, got_frame);
+        if (!(name = ffgpu_ffv1_decoder_pix_fmt(s->dec)))
+            return ret < 0 ? ret : AVERROR_INVALIDDATA;
+    }
+    avctx->pix_fmt = av_get_pix_fmt(name);
+    if ((ret = ff_get_buffer(avctx, frame, AV_GET_BUFFER_FLAG_REF)) < 0)
+        return ret;
+    for (i = 0; i < 4; i++) {
+        out.data[i] = frame->data[i];
+        out.linesize[i] = frame->linesize[i];
+    }
+    ret = ffgpu_ffv1_decode_frame(s->dec, avpkt->data, avpkt->size, &out, got_frame);
+    if (ret < 0) {
+        av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
+        av_frame_unref(frame);
+        return ret;
+    }
+    frame->pict_type = AV_PICTURE_TYPE_I;
+    frame->key_frame = out.key_frame;
+    frame->interlaced_frame = out.interlaced_frame;
+    frame->top_field_first = out.top_field_first;
+    frame->sample_aspect_ratio = (AVRational){ out.sar_num, out.sar_den };
+    if (out.damaged_slices)
+        av_log(avctx, AV_LOG_ERROR, "%d damaged slice(s) concealed\n", out.damaged_slices);
+    return ret;                                /* bytes consumed, like ffv1dec.c:982 */
+}
+
+#define OFFSET(x) offsetof(FFV1GpuContext, x)
+#define VE AV_OPT_FLAG_VIDEO_PARAM | AV_OPT_FLAG_ENCODING_PARAM
+#define VD AV_OPT_FLAG_VIDEO_PARAM | AV_OPT_FLAG_DECODING_PARAM
+static const AVOption enc_options[] = {
+    /* unchanged from ffv1enc.c:1291-1307 */
+    { "slicecrc", "Protect slices with CRCs", OFFSET(ec), AV_OPT_TYPE_BOOL, { .i64 = -1 }, -1, 1, VE },
+    { "coder", "Coder type", OFFSET(ac), AV_OPT_TYPE_INT, { .i64 = 0 }, -2, 2, VE, "coder" },
+        { "rice", "Golomb rice", 0, AV_OPT_TYPE_CONST, { .i64 = 0 }, INT_MIN, INT_MAX, VE, "coder" },
+        { "range_def", "Range with default table", 0, AV_OPT_TYPE_CONST, { .i64 = -2 }, INT_MIN, INT_MAX, VE, "coder" },
+        { "range_tab", "Range with custom table", 0, AV_OPT_TYPE_CONST, { .i64 = 2 }, INT_MIN, INT_MAX, VE, "coder" },
+        { "ac", "Range with custom table (the ac option exists for compatibility and is deprecated)", 0,
+          AV_OPT_TYPE_CONST, { .i64 = 1 }, INT_MIN, INT_MAX, VE, "coder" },
+    { "context", "Context model", OFFSET(context_model), AV_OPT_TYPE_INT, { .i64 = 0 }, 0, 1, VE },
+    /* new */
+    { "gpu", "CUDA device ordinal", OFFSET(gpu), AV_OPT_TYPE_INT, { .i64 = 0 }, 0, 64, VE },
+    { "gpu_batch", "pictures per launch group (0 = auto)", OFFSET(max_batch), AV_OPT_TYPE_INT, { .i64 = 0 }, 0, 1024, VE },
+    { "gpu_depth", "launch groups in flight (0 = auto)", OFFSET(depth), AV_OPT_TYPE_INT, { .i64 = 0 }, 0, 8, VE },
+    { NULL }
+};
+static const AVOption dec_options[] = {
+    { "gpu", "CUDA device ordinal", OFFSET(gpu), AV_OPT_TYPE_INT, { .i64 = 0 }, 0, 64, VD },
+    { "gpu_batch", "packets per launch group (0 = auto)", OFFSET(max_batch), AV_OPT_TYPE_INT, { .i64 = 0 }, 0, 1024, VD },
+    { "gpu_depth", "launch groups in flight (0 = auto)", OFFSET(depth), AV_OPT_TYPE_INT, { .i64 = 0 }, 0, 8, VD },
+    { NULL }
+};
+
+static const AVClass enc_class = {
+    .class_name = "ffv1 gpu encoder", .item_name = av_default_item_name,
+    .option = enc_options, .version = LIBAVUTIL_VERSION_INT,
+};
+static const AVClass dec_class = {
+    .class_name = "ffv1 gpu decoder", .item_name = av_default_item_name,
+    .option = dec_options, .version = LIBAVUTIL_VERSION_INT,
+};
+
+AVCodec ff_ffv1_gpu_encoder = {
+    .name           = "ffv1_gpu",
+    .long_name      = NULL_IF_CONFIG_SMALL("FFmpeg video codec #1 (B200 CUDA slice path)"),
+    .type           = AVMEDIA_TYPE_VIDEO,
+    .id             = AV_CODEC_ID_FFV1,
+    .priv_data_size = sizeof(FFV1GpuContext),
+    .init           = gpu_encode_init,
+    .send_frame     = gpu_send_frame,
+    .receive_packet = gpu_receive_packet,
+    .close          = gpu_close,
+    .capabilities   = AV_CODEC_CAP_DELAY,
+    .pix_fmts       = (const enum AVPixelFormat[]) {   /* ffv1enc.c:1333-1355 */
+        AV_PIX_FMT_YUV420P,   AV_PIX_FMT_YUVA420P,  AV_PIX_FMT_YUVA422P,  AV_PIX_FMT_YUV444P,
+        AV_PIX_FMT_YUVA444P,  AV_PIX_FMT_YUV440P,   AV_PIX_FMT_YUV422P,   AV_PIX_FMT_YUV411P,
+        AV_PIX_FMT_YUV410P,   AV_PIX_FMT_0RGB32,    AV_PIX_FMT_RGB32,     AV_PIX_FMT_YUV420P16,
+        AV_PIX_FMT_YUV422P16, AV_PIX_FMT_YUV444P16, AV_PIX_FMT_YUV444P9,  AV_PIX_FMT_YUV422P9,
+        AV_PIX_FMT_YUV420P9,  AV_PIX_FMT_YUV420P10, AV_PIX_FMT_YUV422P10, AV_PIX_FMT_YUV444P10,
+        AV_PIX_FMT_YUV420P12, AV_PIX_FMT_YUV422P12, AV_PIX_FMT_YUV444P12,
+        AV_PIX_FMT_YUVA444P16, AV_PIX_FMT_YUVA422P16, AV_PIX_FMT_YUVA420P16,
+        AV_PIX_FMT_YUVA444P10, AV_PIX_FMT_YUVA422P10, AV_PIX_FMT_YUVA420P10,
+        AV_PIX_FMT_YUVA444P9, AV_PIX_FMT_YUVA422P9, AV_PIX_FMT_YUVA420P9,
+        AV_PIX_FMT_GRAY16,    AV_PIX_FMT_GRAY8,     AV_PIX_FMT_GBRP9,     AV_PIX_FMT_GBRP10,
+        AV_PIX_FMT_GBRP12,    AV_PIX_FMT_GBRP14,    AV_PIX_FMT_GBRAP10,   AV_PIX_FMT_GBRAP12,
+        AV_PIX_FMT_YA8,       AV_PIX_FMT_GRAY10,    AV_PIX_FMT_GRAY12,    AV_PIX_FMT_GBRP16,
+        AV_PIX_FMT_RGB48,     AV_PIX_FMT_GBRAP16,   AV_PIX_FMT_RGBA64,    AV_PIX_FMT_GRAY9,
+        AV_PIX_FMT_YUV420P14, AV_PIX_FMT_YUV422P14, AV_PIX_FMT_YUV444P14,
+        AV_PIX_FMT_YUV440P10, AV_PIX_FMT_YUV440P12,
+        AV_PIX_FMT_NONE
+    },
+    .priv_class     = &enc_class,
+};
+
+AVCodec ff_ffv1_gpu_decoder = {
+    .name           = "ffv1_gpu",
+    .long_name      = NULL_IF_CONFIG_SMALL("FFmpeg video codec #1 (B200 CUDA slice path)"),
+    .type           = AVMEDIA_TYPE_VIDEO,
+    .id             = AV_CODEC_ID_FFV1,
+    .priv_data_size = sizeof(FFV1GpuContext),
+    .init           = gpu_decode_init,
+    .close          = gpu_close,
+    .decode         = gpu_decode_frame,
+    .capabilities   = AV_CODEC_CAP_DR1,
+    .caps_internal  = FF_CODEC_CAP_INIT_CLEANUP,
+    .priv_class     = &dec_class,
+};

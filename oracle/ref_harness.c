@@ -33,8 +33,30 @@
 #include "libavcodec/thread.h"
 #include "libavcodec/ffv1.h"
 
+/* -DHARNESS_GPU builds the same harness around the product's libavcodec glue
+ * (integration/ffv1_gpu.c -> libffgpu.so) instead of the reference codec objects: both are
+ * then driven through the identical AVCodec boundary and can be compared packet by packet. */
+#ifdef HARNESS_GPU
+extern AVCodec ff_ffv1_gpu_encoder;
+extern AVCodec ff_ffv1_gpu_decoder;
+void ff_ffv1_gpu_set_options(void *priv, int slicecrc, int coder, int context);
+#define ff_ffv1_encoder ff_ffv1_gpu_encoder
+#define ff_ffv1_decoder ff_ffv1_gpu_decoder
+#define ffv1ref_encoder_open      ffv1glue_encoder_open
+#define ffv1ref_encoder_extradata ffv1glue_encoder_extradata
+#define ffv1ref_encoder_info      ffv1glue_encoder_info
+#define ffv1ref_encode            ffv1glue_encode
+#define ffv1ref_encoder_close     ffv1glue_encoder_close
+#define ffv1ref_decoder_open      ffv1glue_decoder_open
+#define ffv1ref_decode            ffv1glue_decode
+#define ffv1ref_decoder_close     ffv1glue_decoder_close
+#define ffv1ref_plane_geometry    ffv1glue_plane_geometry
+#define ffv1ref_last_error        ffv1glue_last_error
+#define ffv1ref_set_log_level     ffv1glue_set_log_level
+#else
 extern AVCodec ff_ffv1_encoder;
 extern AVCodec ff_ffv1_decoder;
+#endif
 
 /* ------------------------------------------------------------------ */
 /* libavutil / libavcodec services the FFV1 objects import             */
@@ -281,6 +303,21 @@ int ff_thread_ref_frame(ThreadFrame *dst, ThreadFrame *src)
     return av_frame_ref(dst->f, src->f);
 }
 
+#ifdef HARNESS_GPU
+int ff_get_buffer(AVCodecContext *avctx, AVFrame *frame, int flags)
+{
+    ThreadFrame tf = { frame, { avctx, avctx }, NULL };
+    return ff_thread_get_buffer(avctx, &tf, flags);
+}
+void av_packet_unref(AVPacket *pkt)
+{
+    memset(pkt, 0, sizeof(*pkt));
+}
+void avpriv_report_missing_feature(void *avc, const char *msg, ...)
+{
+    av_log(avc, AV_LOG_WARNING, "%s is not implemented\n", msg);
+}
+#endif
 void ff_thread_finish_setup(AVCodecContext *avctx) { (void)avctx; }
 void ff_thread_report_progress(ThreadFrame *f, int progress, int field) { (void)f; (void)progress; (void)field; }
 void ff_thread_await_progress(ThreadFrame *f, int progress, int field) { (void)f; (void)progress; (void)field; }
@@ -491,9 +528,14 @@ void *ffv1ref_encoder_open(const FFV1RefParams *p, int *err)
     a->strict_std_compliance = p->strict;
     a->bits_per_raw_sample = p->bits_per_raw_sample;
     /* AVOption defaults of ffv1enc.c:1291-1307, then the caller's values */
+#ifdef HARNESS_GPU
+    (void)s;
+    ff_ffv1_gpu_set_options(a->priv_data, p->slicecrc, p->coder, p->context);
+#else
     s->ec = p->slicecrc;
     s->ac = p->coder;
     s->context_model = p->context;
+#endif
     g_last_log[0] = 0;
     ret = ff_ffv1_encoder.init(a);
     if (ret < 0) {
@@ -518,6 +560,10 @@ int ffv1ref_encoder_extradata(void *hh, const uint8_t **data)
 void ffv1ref_encoder_info(void *hh, int info[8])
 {
     Harness *h = hh;
+#ifdef HARNESS_GPU
+    memset(info, 0, 8 * sizeof(int));
+    info[6] = h->avctx->bits_per_raw_sample;
+#else
     FFV1Context *s = h->avctx->priv_data;
     info[0] = s->version;
     info[1] = s->micro_version;
@@ -527,6 +573,7 @@ void ffv1ref_encoder_info(void *hh, int info[8])
     info[5] = s->ec;
     info[6] = s->bits_per_raw_sample;
     info[7] = s->colorspace;
+#endif
 }
 
 int ffv1ref_encode(void *hh, const uint8_t *const planes[4], const int linesize[4],
@@ -547,7 +594,22 @@ int ffv1ref_encode(void *hh, const uint8_t *const planes[4], const int linesize[
     h->in->pts = 0;
     memset(&pkt, 0, sizeof(pkt));
     g_last_log[0] = 0;
+#ifdef HARNESS_GPU
+    /* send_frame / receive_packet: one picture, flush, one packet (the EOF re-arms the handle) */
+    if ((ret = ff_ffv1_encoder.send_frame(a, h->in)) < 0)
+        return ret;
+    if ((ret = ff_ffv1_encoder.send_frame(a, NULL)) < 0)
+        return ret;
+    ret = ff_ffv1_encoder.receive_packet(a, &pkt);
+    if (ret >= 0) {
+        AVPacket eof;
+        got = 1;
+        memset(&eof, 0, sizeof(eof));
+        ff_ffv1_encoder.receive_packet(a, &eof);      /* AVERROR_EOF */
+    }
+#else
     ret = ff_ffv1_encoder.encode2(a, &pkt, h->in, &got);
+#endif
     if (ret < 0)
         return ret;
     if (!got)

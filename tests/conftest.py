@@ -23,6 +23,10 @@ def pytest_configure(config):
             os.path.join(ROOT, "oracle", "_ref", "libffv1ref.so")):
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref"],
                        check=True, stdout=subprocess.DEVNULL)
+    if os.path.isdir("/root/reference/libavcodec") and os.path.exists(
+            os.path.join(ROOT, "ffmpeg_ffv2_b200", "libffgpu.so")):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "glue"],
+                       check=False, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
     # the product library and the CPU emulation of its device functions: rebuild when stale

@@ -20,6 +20,9 @@ _ROOT = os.path.abspath(os.path.join(_HERE, ".."))
 PATHS = {
     "ref": (os.path.join(_ROOT, "oracle", "_ref", "libffv1ref.so"), "ffv1ref_"),
     "oracle": (os.path.join(_ROOT, "oracle", "libffv1_oracle.so"), "ffv1o_"),
+    # the product's libavcodec glue (integration/ffv1_gpu.c -> libffgpu.so) behind the SAME
+    # AVCodec-vtable harness as "ref": needs a GPU to encode/decode
+    "glue": (os.path.join(_ROOT, "oracle", "_ref", "libffv1glue.so"), "ffv1glue_"),
     # the product's device functions compiled for the CPU (tests/emul, test-only)
     "emul": (os.path.join(_ROOT, "tests", "emul", "libffv1_emul.so"), "ffv1emul_"),
 }

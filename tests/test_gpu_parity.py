@@ -247,6 +247,31 @@ def test_damaged_packets_behave_like_the_reference(fmt, kw):
         dec.close()
 
 
+def test_libavcodec_glue_is_a_drop_in():
+    """integration/ffv1_gpu.c (AVCodec objects forwarding to libffgpu.so) and the UNMODIFIED
+    reference codec objects, driven through the same AVCodec init/send/receive/decode/close
+    boundary by the same harness: identical extradata, packets and pictures"""
+    if not (cc.available("glue") and cc.available("ref")):
+        pytest.skip("oracle/_ref (reference + glue harness) not built")
+    w, h = 352, 288
+    for fmt, kw in (("yuv420p", dict(slices=4)), ("yuv420p10le", dict(slices=30, gop_size=1)),
+                    ("bgr0", dict(level=3, coder=2, context=1)), ("yuv444p16le", dict(level=3)),
+                    ("yuv420p", dict())):
+        ref = cc.Encoder("ref", w, h, fmt, **kw)
+        glue = cc.Encoder("glue", w, h, fmt, **kw)
+        assert glue.extradata == ref.extradata
+        dref = cc.Decoder("ref", w, h, ref.extradata)
+        dglue = cc.Decoder("glue", w, h, ref.extradata)
+        for i in range(3):
+            planes = synth.testsrc2_like(fmt, w, h, i)
+            a, b = ref.encode(planes), glue.encode(planes)
+            assert a == b, (fmt, kw, i)
+            fa, fb = dref.decode(a), dglue.decode(a)
+            assert dref.pix_fmt == dglue.pix_fmt
+            for x, y in zip(fa, fb):
+                assert np.array_equal(x, y), (fmt, kw, i)
+
+
 def test_device_resident_batch():
     """pictures already in HBM -> packets in HBM (the path bench.py's `value` times)"""
     import torch
