@@ -78,6 +78,7 @@ SYMBOLS = [
     ("ffgpu_ffv1_decode_init", C.c_int, [C.POINTER(C.c_void_p), C.POINTER(DecOptions)]),
     ("ffgpu_ffv1_decoder_pix_fmt", C.c_char_p, [C.c_void_p]),
     ("ffgpu_ffv1_decoder_info", None, [C.c_void_p, C.POINTER(C.c_int)]),
+    ("ffgpu_ffv1_decoder_probe", C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     ("ffgpu_ffv1_decode_frame", C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t,
                                           C.POINTER(PictureOut), C.POINTER(C.c_int)]),
     ("ffgpu_ffv1_decode_send_packet", C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int64,
@@ -311,9 +312,11 @@ class FFV1Decoder:
     def decode(self, pkt, fmt_hint=None):
         """AVCodec.decode: packet bytes -> list of 2-D uint8 planes.  For v0/v1 streams the
         output format is only known after the header; pass fmt_hint or rely on a retry."""
+        if self.pix_fmt is None:
+            r = lib().ffgpu_ffv1_decoder_probe(self.h, pkt, len(pkt))
+            if r < 0:
+                raise FFGpuError("decoder_probe", r, _err())
         fmt = self.pix_fmt or fmt_hint
-        if fmt is None:
-            raise ValueError("output pix_fmt unknown before the first key frame: pass fmt_hint")
         out, arrs = self._alloc_out(fmt)
         got = C.c_int()
         r = lib().ffgpu_ffv1_decode_frame(self.h, pkt, len(pkt), C.byref(out), C.byref(got))

@@ -1052,6 +1052,29 @@ extern "C" int ffgpu_ffv1_decode_init(ffgpu_decoder **pdec, const ffgpu_dec_opti
     return 0;
 }
 
+/* Streams without extradata (v0/v1) announce their parameters in the first key frame: parse
+ * that header (host only, nothing is decoded) so the caller can size its output picture. */
+extern "C" int ffgpu_ffv1_decoder_probe(ffgpu_decoder *d, const uint8_t *pkt, size_t size)
+{
+    FFDecSlice tmp[1];
+    FFDecFrameInfo info;
+    FFDecHostState hs;
+    int r;
+    if (!d || !pkt)
+        return fail(FFGPU_EINVAL, "null argument");
+    if (d->have_params)
+        return 0;
+    hs = d->hs;
+    hs.max_slices = 1;
+    r = ff_dec_parse_packet(&d->s, &hs, pkt, size, 0, tmp, &info);
+    if (r < 0)
+        return fail(r, "invalid packet (%d)", r);
+    if ((r = dec_setup_stream(d)) < 0)
+        return r;
+    d->hs.max_slices = d->max_slices;
+    return 0;
+}
+
 extern "C" const char *ffgpu_ffv1_decoder_pix_fmt(const ffgpu_decoder *d)
 {
     return d && d->s.pf ? d->s.pf->name : NULL;

@@ -994,10 +994,21 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
     int32_t *cur = D.lines;
     const int32_t *prev = D.lines;
     uint8_t *outp = D.frame;
-    int ostep = 0;
+    const uint8_t *prow = D.frame, *pprow = D.frame;   /* picture rows y-1 and y-2 (planar modes) */
+    int ostep = 0, havep = 0, havepp = 0, usepic = 0;
     int sbase = 0;
     (void)tab_; (void)row_; (void)qt_all_;
 
+    /* planar YCbCr, full-resolution planes: the previous lines are read back from the output
+     * picture itself (what decode_plane just stored, ffv1dec.c:142-161), so no separate line
+     * buffer is written.  Subsampled chroma planes keep private line buffers: with an odd
+     * luma offset the chroma rectangles of neighbouring slices share a column/row
+     * (ffv1dec.c:324-327), and another thread may be writing it. */
+#define FF_PIC(rowp, xx) (smode == 1 ? (int)(rowp)[(size_t)(xx) * ostep]                                     \
+                          : smode == 2 ? (int)(int16_t) * (const uint16_t *)((rowp) + (size_t)(xx) * ostep)   \
+                                       : (int)(int16_t)(*(const uint16_t *)((rowp) + (size_t)(xx) * ostep) >> shl))
+#define FF_PREV(xx) (usepic ? (havep ? FF_PIC(prow, xx) : 0) : prev[xx])
+#define FF_PREV2(xx) (usepic ? (havepp ? FF_PIC(pprow, xx) : 0) : cur[xx])
     c.buf = pkt + d.pkt_off;
     c.low = d.low;
     c.range = d.range;
@@ -1006,8 +1017,9 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
     c.overread = d.overread;
 
     for (int k = 0; k < P.ncoded; k++)
-        for (x = 0; x < 2 * D.line_stride; x++)
-            D.lines[(size_t)k * 2 * D.line_stride + x] = 0;
+        if (!smode || P.cp[k].hs || P.cp[k].vs)
+            for (x = 0; x < 2 * D.line_stride; x++)
+                D.lines[(size_t)k * 2 * D.line_stride + x] = 0;
 
     if (!ff_line_first(P, d, &it))
         goto finish;
@@ -1043,18 +1055,23 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
                                (size_t)((d.y >> cp.vs) + it.y) * P.pitch[cp.mem] +
                                (size_t)(d.x >> cp.hs) * cp.step + cp.off;
                         ostep = cp.step;
+                        prow = outp - P.pitch[cp.mem];
+                        pprow = prow - P.pitch[cp.mem];
+                        havep = it.y >= 1;
+                        havepp = it.y >= 2;
+                        usepic = !cp.hs && !cp.vs;
                     }
                 }
                 x = 0;
-                T = prev[0];
-                LT = cur[0];
+                T = FF_PREV(0);
+                LT = FF_PREV2(0);
                 L = T;
                 LL = 0;
                 /* look-ahead on the previous line: q0..q3 = prev[min(x+1..x+4, w-1)] */
-                q0 = prev[ff_min(1, w - 1)];
-                q1 = prev[ff_min(2, w - 1)];
-                q2 = prev[ff_min(3, w - 1)];
-                q3 = prev[ff_min(4, w - 1)];
+                q0 = FF_PREV(ff_min(1, w - 1));
+                q1 = FF_PREV(ff_min(2, w - 1));
+                q2 = FF_PREV(ff_min(3, w - 1));
+                q3 = FF_PREV(ff_min(4, w - 1));
                 if (c.overread > 2) {                /* is_input_end at line start */
                     err = 1;
                     break;
@@ -1067,11 +1084,11 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
             q0 = q1;
             q1 = q2;
             q2 = q3;
-            q3 = prev[ff_min(x + 5, w - 1)];
+            q3 = FF_PREV(ff_min(x + 5, w - 1));
             ctx = FF_QT(qo, (L - LT) & 0xFF) + FF_QT(qo, 256 + ((LT - T) & 0xFF)) +
                   FF_QT(qo, 512 + ((T - RT) & 0xFF));
             if (five)
-                ctx += FF_QT(qo, 768 + ((LL - L) & 0xFF)) + FF_QT(qo, 1024 + ((cur[x] - T) & 0xFF));
+                ctx += FF_QT(qo, 768 + ((LL - L) & 0xFF)) + FF_QT(qo, 1024 + ((FF_PREV2(x) - T) & 0xFF));
             sign = ctx < 0;
             ctx = sbase + (sign ? -ctx : ctx);
             if (ctx != cur_ctx) {
@@ -1135,8 +1152,9 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
             diff = sign ? -diff : diff;
             v = (int)(((uint32_t)ff_median3(L, L + T - LT, T) + (uint32_t)diff) & mask);
             v = use32 ? v : (int)(int16_t)v;
-            cur[x] = v;
-            if (smode == 1) {                        /* decode_plane's store, ffv1dec.c:142-161 */
+            if (!usepic)
+                cur[x] = v;
+            if (smode == 1) {                 /* decode_plane's store, ffv1dec.c:142-161 */
                 *outp = (uint8_t)v;
             } else if (smode == 2) {
                 *(uint16_t *)outp = (uint16_t)v;
@@ -1163,7 +1181,9 @@ finish:
     res->end_pos = c.pos;
     res->overread = c.overread;
     res->error = err;
-
+#undef FF_PIC
+#undef FF_PREV
+#undef FF_PREV2
 }
 
 /* decode_slice after the header, Golomb-Rice streams (ffv1dec.c:304-350) */

@@ -161,6 +161,10 @@ int ffgpu_ffv1_decode_init(ffgpu_decoder **dec, const ffgpu_dec_options *opt);
  * init for streams with extradata, else after the first key frame.  NULL if unknown. */
 const char *ffgpu_ffv1_decoder_pix_fmt(const ffgpu_decoder *dec);
 void ffgpu_ffv1_decoder_info(const ffgpu_decoder *dec, int info[8]);
+/* v0/v1 streams carry their parameters in the first key frame instead of extradata
+ * (read_header, ffv1dec.c:538-590): parse that header without decoding anything, so that
+ * the output format is known before the caller allocates the picture.  0 or an error. */
+int ffgpu_ffv1_decoder_probe(ffgpu_decoder *dec, const uint8_t *pkt, size_t pkt_size);
 
 /* AVCodec.decode = decode_frame, ffv1dec.c:837-983, synchronous.  Returns the number of
  * bytes consumed (pkt_size) like the reference, negative on error. */

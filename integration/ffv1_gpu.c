@@ -201,12 +201,13 @@ static int gpu_decode_frame(AVCodecContext *avctx, void *data, int *got_frame, A
     const char *name;
     int ret, i;
 
-    /* v0/v1 streams announce their format in the first key frame: decode it into a picture
-     * only once the format is known (the library parses the header before it needs planes) */
+    /* v0/v1 streams announce their format in the first key frame */
     if (!(name = ffgpu_ffv1_decoder_pix_fmt(s->dec))) {
-        ret = ffgpu_ffv1_decode_frame(s->dec, avpkt->data, avpkt->size, &out, got_frame);
-        if (!(name = ffgpu_ffv1_decoder_pix_fmt(s->dec)))
-            return ret < 0 ? ret : AVERROR_INVALIDDATA;
+        if ((ret = ffgpu_ffv1_decoder_probe(s->dec, avpkt->data, avpkt->size)) < 0) {
+            av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
+            return ret;
+        }
+        name = ffgpu_ffv1_decoder_pix_fmt(s->dec);
     }
     avctx->pix_fmt = av_get_pix_fmt(name);
     if ((ret = ff_get_buffer(avctx, frame, AV_GET_BUFFER_FLAG_REF)) < 0)
