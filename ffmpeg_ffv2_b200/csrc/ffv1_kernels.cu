@@ -71,7 +71,8 @@ k_symbolize(const FFDevParams P, const FFDevSlice *__restrict__ slices,
  * above it (two coalesced row reads); the left / top-left / top-right neighbours come from
  * the adjacent lanes by warp shuffle, only the lanes at a 32-sample seam or at the slice
  * border issue an extra load.  The context quantiser lives in shared memory. */
-__global__ void __launch_bounds__(SYM_THREADS)
+template <bool WIDE>
+__global__ void __launch_bounds__(SYM_THREADS, 3)
 k_symbolize_planar(const FFDevParams P, const FFDevSlice *__restrict__ slices,
                    const uint8_t *__restrict__ frames, const int16_t *__restrict__ qt,
                    uint32_t *__restrict__ tokens, uint32_t *__restrict__ weight)
@@ -91,13 +92,14 @@ k_symbolize_planar(const FFDevParams P, const FFDevSlice *__restrict__ slices,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nrows_step = (SYM_THREADS / 32) * gridDim.z;
     const int five = sq[FF_MAX_CTX_INPUTS * 256];
-    const int wide = P.sbits > 8;
     const int shift = P.packed_lsb ? 0 : 16 - P.sbits;
     const int cbits = P.cbits;
     uint32_t wsum = 0, base = 0;
 
-#define SAMPLE(rowp, xx) ((int)(int16_t)(wide ? (*(const uint16_t *)((rowp) + 2 * (size_t)(xx)) >> shift) \
-                                              : (rowp)[(size_t)(xx) * step]))
+    /* sample xx of the row starting at rowp: u8 with a byte step, or u16 (LSB- or MSB-aligned);
+     * wrapped to int16 like the reference's sample buffer (ffv1enc.c:291-305) */
+#define SAMPLE(rowp, xx) (WIDE ? (int)(int16_t)(((const uint16_t *)(rowp))[xx] >> shift) \
+                               : (int)(rowp)[(xx) * step])
     /* each warp takes groups of SYM_ROWS consecutive rows: the SYM_ROWS + 1 row loads of a
      * step are independent and all in flight together (memory-level parallelism), and the
      * row above a sample is the previous row of the same group */
@@ -111,6 +113,8 @@ k_symbolize_planar(const FFDevParams P, const FFDevSlice *__restrict__ slices,
         const int ngroups = (h + SYM_ROWS - 1) / SYM_ROWS;
         for (int g = blockIdx.z * (SYM_THREADS / 32) + warp; g < ngroups; g += nrows_step) {
             const int y0 = g * SYM_ROWS;
+            const uint8_t *rtop = pbase + (size_t)(y0 - 1) * pitch;    /* row y0-1 */
+            uint32_t *trow = tok + base + (uint32_t)y0 * w;
             for (int x0 = 0; x0 < w; x0 += 32) {
                 const int x = x0 + lane;
                 const bool valid = x < w;
@@ -118,20 +122,20 @@ k_symbolize_planar(const FFDevParams P, const FFDevSlice *__restrict__ slices,
 #pragma unroll
                 for (int j = 0; j <= SYM_ROWS; j++) {
                     const int yy = y0 - 1 + j;
-                    v[j] = (valid && yy >= 0 && yy < h) ? SAMPLE(pbase + (size_t)yy * pitch, x) : 0;
+                    v[j] = (valid && yy >= 0 && yy < h) ? SAMPLE(rtop + (size_t)j * pitch, x) : 0;
                 }
 #pragma unroll
                 for (int j = 1; j <= SYM_ROWS; j++) {
                     const int y = y0 + j - 1;
                     if (y >= h)
                         break;
-                    const uint8_t *r0 = pbase + (size_t)y * pitch;
+                    const uint8_t *r0 = rtop + (size_t)j * pitch;
                     const uint8_t *r1 = r0 - pitch, *r2 = r1 - pitch;
                     const int cur = v[j], T = v[j - 1];
                     int L = __shfl_up_sync(0xffffffffu, cur, 1);
                     int LT = __shfl_up_sync(0xffffffffu, T, 1);
                     int RT = __shfl_down_sync(0xffffffffu, T, 1);
-                    int LL = __shfl_up_sync(0xffffffffu, cur, 2);
+                    int LL = five ? __shfl_up_sync(0xffffffffu, cur, 2) : 0;
                     if (valid) {
                         if (x == 0) {                /* left border: ffv1enc.c:287 */
                             L = T;
@@ -155,13 +159,11 @@ k_symbolize_planar(const FFDevParams P, const FFDevSlice *__restrict__ slices,
                             ctx += sq[768 + ((LL - L) & 0xFF)] + sq[1024 + ((TT - T) & 0xFF)];
                         }
                         int diff = cur - ff_median3(L, L + T - LT, T);
-                        if (ctx < 0) {
-                            ctx = -ctx;
-                            diff = -diff;
-                        }
-                        diff = ff_fold(diff, cbits);
+                        const int neg = ctx < 0;
+                        ctx = neg ? -ctx : ctx;
+                        diff = ff_fold(neg ? -diff : diff, cbits);
                         const uint32_t t = ((uint32_t)diff << FF_TOKEN_CTX_BITS) | (uint32_t)(ctx_base + ctx);
-                        tok[base + (uint32_t)y * w + x] = t;
+                        trow[(j - 1) * w + x] = t;
                         wsum += ff_token_weight(t);
                     }
                 }
@@ -313,8 +315,12 @@ extern "C" int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nfr
             if (zr < 1) zr = 1;
             if (zr > 64) zr = 64;
             dim3 g2(P->nslices, nframes, zr);
-            k_symbolize_planar<<<g2, SYM_THREADS, 0, st>>>(*P, E->slices, E->frames, E->qt, E->tokens,
-                                                           E->weight);
+            if (P->sbits > 8)
+                k_symbolize_planar<true><<<g2, SYM_THREADS, 0, st>>>(*P, E->slices, E->frames, E->qt,
+                                                                     E->tokens, E->weight);
+            else
+                k_symbolize_planar<false><<<g2, SYM_THREADS, 0, st>>>(*P, E->slices, E->frames, E->qt,
+                                                                      E->tokens, E->weight);
         } else {
             k_symbolize<<<grid, SYM_THREADS, 0, st>>>(*P, E->slices, E->frames, E->qt, E->tokens, E->weight);
         }
