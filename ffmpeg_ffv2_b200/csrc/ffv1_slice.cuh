@@ -234,18 +234,12 @@ __device__ __forceinline__ void ff_cp_async_wait(void)
 }
 #endif
 #define FF_CODE_THREADS 128      /* threads per block of the slice-coder kernels */
-/* per-thread context-row cache: FF_ROW_WAYS rows of 32 state bytes, direct-mapped by the low
- * bits of the context index (neighbouring contexts differ by 1, 11 or 121, all odd, so the
- * contexts a sample sequence alternates between land in different ways).  37 words per
- * thread: odd stride, conflict-free when all lanes touch the same way and slot. */
-#define FF_ROW_WAYS 4
-#define FF_ROW_THREAD_WORDS (FF_ROW_WAYS * FF_ROW_WORDS + 1)
 
 #if defined(__CUDACC__)
 /* statically named shared memory, so that the device code below addresses it with LDS/STS
  * and immediate offsets instead of generic pointers */
 static __shared__ FFRacTables ff_s_tab;
-static __shared__ uint32_t ff_s_rows[FF_CODE_THREADS * FF_ROW_THREAD_WORDS];
+static __shared__ uint32_t ff_s_rows[FF_CODE_THREADS * FF_ROW_WORDS];
 extern __shared__ int16_t ff_s_qt[];             /* decoder: qt_count quant table sets */
 /* stage B token stream: per lane a ring of 16-byte chunks filled by cp.async (LDGSTS) six
  * chunks ahead of the read position, so a lane's DRAM/L2 miss never stalls its warp */
@@ -255,40 +249,15 @@ static __shared__ FFU128 ff_s_tok[FF_TOK_CHUNKS * FF_CODE_THREADS];
 #endif
 #if defined(__CUDA_ARCH__)
 #define FF_TAB(i)   (((const uint8_t *)&ff_s_tab)[i])
-#define FF_ROWB(i)  (((uint8_t *)ff_s_rows)[threadIdx.x * (FF_ROW_THREAD_WORDS * 4) + way * (FF_ROW_WORDS * 4) + (i)])
-#define FF_ROWW(wy) (&ff_s_rows[threadIdx.x * FF_ROW_THREAD_WORDS + (wy) * FF_ROW_WORDS])
+#define FF_ROWB(i)  (((uint8_t *)ff_s_rows)[threadIdx.x * (FF_ROW_WORDS * 4) + (i)])
+#define FF_ROWW     (&ff_s_rows[threadIdx.x * FF_ROW_WORDS])
 #define FF_QT(set_off, i) (ff_s_qt[(set_off) + (i)])
 #else
 #define FF_TAB(i)   (((const uint8_t *)tab_)[i])
-#define FF_ROWB(i)  (((uint8_t *)row_)[way * (FF_ROW_WORDS * 4) + (i)])
-#define FF_ROWW(wy) (row_ + (wy) * FF_ROW_WORDS)
+#define FF_ROWB(i)  (((uint8_t *)row_)[i])
+#define FF_ROWW     (row_)
 #define FF_QT(set_off, i) (qt_all_[(set_off) + (i)])
 #endif
-
-/* make context `cx` the current row: hit -> nothing; miss -> write the evicted row back to
- * the state arena and fetch the new one.  tag0..tag3 / way are locals of the caller. */
-#define FF_ROW_SELECT(cx, arena)                                                              \
-    do {                                                                                      \
-        int t_;                                                                               \
-        way = (cx) & (FF_ROW_WAYS - 1);                                                       \
-        t_ = way == 0 ? tag0 : way == 1 ? tag1 : way == 2 ? tag2 : tag3;                      \
-        if (t_ != (cx)) {                                                                     \
-            if (t_ >= 0)                                                                      \
-                ff_row_store(FF_ROWW(way), (arena) + (size_t)t_ * FF_CONTEXT_SIZE);           \
-            ff_row_load(FF_ROWW(way), (arena) + (size_t)(cx) * FF_CONTEXT_SIZE);              \
-            tag0 = way == 0 ? (cx) : tag0;                                                    \
-            tag1 = way == 1 ? (cx) : tag1;                                                    \
-            tag2 = way == 2 ? (cx) : tag2;                                                    \
-            tag3 = way == 3 ? (cx) : tag3;                                                    \
-        }                                                                                     \
-    } while (0)
-#define FF_ROW_FLUSH(arena)                                                                   \
-    do {                                                                                      \
-        if (tag0 >= 0) ff_row_store(FF_ROWW(0), (arena) + (size_t)tag0 * FF_CONTEXT_SIZE);    \
-        if (tag1 >= 0) ff_row_store(FF_ROWW(1), (arena) + (size_t)tag1 * FF_CONTEXT_SIZE);    \
-        if (tag2 >= 0) ff_row_store(FF_ROWW(2), (arena) + (size_t)tag2 * FF_CONTEXT_SIZE);    \
-        if (tag3 >= 0) ff_row_store(FF_ROWW(3), (arena) + (size_t)tag3 * FF_CONTEXT_SIZE);    \
-    } while (0)
 
 
 
@@ -349,7 +318,7 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
     FFRacEnc c;
     const uint32_t n = sl.ntok;
     uint32_t i = 0, nb;
-    int tag0 = -1, tag1 = -1, tag2 = -1, tag3 = -1, way = 0;
+    int cur_ctx = -1;
     int a = 0, e = 0, neg = 0, step = 0, nsteps = 0;
     (void)tab_; (void)row_;
 
@@ -386,7 +355,12 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
             i++;
             ctx = (int)(tok & FF_TOKEN_CTX_MASK);
             diff = (int32_t)tok >> FF_TOKEN_CTX_BITS;
-            FF_ROW_SELECT(ctx, state);
+            if (ctx != cur_ctx) {
+                if (cur_ctx >= 0)
+                    ff_row_store(FF_ROWW, state + (size_t)cur_ctx * FF_CONTEXT_SIZE);
+                ff_row_load(FF_ROWW, state + (size_t)ctx * FF_CONTEXT_SIZE);
+                cur_ctx = ctx;
+            }
             a = diff < 0 ? -diff : diff;
             neg = diff < 0;
             e = ffrac_ilog2((uint32_t)a);
@@ -410,7 +384,8 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
             ffrac_enc_shift1(&c);
         step++;
     }
-    FF_ROW_FLUSH(state);
+    if (cur_ctx >= 0)
+        ff_row_store(FF_ROWW, state + (size_t)cur_ctx * FF_CONTEXT_SIZE);
     nb = ffrac_enc_finish(&c, tab_, 1);              /* ffv1enc.c:1242 */
     *overflow = c.overflow;
     return nb;
@@ -1010,8 +985,7 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
     const int shl = 16 - P.sbits, shr = 2 * P.sbits - 16;
     FFRacDec c;
     FFLineIt it;
-    int x, err = 0, need_new = 1;
-    int tag0 = -1, tag1 = -1, tag2 = -1, tag3 = -1, way = 0;
+    int x, err = 0, cur_ctx = -1, need_new = 1;
     int w = 0, five = 0, sign = 0, e = 0, mi = 0, slot = 0;
     uint32_t a = 0;
     int T = 0, LT = 0, L = 0, LL = 0, RT = 0;
@@ -1117,7 +1091,12 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
                 ctx += FF_QT(qo, 768 + ((LL - L) & 0xFF)) + FF_QT(qo, 1024 + ((FF_PREV2(x) - T) & 0xFF));
             sign = ctx < 0;
             ctx = sbase + (sign ? -ctx : ctx);
-            FF_ROW_SELECT(ctx, D.rstate);
+            if (ctx != cur_ctx) {
+                if (cur_ctx >= 0)
+                    ff_row_store(FF_ROWW, D.rstate + (size_t)cur_ctx * FF_CONTEXT_SIZE);
+                ff_row_load(FF_ROWW, D.rstate + (size_t)ctx * FF_CONTEXT_SIZE);
+                cur_ctx = ctx;
+            }
             need_new = 0;
             slot = 0;
         }
@@ -1192,7 +1171,8 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
         }
     }
 finish:
-    FF_ROW_FLUSH(D.rstate);
+    if (cur_ctx >= 0)
+        ff_row_store(FF_ROWW, D.rstate + (size_t)cur_ctx * FF_CONTEXT_SIZE);
     /* end-of-slice check, ffv1dec.c:351-359 */
     if (P.version > 2) {
         uint8_t term = 129;

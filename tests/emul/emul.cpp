@@ -114,7 +114,7 @@ extern "C" int ffv1emul_encode(void *h, const uint8_t *const planes[4], const in
     for (int i = 0; i < P.nslices; i++) {
         FFSliceRect r = { e->sl[i].x, e->sl[i].y, e->sl[i].w, e->sl[i].h };
         uint32_t ovf = 0;
-        alignas(16) uint32_t row[FF_ROW_THREAD_WORDS];
+        alignas(16) uint32_t row[FF_ROW_WORDS];
         int rc = ff_enc_slice_prefix(&e->s, i, &r, keyf, 3, 0, 1, &pre[i], &e->prebytes[(size_t)i * 2048], 2048);
         if (rc < 0) return rc;
         pre[i].byte_off = (uint32_t)i * 2048;
@@ -237,7 +237,7 @@ extern "C" int ffv1emul_decode(void *h, const uint8_t *pkt_in, int size, uint8_t
         FFDecCtx D;
         D.qt_all = d->qt.data(); D.tab = &d->s.cur_tab; D.rstate = rs; D.vstate = vs;
         D.lines = d->lines.data(); D.line_stride = line_stride; D.frame = frame;
-        alignas(16) uint32_t row[FF_ROW_THREAD_WORDS];
+        alignas(16) uint32_t row[FF_ROW_WORDS];
         ff_decode_slice(P, work[i], pkt.data(), D, &res[i], row);
         if (P.ac != FF_AC_GOLOMB && P.version > 2) {
             int v = (int)work[i].size - (int)res[i].end_pos - 2 - 5 * P.ec;
