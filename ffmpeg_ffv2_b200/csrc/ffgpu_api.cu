@@ -837,7 +837,6 @@ struct ffgpu_decoder {
     int fill, head, flushing;
     uint64_t launches;
     int profile, profile_next;
-    int lb_ok;                  /* slice headers follow the regular grid (widths bounded) */
     void *events[FFK_DEC_KERNELS + 1];
     Trace trace;
 };
@@ -899,7 +898,6 @@ static int dec_setup_stream(ffgpu_decoder *d)
     }
     if (d->depth > MAX_DEPTH)
         d->depth = MAX_DEPTH;
-    d->lb_ok = 1;
     d->have_params = 1;
     return 0;
 }
@@ -1108,21 +1106,6 @@ static void dec_fill_dev(const ffgpu_decoder *d, const DecJob *j, uint8_t *frame
     D->max_ctx = d->max_ctx;
     D->state_per_frame = d->intra;
     D->qt_count = d->s.qt_count;
-    {
-        /* shared-memory line buffer for the range decoder when the widest slice is narrow:
-         * planar YCbCr, 3-input context model, odd 32-bit-word stride per lane */
-        int five = 0, wmax = d->line_stride - 8;
-        for (int i = 0; i < d->s.qt_count; i++)
-            five |= d->s.qt[i][3][127] || d->s.qt[i][4][127];
-        D->lb_stride = 0;
-        if (d->s.colorspace == 0 && d->s.ac != FF_AC_GOLOMB && !five && wmax <= 160 && d->lb_ok) {
-            int st = (wmax + 2) | 1;               /* int16 elements */
-            st = ((st + 1) & ~1) + 2;              /* even count of int16 -> whole words ... */
-            if (((st / 2) & 1) == 0)
-                st += 2;                           /* ... and an odd number of words */
-            D->lb_stride = st;
-        }
-    }
     D->hdr.micro_version = d->s.micro_version;
     D->hdr.qt_count = d->s.qt_count;
     D->hdr.ctx_cap = d->max_ctx;

@@ -470,9 +470,6 @@ k_decode(const FFDevParams P, const FFDecDev D, int nframes)
             C.lines = D.lines + (size_t)gid * P.ncoded * 2 * D.line_stride;
             C.line_stride = D.line_stride;
             C.frame = D.frames + (size_t)f * P.frame_bytes;
-            C.lb_stride = D.lb_stride;
-            C.lb_off = D.qt_count * FF_QT_STRIDE;
-            C.lb_host = 0;
             ff_decode_slice(P, w, D.pkt, C, &r, 0);
         }
     }
@@ -517,8 +514,7 @@ extern "C" int ffk_decode_group(const FFDevParams *P, const FFDecDev *D, int nfr
     }
     mark(D->events, FFK_DEC_SORT + 1, st);
     k_decode<<<(total + CODE_THREADS - 1) / CODE_THREADS, CODE_THREADS,
-               ((size_t)D->qt_count * FF_QT_STRIDE + (size_t)D->lb_stride * CODE_THREADS) * sizeof(int16_t),
-               st>>>(*P, *D, nframes);
+               (size_t)D->qt_count * FF_QT_STRIDE * sizeof(int16_t), st>>>(*P, *D, nframes);
     mark(D->events, FFK_DECODE + 1, st);
     if (!launch_ok()) return FFGPU_EXTERNAL;
     return 3;

@@ -74,7 +74,6 @@ typedef struct FFDecDev {
     int state_per_frame;
     int qt_count;                   /* quant table sets of the stream                   */
     FFDecHdr hdr;                   /* constants for device-side slice header parsing   */
-    int lb_stride;                  /* int16 per lane of the shared-memory line buffer (0 = off) */
     uint32_t *weight;               /* [nframes*max_slices] slice byte counts            */
     uint32_t *weight_sorted;
     const uint32_t *iota;

@@ -708,10 +708,6 @@ typedef struct FFDecCtx {
     int32_t *lines;             /* [ncoded][2][line_stride] scratch                   */
     int      line_stride;
     uint8_t *frame;             /* output picture                                     */
-    /* shared-memory line buffer (range decoder, narrow slices): int16 per sample, lb_stride
-     * elements per lane starting lb_off int16 into the dynamic shared memory; 0 = unused */
-    int lb_stride, lb_off;
-    int16_t *lb_host;           /* CPU emulation only                                  */
 } FFDecCtx;
 
 FFGPU_HD int ff_wrap_sample(const FFDevParams &P, int v)
@@ -1000,9 +996,6 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
     uint8_t *outp = D.frame;
     const uint8_t *prow = D.frame, *pprow = D.frame;   /* picture rows y-1 and y-2 (planar modes) */
     int ostep = 0, havep = 0, havepp = 0, usepic = 0;
-    /* shared-memory line buffer; a header-declared rectangle wider than it takes the global path */
-    const int lbmode = smode && D.lb_stride > 0 && d.w + 2 <= D.lb_stride;
-    int lt1 = 0, lt2 = 0;                            /* first samples of lines y-1 and y-2 */
     int sbase = 0;
     (void)tab_; (void)row_; (void)qt_all_;
 
@@ -1014,15 +1007,6 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
 #define FF_PIC(rowp, xx) (smode == 1 ? (int)(rowp)[(size_t)(xx) * ostep]                                     \
                           : smode == 2 ? (int)(int16_t) * (const uint16_t *)((rowp) + (size_t)(xx) * ostep)   \
                                        : (int)(int16_t)(*(const uint16_t *)((rowp) + (size_t)(xx) * ostep) >> shl))
-    /* narrow slices (the high-slice-count configurations): the previous line of the current
-     * plane lives in shared memory, one int16 row per lane, updated in place as the line is
-     * decoded (T is read before position x is overwritten, LT is carried in a register, the
-     * first sample of line y-2 in lt2).  No per-sample global load is left. */
-#if defined(__CUDA_ARCH__)
-#define FF_LB(xx) (((int16_t *)(ff_s_qt + D.lb_off))[threadIdx.x * D.lb_stride + (xx)])
-#else
-#define FF_LB(xx) (D.lb_host[xx])
-#endif
 #define FF_PREV(xx) (usepic ? (havep ? FF_PIC(prow, xx) : 0) : prev[xx])
 #define FF_PREV2(xx) (usepic ? (havepp ? FF_PIC(pprow, xx) : 0) : cur[xx])
     c.buf = pkt + d.pkt_off;
@@ -1032,7 +1016,7 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
     c.end = d.size;
     c.overread = d.overread;
 
-    for (int k = 0; k < P.ncoded && !lbmode; k++)
+    for (int k = 0; k < P.ncoded; k++)
         if (!smode || P.cp[k].hs || P.cp[k].vs)
             for (x = 0; x < 2 * D.line_stride; x++)
                 D.lines[(size_t)k * 2 * D.line_stride + x] = 0;
@@ -1079,28 +1063,15 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
                     }
                 }
                 x = 0;
-                if (lbmode) {
-                    if (it.y == 0) {                 /* new plane: memset of the sample buffer */
-                        for (int i = 0; i < w; i++)
-                            FF_LB(i) = 0;
-                        lt1 = lt2 = 0;
-                    }
-                    T = FF_LB(0);
-                    LT = lt2;
-                    lt2 = lt1;
-                } else {
-                    T = FF_PREV(0);
-                    LT = FF_PREV2(0);
-                }
+                T = FF_PREV(0);
+                LT = FF_PREV2(0);
                 L = T;
                 LL = 0;
                 /* look-ahead on the previous line: q0..q3 = prev[min(x+1..x+4, w-1)] */
-                if (!lbmode) {
-                    q0 = FF_PREV(ff_min(1, w - 1));
-                    q1 = FF_PREV(ff_min(2, w - 1));
-                    q2 = FF_PREV(ff_min(3, w - 1));
-                    q3 = FF_PREV(ff_min(4, w - 1));
-                }
+                q0 = FF_PREV(ff_min(1, w - 1));
+                q1 = FF_PREV(ff_min(2, w - 1));
+                q2 = FF_PREV(ff_min(3, w - 1));
+                q3 = FF_PREV(ff_min(4, w - 1));
                 if (c.overread > 2) {                /* is_input_end at line start */
                     err = 1;
                     break;
@@ -1109,15 +1080,11 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
                 err = 1;
                 break;
             }
-            if (lbmode) {
-                RT = FF_LB(ff_min(x + 1, w - 1));
-            } else {
-                RT = q0;
-                q0 = q1;
-                q1 = q2;
-                q2 = q3;
-                q3 = FF_PREV(ff_min(x + 5, w - 1));
-            }
+            RT = q0;
+            q0 = q1;
+            q1 = q2;
+            q2 = q3;
+            q3 = FF_PREV(ff_min(x + 5, w - 1));
             ctx = FF_QT(qo, (L - LT) & 0xFF) + FF_QT(qo, 256 + ((LT - T) & 0xFF)) +
                   FF_QT(qo, 512 + ((T - RT) & 0xFF));
             if (five)
@@ -1185,12 +1152,8 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
             diff = sign ? -diff : diff;
             v = (int)(((uint32_t)ff_median3(L, L + T - LT, T) + (uint32_t)diff) & mask);
             v = use32 ? v : (int)(int16_t)v;
-            if (lbmode) {
-                FF_LB(x) = (int16_t)v;
-                lt1 = x ? lt1 : v;
-            } else if (!usepic) {
+            if (!usepic)
                 cur[x] = v;
-            }
             if (smode == 1) {                 /* decode_plane's store, ffv1dec.c:142-161 */
                 *outp = (uint8_t)v;
             } else if (smode == 2) {
@@ -1218,7 +1181,6 @@ finish:
     res->end_pos = c.pos;
     res->overread = c.overread;
     res->error = err;
-#undef FF_LB
 #undef FF_PIC
 #undef FF_PREV
 #undef FF_PREV2

@@ -237,12 +237,6 @@ extern "C" int ffv1emul_decode(void *h, const uint8_t *pkt_in, int size, uint8_t
         FFDecCtx D;
         D.qt_all = d->qt.data(); D.tab = &d->s.cur_tab; D.rstate = rs; D.vstate = vs;
         D.lines = d->lines.data(); D.line_stride = line_stride; D.frame = frame;
-        std::vector<int16_t> lb(P.width + 8, 0);
-        int five = 0;
-        for (int q = 0; q < d->s.qt_count; q++) five |= d->s.qt[q][3][127] || d->s.qt[q][4][127];
-        /* alternate between the two previous-line paths so both are exercised */
-        D.lb_stride = (d->s.colorspace == 0 && !five && (i & 1) == 0) ? P.width + 8 : 0;
-        D.lb_off = 0; D.lb_host = lb.data();
         alignas(16) uint32_t row[FF_ROW_WORDS];
         ff_decode_slice(P, work[i], pkt.data(), D, &res[i], row);
         if (P.ac != FF_AC_GOLOMB && P.version > 2) {
