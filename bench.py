@@ -349,54 +349,81 @@ def main():
         enc = F.FFV1Encoder(w, h, fmt, device=local, max_batch=vb, pipeline_depth=args.e2e_depth, **opts)
         dec = F.FFV1Decoder(w, h, enc.extradata, device=local, max_batch=vb, pipeline_depth=args.e2e_depth)
 
+        import queue
+
         def e2e_step():
-            """encoder and decoder run concurrently, like a transcode pipeline: packets are fed
-            to the decoder as soon as the encoder returns them, so H2D of pictures, kernels of
-            both directions and D2H of decoded pictures overlap"""
-            out_pk = []
-            sent = dec_sent = dec_got = 0
-            enc_done = dec_done = False
-            deadline = time.perf_counter() + 120.0
+            """encoder and decoder run concurrently on two host threads, like the codec threads
+            of a transcoder: packets go to the decoder as soon as the encoder returns them, so
+            H2D of pictures, kernels of both directions and D2H of decoded pictures overlap and
+            a blocking wait in one codec does not stall the other (ctypes releases the GIL)"""
             NE = B * args.e2e_repeat
-            while dec_got < NE:
-                if time.perf_counter() > deadline:
-                    raise SystemExit("e2e pipeline stalled: sent %d, packets %d, decoded %d" % (
-                        sent, len(out_pk), dec_got))
-                if sent < NE and enc.send_frame(host_planes[sent % B], pts=sent):
-                    sent += 1
-                    if sent == NE:
-                        enc.send_frame(None)
-                while True:
-                    if dec_sent < len(out_pk):
-                        if not dec.send_packet(out_pk[dec_sent], pts=dec_sent, dst=dsts[dec_sent % B]):
-                            break
-                        dec_sent += 1
-                        if dec_sent == NE:
-                            dec.send_packet(None)
-                        continue
-                    if enc_done:
-                        break
-                    r = enc.receive_packet()
-                    if r == F.EOF:
-                        enc_done = True
-                        break
-                    if r is None:
-                        break
-                    out_pk.append(r[0])
-                while not dec_done:
-                    r = dec.receive_frame()
-                    if r == F.EOF:
-                        dec_done = True
-                        break
-                    if r is None:
-                        break
-                    dec_got += 1
-            # leave both handles drained and reusable (the EOF ends the flush)
-            while not enc_done:
-                enc_done = enc.receive_packet() == F.EOF
-            while not dec_done:
-                dec_done = dec.receive_frame() == F.EOF
-            return out_pk, dec_got
+            q = queue.Queue()
+            out_pk = []
+            state = {"decoded": 0, "err": None}
+            deadline = time.perf_counter() + 120.0
+
+            def enc_thread():
+                try:
+                    sent, done = 0, False
+                    while not done:
+                        if time.perf_counter() > deadline:
+                            raise RuntimeError("encoder stalled at %d" % sent)
+                        if sent < NE and enc.send_frame(host_planes[sent % B], pts=sent):
+                            sent += 1
+                            if sent == NE:
+                                enc.send_frame(None)
+                        while True:
+                            r = enc.receive_packet()
+                            if r == F.EOF:
+                                done = True
+                                break
+                            if r is None:
+                                break
+                            out_pk.append(r[0])
+                            q.put(r[0])
+                except Exception as e:           # noqa: BLE001
+                    state["err"] = e
+                q.put(None)
+
+            def dec_thread():
+                try:
+                    sent, got, done, eos = 0, 0, False, False
+                    pend = None
+                    while not done:
+                        if time.perf_counter() > deadline:
+                            raise RuntimeError("decoder stalled at %d/%d" % (got, sent))
+                        if pend is None and not eos:
+                            try:
+                                pend = q.get(timeout=0.0005) if sent > got else q.get(timeout=0.05)
+                                if pend is None:
+                                    eos = True
+                                    dec.send_packet(None)
+                            except queue.Empty:
+                                pend = None
+                        if pend is not None and dec.send_packet(pend, pts=sent, dst=dsts[sent % B]):
+                            sent += 1
+                            pend = None
+                        while True:
+                            r = dec.receive_frame()
+                            if r == F.EOF:
+                                done = True
+                                break
+                            if r is None:
+                                break
+                            got += 1
+                    state["decoded"] = got
+                except Exception as e:           # noqa: BLE001
+                    state["err"] = e
+
+            te = threading.Thread(target=enc_thread)
+            td = threading.Thread(target=dec_thread)
+            te.start()
+            td.start()
+            te.join()
+            td.join()
+            if state["err"] is not None:
+                raise SystemExit("e2e pipeline failed: %r" % (state["err"],))
+            return out_pk, state["decoded"]
 
         dsts = []
         for i in range(B):

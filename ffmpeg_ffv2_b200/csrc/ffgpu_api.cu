@@ -831,6 +831,7 @@ struct ffgpu_decoder {
     uint8_t *d_initial;
     uint8_t *d_state_shared;
     uint8_t *d_prev;            /* last output picture, for concealment */
+    cudaEvent_t prev_ready;
     uint32_t *d_iota;
     int have_prev;
     DecJob jobs[MAX_DEPTH];
@@ -972,6 +973,8 @@ static int dec_device_init(ffgpu_decoder *d)
         CK(cudaMalloc(&d->d_state_shared, state_frame));
     CK(cudaMalloc(&d->d_prev, P->frame_bytes));
     CK(cudaMemset(d->d_prev, 0, P->frame_bytes));
+    CK(cudaEventCreateWithFlags(&d->prev_ready, cudaEventDisableTiming));
+    CK(cudaEventRecord(d->prev_ready, 0));
     {
         const size_t n = (size_t)d->max_batch * d->max_slices;
         uint32_t *iota = (uint32_t *)malloc(n * sizeof(uint32_t));
@@ -1235,6 +1238,8 @@ static int dec_finish_frame(ffgpu_decoder *d, DecJob *j, int i, ffgpu_picture_ou
     }
     if (damaged && d->have_prev) {
         const uint8_t *prev = i > 0 ? j->d_frames + (size_t)(i - 1) * P->frame_bytes : d->d_prev;
+        if (i == 0)
+            CK(cudaEventSynchronize(d->prev_ready));
         for (int s = m->nslices - 1; s >= 0; s--)
             if (m->damaged[s]) {
                 r = ffk_conceal_rect(P, frame, prev, m->rect[s].x, m->rect[s].y, m->rect[s].w, m->rect[s].h,
@@ -1248,9 +1253,10 @@ static int dec_finish_frame(ffgpu_decoder *d, DecJob *j, int i, ffgpu_picture_ou
         CK(cudaStreamSynchronize(j->stream));
     }
     if (i == j->n - 1) {
-        /* keep the last picture of the group for the next group's concealment */
+        /* keep the last picture of the group for the next group's concealment; the copy is
+         * only awaited by the (rare) concealment path itself */
         CK(cudaMemcpyAsync(d->d_prev, frame, P->frame_bytes, cudaMemcpyDeviceToDevice, j->stream));
-        CK(cudaStreamSynchronize(j->stream));
+        CK(cudaEventRecord(d->prev_ready, j->stream));
     }
     d->have_prev = 1;
     if (out) {
@@ -1526,6 +1532,7 @@ extern "C" int ffgpu_ffv1_decode_close(ffgpu_decoder *d)
             dec_free_job(&d->jobs[i]);
         cudaFree(d->d_qt); cudaFree(d->d_tab); cudaFree(d->d_initial); cudaFree(d->d_state_shared);
         cudaFree(d->d_prev); cudaFree(d->d_iota);
+        if (d->prev_ready) cudaEventDestroy(d->prev_ready);
     }
     free(d->h_slices);
     ff_stream_free(&d->s);
