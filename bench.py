@@ -189,9 +189,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="pictures per step and GPU (0 = default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-groups", type=int, default=4, help="launch groups a step's pictures are split into")
-    ap.add_argument("--e2e-depth", type=int, default=4, help="launch groups in flight (e2e leg)")
-    ap.add_argument("--e2e-repeat", type=int, default=3,
+    ap.add_argument("--e2e-groups", type=int, default=1, help="launch groups a step's pictures are split into")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="launch groups in flight (e2e leg)")
+    ap.add_argument("--e2e-repeat", type=int, default=6,
                     help="the e2e leg streams the step's pictures this many times back to back, so "
                          "pipeline fill and drain are amortised like in a long transcode")
     args = ap.parse_args()
