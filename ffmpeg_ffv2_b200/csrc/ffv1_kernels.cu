@@ -470,6 +470,8 @@ k_decode(const FFDevParams P, const FFDecDev D, int nframes)
             C.lines = D.lines + (size_t)gid * P.ncoded * 2 * D.line_stride;
             C.line_stride = D.line_stride;
             C.frame = D.frames + (size_t)f * P.frame_bytes;
+            C.gate_div = D.gate_div;
+            C.gate_wait = D.gate_wait;
             ff_decode_slice(P, w, D.pkt, C, &r, 0);
         }
     }

@@ -208,6 +208,8 @@ FFGPU_HD void ff_enc_resume(FFRacEnc *c, const FFRacPrefix &pre, const uint8_t *
  * same slot) so that the per-decision state read/update is an LDS/STS instead of a global
  * round trip; it is written back only when the context changes. */
 #define FF_ROW_WORDS 9
+#define FF_NEW_WAIT 24          /* iterations a lane may wait for the rest of its warp before the (divergent,
+                                 * expensive) per-sample set-up runs; measured optimum on B200 */
 
 typedef struct
 #if defined(__CUDACC__)
@@ -708,6 +710,7 @@ typedef struct FFDecCtx {
     int32_t *lines;             /* [ncoded][2][line_stride] scratch                   */
     int      line_stride;
     uint8_t *frame;             /* output picture                                     */
+    int gate_div, gate_wait;    /* sample set-up gating: 1/gate_div of the lanes, max wait */
 } FFDecCtx;
 
 FFGPU_HD int ff_wrap_sample(const FFDevParams &P, int v)
@@ -985,7 +988,7 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
     const int shl = 16 - P.sbits, shr = 2 * P.sbits - 16;
     FFRacDec c;
     FFLineIt it;
-    int x, err = 0, cur_ctx = -1, need_new = 1;
+    int x, err = 0, cur_ctx = -1, need_new = 1, waited = 0;
     int w = 0, five = 0, sign = 0, e = 0, mi = 0, slot = 0;
     uint32_t a = 0;
     int T = 0, LT = 0, L = 0, LL = 0, RT = 0;
@@ -997,7 +1000,7 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
     const uint8_t *prow = D.frame, *pprow = D.frame;   /* picture rows y-1 and y-2 (planar modes) */
     int ostep = 0, havep = 0, havepp = 0, usepic = 0;
     int sbase = 0;
-    (void)tab_; (void)row_; (void)qt_all_;
+    (void)tab_; (void)row_; (void)qt_all_; (void)waited;
 
     /* planar YCbCr, full-resolution planes: the previous lines are read back from the output
      * picture itself (what decode_plane just stored, ffv1dec.c:142-161), so no separate line
@@ -1026,6 +1029,24 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
     x = -1;                                          /* -1: the line has to be set up */
     for (;;) {
         int s, r1, bit, done, diff;
+#if defined(__CUDA_ARCH__)
+        /* The sample set-up below is the expensive, divergent part of the loop.  The lanes
+         * of a warp finish their symbols at different iterations, so running it whenever ANY
+         * lane needs a new sample executes it almost every iteration for a handful of lanes.
+         * Instead a lane that needs a sample waits (idles) until a quarter of the active
+         * lanes need one, or until it has waited FF_NEW_WAIT iterations. */
+        {
+            const unsigned act = __activemask();
+            const unsigned need = __ballot_sync(act, need_new);
+            const int go = __popc(need) * D.gate_div >= __popc(act) ||
+                           __any_sync(act, need_new && waited >= D.gate_wait);
+            if (need_new && !go) {
+                waited++;
+                continue;
+            }
+            waited = 0;
+        }
+#endif
         if (need_new) {
             int ctx;
             if (x < 0 || x == w) {
