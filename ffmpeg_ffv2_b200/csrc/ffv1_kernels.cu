@@ -200,6 +200,8 @@ k_code_range(const FFDevParams P, const FFEncDev E, int nframes)
 {
     for (int i = threadIdx.x; i < (int)sizeof(FFRacTables) / 4; i += CODE_THREADS)
         ((uint32_t *)&ff_s_tab)[i] = ((const uint32_t *)E.tab)[i];
+    for (int i = threadIdx.x; i < FF_STAB_ROWS * FF_STAB_STRIDE; i += CODE_THREADS)
+        ff_s_stab[i] = (uint8_t)ff_slot_of(i / FF_STAB_STRIDE, i % FF_STAB_STRIDE);
     __syncthreads();
     const int tid = blockIdx.x * CODE_THREADS + threadIdx.x;
     if (tid >= nframes * P.nslices)

@@ -302,6 +302,37 @@ FFGPU_HD void ffrac_enc_shift1(FFRacEnc *c)
     c->range <<= 8;
 }
 
+/* state slot of decision `step` of a residual with exponent e (put_symbol_inline,
+ * ffv1enc.c:185-231): 0 zero flag | 1..e+1 unary exponent | e+2..2e+1 mantissa | 2e+2 sign */
+#define FF_STAB_STRIDE 40
+#define FF_STAB_ROWS   19
+FFGPU_HD int ff_slot_of(int e, int step)
+{
+    if (step == 0)
+        return 0;
+    if (step <= e + 1)
+        return 1 + ff_min(step - 1, 9);
+    if (step <= 2 * e + 1)
+        return 22 + ff_min(2 * e + 1 - step, 9);
+    return 11 + ff_min(e, 10);
+}
+
+#if defined(__CUDACC__)
+static __shared__ uint8_t ff_s_stab[FF_STAB_ROWS * FF_STAB_STRIDE];
+/* shared-memory byte access through an explicit 32-bit shared address: one LDS/STS each,
+ * no generic-address arithmetic in the decision loop */
+__device__ __forceinline__ uint32_t ff_lds8(uint32_t sa)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(sa));
+    return v;
+}
+__device__ __forceinline__ void ff_sts8(uint32_t sa, uint32_t v)
+{
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(sa), "r"(v) : "memory");
+}
+#endif
+
 /* Stage B, range coder.  The 32 lanes of a warp code 32 different slices, so the loop is
  * written as ONE BINARY DECISION PER ITERATION with a small per-lane state machine
  * (put_symbol_inline, ffv1enc.c:185-231, unrolled over `step`): a lane that is inside a
@@ -321,10 +352,15 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
     const uint32_t n = sl.ntok;
     uint32_t i = 0, nb;
     int cur_ctx = -1;
-    int a = 0, e = 0, neg = 0, step = 0, nsteps = 0;
+    int e = 0, step = 0, nsteps = 0;
+    uint64_t seq = 0;                                /* bit k = value of decision k of the residual */
     (void)tab_; (void)row_;
 
 #if defined(__CUDA_ARCH__)
+    const uint32_t row_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_rows[threadIdx.x * FF_ROW_WORDS]);
+    const uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_tab);
+    const uint32_t stab_sa = (uint32_t)__cvta_generic_to_shared(ff_s_stab);
+    uint32_t srow = stab_sa, slot = 0;
     const uint32_t nchunks = (n + 3) >> 2;
     for (uint32_t ch = 0; ch < FF_TOK_AHEAD; ch++) {
         if (ch < nchunks)
@@ -334,9 +370,9 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
 #endif
     ff_enc_resume(&c, pre, pre_bytes, out, sl.bs_cap);
     for (;;) {
-        int slot, bit, s, r1, rb, um, mm;
+        int bit, s, r1, rb;
         if (step == nsteps) {                        /* fetch the next residual */
-            uint32_t tok;
+            uint32_t tok, a, neg;
             int ctx, diff;
             if (i == n)
                 break;
@@ -363,28 +399,58 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
                 ff_row_load(FF_ROWW, state + (size_t)ctx * FF_CONTEXT_SIZE);
                 cur_ctx = ctx;
             }
-            a = diff < 0 ? -diff : diff;
+            a = (uint32_t)(diff < 0 ? -diff : diff);
             neg = diff < 0;
-            e = ffrac_ilog2((uint32_t)a);
-            nsteps = a ? 2 * e + 3 : 1;
+            e = ffrac_ilog2(a);
+            /* the residual's decisions as a bit string, first decision in bit 0:
+             * zero flag, e ones, a zero, the e mantissa bits MSB first, the sign */
+            if (a) {
+                uint32_t m = a & ((1u << e) - 1), rev = 0;
+#if defined(__CUDA_ARCH__)
+                rev = e ? __brev(m) >> (32 - e) : 0; /* mantissa reversed: MSB goes out first */
+#else
+                for (int k = 0; k < e; k++)
+                    rev |= ((m >> k) & 1u) << (e - 1 - k);
+#endif
+                seq = ((uint64_t)((1u << e) - 1) << 1) | ((uint64_t)rev << (e + 2)) |
+                      ((uint64_t)neg << (2 * e + 2));
+                nsteps = 2 * e + 3;
+            } else {
+                seq = 1;
+                nsteps = 1;
+            }
             step = 0;
+#if defined(__CUDA_ARCH__)
+            srow = stab_sa + (uint32_t)e * FF_STAB_STRIDE;
+            slot = 0;
+#endif
         }
-        /* (slot, bit) of decision `step`, branch-free */
-        um = ff_min(step - 1, 9);                    /* unary index, steps 1..e+1      */
-        mm = 2 * e + 1 - step;                       /* mantissa bit, steps e+2..2e+1  */
-        slot = step == 0 ? 0 : step <= e + 1 ? 1 + um : step <= 2 * e + 1 ? 22 + ff_min(mm, 9)
-                                                                          : 11 + ff_min(e, 10);
-        bit = step == 0 ? (a == 0) : step <= e ? 1 : step == e + 1 ? 0
-                                 : step <= 2 * e + 1 ? ((a >> (mm & 31)) & 1) : neg;
-        s = FF_ROWB(slot);
-        r1 = (c.range * s) >> 8;                     /* put_rac, rangecoder.h:104-121 */
-        rb = c.range - r1;
-        FF_ROWB(slot) = FF_TAB(s + (bit ? 0 : 256));
+        bit = (int)(seq & 1);
+        seq >>= 1;
+#if defined(__CUDA_ARCH__)
+        {
+            const uint32_t sa = row_sa + slot;
+            s = (int)ff_lds8(sa);
+            r1 = (c.range * s) >> 8;                 /* put_rac, rangecoder.h:104-121 */
+            rb = c.range - r1;
+            ff_sts8(sa, ff_lds8(tab_sa + (uint32_t)s + (bit ? 0u : 256u)));
+            step++;
+            slot = ff_lds8(srow + (uint32_t)step);   /* slot of the next decision */
+        }
+#else
+        {
+            const int slot = ff_slot_of(e, step);
+            s = FF_ROWB(slot);
+            r1 = (c.range * s) >> 8;
+            rb = c.range - r1;
+            FF_ROWB(slot) = FF_TAB(s + (bit ? 0 : 256));
+            step++;
+        }
+#endif
         c.low += bit ? rb : 0;
         c.range = bit ? r1 : rb;
         if (c.range < 0x100)
             ffrac_enc_shift1(&c);
-        step++;
     }
     if (cur_ctx >= 0)
         ff_row_store(FF_ROWW, state + (size_t)cur_ctx * FF_CONTEXT_SIZE);
