@@ -1078,6 +1078,10 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
                                        : (int)(int16_t)(*(const uint16_t *)((rowp) + (size_t)(xx) * ostep) >> shl))
 #define FF_PREV(xx) (usepic ? (havep ? FF_PIC(prow, xx) : 0) : prev[xx])
 #define FF_PREV2(xx) (usepic ? (havepp ? FF_PIC(pprow, xx) : 0) : cur[xx])
+#if defined(__CUDA_ARCH__)
+    const uint32_t row_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_rows[threadIdx.x * FF_ROW_WORDS]);
+    const uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_tab);
+#endif
     c.buf = pkt + d.pkt_off;
     c.low = d.low;
     c.range = d.range;
@@ -1188,11 +1192,19 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
             slot = 0;
         }
         /* one binary decision: get_rac + refill, rangecoder.h:123-152 */
+#if defined(__CUDA_ARCH__)
+        s = (int)ff_lds8(row_sa + (uint32_t)slot);
+        r1 = (c.range * s) >> 8;
+        c.range -= r1;
+        bit = c.low >= c.range;
+        ff_sts8(row_sa + (uint32_t)slot, ff_lds8(tab_sa + (uint32_t)s + (bit ? 0u : 256u)));
+#else
         s = FF_ROWB(slot);
         r1 = (c.range * s) >> 8;
         c.range -= r1;
         bit = c.low >= c.range;
         FF_ROWB(slot) = FF_TAB(s + (bit ? 0 : 256));
+#endif
         c.low -= bit ? c.range : 0;
         c.range = bit ? r1 : c.range;
         if (c.range < 0x100) {
