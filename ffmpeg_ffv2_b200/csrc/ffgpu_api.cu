@@ -524,6 +524,8 @@ static int enc_fetch(ffgpu_encoder *e, EncJob *j)
 
 extern "C" int ffgpu_ffv1_encode_send_frame(ffgpu_encoder *e, const ffgpu_picture *pic)
 {
+    if (e)
+        cudaSetDevice(e->opt.device);        /* the current device is per host thread */
     EncJob *j;
     int r, key, set, ps;
     if (!e)
@@ -573,6 +575,8 @@ extern "C" int ffgpu_ffv1_encode_send_frame(ffgpu_encoder *e, const ffgpu_pictur
 extern "C" int ffgpu_ffv1_encode_receive_packet(ffgpu_encoder *e, uint8_t *pkt, size_t cap,
                                                 size_t *size, int *key_frame, int64_t *pts)
 {
+    if (e)
+        cudaSetDevice(e->opt.device);        /* the current device is per host thread */
     EncJob *j;
     int r, i;
     if (!e)
@@ -653,6 +657,8 @@ extern "C" int ffgpu_ffv1_encode_frame(ffgpu_encoder *e, const ffgpu_picture *pi
 extern "C" int ffgpu_ffv1_encode_device(ffgpu_encoder *e, const void *d_frames, int nframes,
                                         void *cuda_stream)
 {
+    if (e)
+        cudaSetDevice(e->opt.device);        /* the current device is per host thread */
     EncJob *j;
     FFEncDev E;
     cudaStream_t st;
@@ -707,6 +713,8 @@ static int enc_device_sizes(ffgpu_encoder *e, EncJob *j)
 extern "C" int ffgpu_ffv1_encode_device_result(ffgpu_encoder *e, int frame, const void **d_pkt,
                                                size_t *pkt_size)
 {
+    if (e)
+        cudaSetDevice(e->opt.device);        /* the current device is per host thread */
     EncJob *j;
     int r;
     if (!e || !e->dev_ready)
@@ -724,6 +732,8 @@ extern "C" int ffgpu_ffv1_encode_device_result(ffgpu_encoder *e, int frame, cons
 extern "C" int ffgpu_ffv1_encode_device_fetch(ffgpu_encoder *e, int frame, uint8_t *pkt, size_t cap,
                                               size_t *pkt_size)
 {
+    if (e)
+        cudaSetDevice(e->opt.device);        /* the current device is per host thread */
     const void *d;
     size_t n;
     int r = ffgpu_ffv1_encode_device_result(e, frame, &d, &n);
@@ -768,6 +778,7 @@ extern "C" int ffgpu_ffv1_encode_close(ffgpu_encoder *e)
     if (!e)
         return 0;
     if (e->dev_ready) {
+        cudaSetDevice(e->opt.device);
         cudaDeviceSynchronize();
         for (int i = 0; i <= FFK_ENC_KERNELS; i++)
             if (e->events[i])
@@ -1290,6 +1301,8 @@ static int dec_launch_group(ffgpu_decoder *d, DecJob *j)
 extern "C" int ffgpu_ffv1_decode_send_packet(ffgpu_decoder *d, const uint8_t *pkt, size_t size,
                                               int64_t pts, const ffgpu_picture_out *dst)
 {
+    if (d)
+        cudaSetDevice(d->opt.device);        /* the current device is per host thread */
     DecJob *j;
     int r;
     if (!d)
@@ -1361,6 +1374,8 @@ extern "C" int ffgpu_ffv1_decode_send_packet(ffgpu_decoder *d, const uint8_t *pk
 
 extern "C" int ffgpu_ffv1_decode_receive_frame(ffgpu_decoder *d, ffgpu_picture_out *out)
 {
+    if (d)
+        cudaSetDevice(d->opt.device);        /* the current device is per host thread */
     DecJob *j;
     int r, i;
     if (!d)
@@ -1448,6 +1463,8 @@ extern "C" int ffgpu_ffv1_decode_device(ffgpu_decoder *d, const uint8_t *const *
                                         const size_t *sizes, int nframes, void *d_frames,
                                         void *cuda_stream)
 {
+    if (d)
+        cudaSetDevice(d->opt.device);        /* the current device is per host thread */
     DecJob *j;
     cudaStream_t st;
     int r;
@@ -1529,6 +1546,7 @@ extern "C" int ffgpu_ffv1_decode_close(ffgpu_decoder *d)
         if (d->events[i])
             cudaEventDestroy((cudaEvent_t)d->events[i]);
     if (d->dev_ready) {
+        cudaSetDevice(d->opt.device);
         cudaDeviceSynchronize();
         for (int i = 0; i < MAX_DEPTH; i++)
             dec_free_job(&d->jobs[i]);
