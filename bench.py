@@ -147,7 +147,7 @@ def run_cpu(wl, frames, threads, budget_s, max_frames):
                 enc_fps=n / t_enc, dec_fps=n / t_dec, fps=n / (t_enc + t_dec))
 
 
-def reference_arm(args, wl, rank, world):
+def reference_arm(args, wl, rank, world, real_stdout):
     """--impl reference: rank 0 alone times the reference CPU implementation"""
     if rank != 0:
         return
@@ -176,10 +176,14 @@ def reference_arm(args, wl, rank, world):
                              sample, len(res), threads)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=real_stdout, flush=True)
 
 
 def main():
+    # the contract is ONE JSON line on stdout: keep the real stdout for it and send whatever
+    # libraries print to fd 1 (e.g. the NCCL version banner) to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -202,7 +206,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        reference_arm(args, wl, rank, world)
+        reference_arm(args, wl, rank, world, real_stdout)
         return 0
 
     import torch
@@ -509,7 +513,7 @@ def main():
         "e2e": e2e, "cpu_baseline": cpu, "pcie": pcie,
     }
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=real_stdout, flush=True)
     enc.close()
     dec.close()
     if world > 1:
