@@ -56,7 +56,7 @@ def raw_metrics(rep):
             "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct"]
     res = collections.OrderedDict()
     for r in rows[2:]:
-        name = r[ix["Kernel Name"]].split("(")[0]
+        name = r[ix["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0].strip()
         res[name] = {w: (r[ix[w]], units[ix[w]]) for w in want if w in ix}
     return res
 
