@@ -77,8 +77,6 @@ k_symbolize_planar(const FFDevParams P, const FFDevSlice *__restrict__ slices,
                    const uint8_t *__restrict__ frames, const int16_t *__restrict__ qt,
                    uint32_t *__restrict__ tokens, uint32_t *__restrict__ weight)
 {
-    typedef cub::BlockReduce<uint32_t, SYM_THREADS> Reduce;
-    __shared__ typename Reduce::TempStorage tmp;
     __shared__ int16_t sq[FF_QT_STRIDE];
     {
         const uint32_t *src = (const uint32_t *)(qt + (size_t)P.set_qidx[0] * FF_QT_STRIDE);
@@ -172,8 +170,12 @@ k_symbolize_planar(const FFDevParams P, const FFDevSlice *__restrict__ slices,
         base += (uint32_t)w * h;
     }
 #undef SAMPLE
-    wsum = Reduce(tmp).Sum(wsum);
-    if (threadIdx.x == 0 && weight)
+    /* per-warp reduction + one atomic per warp: no block-wide barrier at the end, so warps
+     * with fewer rows retire early */
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    if (lane == 0 && weight && wsum)
         atomicAdd(&weight[(size_t)blockIdx.y * P.nslices + blockIdx.x], wsum);
 }
 
