@@ -485,7 +485,27 @@ def main():
         e2.record()
         torch.cuda.synchronize()
         pcie = {"h2d_GBps": nb / e0.elapsed_time(e1) / 1e6, "d2h_GBps": nb / e1.elapsed_time(e2) / 1e6}
-        del hp, dp
+        # both directions at once (what the e2e pipeline asks of the link and of host DRAM)
+        hq = torch.empty(nb, dtype=torch.uint8).pin_memory()
+        dq = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        torch.cuda.synchronize()
+        d0, d1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
+        d0.record()
+        s1.wait_event(d0)
+        s2.wait_event(d0)
+        with torch.cuda.stream(s1):
+            for _ in range(2):
+                dp.copy_(hp, non_blocking=True)
+        with torch.cuda.stream(s2):
+            for _ in range(2):
+                hq.copy_(dq, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(s1)
+        torch.cuda.current_stream().wait_stream(s2)
+        d1.record()
+        torch.cuda.synchronize()
+        pcie["duplex_GBps_each_way"] = 2 * nb / d0.elapsed_time(d1) / 1e6
+        del hp, dp, hq, dq
     except Exception:
         pcie = None
 

@@ -51,9 +51,10 @@ extern "C" int ffgpu_abi_version(void) { return FFGPU_ABI_VERSION; }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-/* FFGPU_TRACE=1: per launch group, when it was enqueued (host clock) and when its kernels
- * started / finished on the device, relative to the handle's first group */
-#include <time.h>
+/* FFGPU_TRACE=1: device timeline of the launch groups.  Every mark is a CUDA event recorded
+ * on the group's stream; the list is printed (times relative to the first mark of the
+ * process) when a handle is closed. */
+#include <pthread.h>
 static int trace_on(void)
 {
     static int v = -1;
@@ -61,41 +62,50 @@ static int trace_on(void)
         v = getenv("FFGPU_TRACE") != NULL;
     return v;
 }
-static double host_ms(void)
-{
-    struct timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    return ts.tv_sec * 1e3 + ts.tv_nsec / 1e6;
-}
-struct Trace {
-    cudaEvent_t base, k0, k1;
-    double host_base;
-    int have_base;
+struct TraceMark {
+    cudaEvent_t ev;
+    const char *what;
+    int group, n;
 };
-static void trace_begin(Trace *t, cudaEvent_t *k0, cudaStream_t st, const char *what, int n)
+static TraceMark g_marks[1 << 14];
+static int g_nmarks;
+static cudaEvent_t g_trace_base;
+static pthread_mutex_t g_trace_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static void trace_mark(cudaStream_t st, const char *what, int group, int n)
 {
     if (!trace_on())
         return;
-    if (!t->have_base) {
-        cudaEventCreate(&t->base);
-        cudaEventRecord(t->base, st);
-        t->host_base = host_ms();
-        t->have_base = 1;
+    pthread_mutex_lock(&g_trace_lock);
+    if (!g_trace_base) {
+        cudaEventCreate(&g_trace_base);
+        cudaEventRecord(g_trace_base, st);
     }
-    cudaEventCreate(k0);
-    cudaEventRecord(*k0, st);
-    fprintf(stderr, "[ffgpu] %s group of %d enqueued at host %+.2f ms\n", what, n, host_ms() - t->host_base);
+    if (g_nmarks < (int)(sizeof(g_marks) / sizeof(g_marks[0]))) {
+        TraceMark *m = &g_marks[g_nmarks++];
+        cudaEventCreate(&m->ev);
+        cudaEventRecord(m->ev, st);
+        m->what = what;
+        m->group = group;
+        m->n = n;
+    }
+    pthread_mutex_unlock(&g_trace_lock);
 }
-static void trace_end(Trace *t, cudaEvent_t k0, cudaEvent_t done, const char *what)
+static void trace_dump(void)
 {
-    float a = 0, b = 0;
-    if (!trace_on() || !t->have_base || !k0)
+    if (!trace_on())
         return;
-    cudaEventSynchronize(done);
-    cudaEventElapsedTime(&a, t->base, k0);
-    cudaEventElapsedTime(&b, t->base, done);
-    fprintf(stderr, "[ffgpu] %s group: device work %.2f .. %.2f ms (%.2f), seen by host at %+.2f ms\n", what, a, b,
-            b - a, host_ms() - t->host_base);
+    pthread_mutex_lock(&g_trace_lock);
+    for (int i = 0; i < g_nmarks; i++) {
+        float ms = 0;
+        cudaEventSynchronize(g_marks[i].ev);
+        cudaEventElapsedTime(&ms, g_trace_base, g_marks[i].ev);
+        fprintf(stderr, "[ffgpu] %10.2f ms  %-10s group %d (%d)\n", ms, g_marks[i].what, g_marks[i].group,
+                g_marks[i].n);
+        cudaEventDestroy(g_marks[i].ev);
+    }
+    g_nmarks = 0;
+    pthread_mutex_unlock(&g_trace_lock);
 }
 
 extern "C" size_t ffgpu_ffv1_frame_layout(const char *pix_fmt, int width, int height,
@@ -132,18 +142,58 @@ static void flatten_qt(const FFStream *s, int16_t *q)
     }
 }
 
+/* Copy a picture between caller memory and the device layout.  Planes whose caller linesize
+ * equals the device pitch go as ONE linear copy (a pitched copy is one DMA descriptor per
+ * row and measurably slower over PCIe), and neighbouring planes that are contiguous on both
+ * sides without padding are merged into the same copy. */
+static int copy_picture(const FFDevParams *P, const FFPixFmt *pf, int w, int h, uint8_t *const data[4],
+                        const int linesize[4], uint8_t *d_frame, int to_device, cudaStream_t st)
+{
+    const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    int k = 0;
+    while (k < pf->nplanes) {
+        int rb, rows;
+        ff_plane_geometry(pf, w, h, k, &rb, &rows);
+        if (!data[k] || linesize[k] < rb)
+            return fail(FFGPU_EINVAL, "picture plane %d missing or linesize too small", k);
+        uint8_t *dev = d_frame + P->plane_off[k];
+        if (linesize[k] == P->pitch[k] && rows > 0) {
+            size_t bytes = (size_t)(rows - 1) * P->pitch[k] + rb;
+            int last = k;
+            /* extend over following planes while both sides stay gap-free */
+            while (last + 1 < pf->nplanes && data[last + 1] && rb == P->pitch[last] &&
+                   linesize[last + 1] == P->pitch[last + 1] &&
+                   P->plane_off[last + 1] == P->plane_off[last] + (size_t)rows * P->pitch[last] &&
+                   data[last + 1] == data[last] + (size_t)rows * P->pitch[last]) {
+                last++;
+                ff_plane_geometry(pf, w, h, last, &rb, &rows);
+                if (rows <= 0)
+                    break;
+                bytes = (size_t)(P->plane_off[last] - P->plane_off[k]) + (size_t)(rows - 1) * P->pitch[last] + rb;
+            }
+            if (to_device)
+                CK(cudaMemcpyAsync(dev, data[k], bytes, kind, st));
+            else
+                CK(cudaMemcpyAsync(data[k], dev, bytes, kind, st));
+            k = last + 1;
+        } else {
+            if (to_device)
+                CK(cudaMemcpy2DAsync(dev, P->pitch[k], data[k], linesize[k], rb, rows, kind, st));
+            else
+                CK(cudaMemcpy2DAsync(data[k], linesize[k], dev, P->pitch[k], rb, rows, kind, st));
+            k++;
+        }
+    }
+    return 0;
+}
+
 static int upload_picture(const FFDevParams *P, const FFPixFmt *pf, int w, int h,
                           const ffgpu_picture *pic, uint8_t *d_frame, cudaStream_t st)
 {
-    for (int k = 0; k < pf->nplanes; k++) {
-        int rb, rows;
-        ff_plane_geometry(pf, w, h, k, &rb, &rows);
-        if (!pic->data[k] || pic->linesize[k] < rb)
-            return fail(FFGPU_EINVAL, "picture plane %d missing or linesize too small", k);
-        CK(cudaMemcpy2DAsync(d_frame + P->plane_off[k], P->pitch[k], pic->data[k], pic->linesize[k],
-                             rb, rows, cudaMemcpyHostToDevice, st));
-    }
-    return 0;
+    uint8_t *data[4];
+    for (int k = 0; k < 4; k++)
+        data[k] = (uint8_t *)pic->data[k];
+    return copy_picture(P, pf, w, h, data, pic->linesize, d_frame, 1, st);
 }
 
 /* ====================================================================== */
@@ -155,7 +205,6 @@ struct EncJob {
     cudaStream_t stream;
     cudaEvent_t done;
     int n, state, drained, fetched;
-    cudaEvent_t tk0;
     uint8_t *d_frames;
     uint32_t *d_tokens;
     uint8_t *d_state;
@@ -208,7 +257,6 @@ struct ffgpu_encoder {
     uint64_t launches;
     int profile;                        /* record events around every kernel of device batches */
     void *events[FFK_ENC_KERNELS + 1];
-    Trace trace;
 };
 
 static int enc_free_job(EncJob *j)
@@ -273,7 +321,7 @@ static int enc_device_init(ffgpu_encoder *e)
         EncJob *j = &e->jobs[i];
         const size_t B = (size_t)e->max_batch;
         CK(cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&j->done, trace_on() ? cudaEventDefault : cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&j->done, cudaEventDisableTiming));
         CK(cudaMalloc(&j->d_frames, B * P->frame_bytes));
         CK(cudaMalloc(&j->d_tokens, B * P->frame_tokens * sizeof(uint32_t)));
         if (e->intra)
@@ -482,14 +530,28 @@ static int enc_launch(ffgpu_encoder *e, EncJob *j)
     CK(cudaMemcpyAsync(j->d_frame_set, j->h_frame_set, j->n, cudaMemcpyHostToDevice, j->stream));
     CK(cudaMemcpyAsync(j->d_frame_key, j->h_frame_key, j->n, cudaMemcpyHostToDevice, j->stream));
     CK(cudaMemsetAsync(j->d_overflow, 0, sizeof(uint32_t), j->stream));
-    trace_begin(&e->trace, &j->tk0, j->stream, "encode", j->n);
+    trace_mark(j->stream, "enc k0", (int)(j - e->jobs), j->n);
     r = ffk_encode_group(&e->P, &E, j->n, j->stream);
     if (r < 0)
         return fail(r, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     e->launches += r;
-    CK(cudaMemcpyAsync(j->h_pkt_size, j->d_pkt_size, sizeof(uint32_t) * j->n, cudaMemcpyDeviceToHost, j->stream));
-    CK(cudaMemcpyAsync(j->h_pkt_off, j->d_pkt_off, sizeof(uint32_t) * (j->n + 1), cudaMemcpyDeviceToHost, j->stream));
-    CK(cudaMemcpyAsync(j->h_overflow, j->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, j->stream));
+    trace_mark(j->stream, "enc k1", (int)(j - e->jobs), j->n);
+    {
+        /* packets and their size tables go to pinned host memory through the SMs: as
+         * copy-engine transfers they would queue behind the decoder's picture downloads */
+        FFCopyArgs c;
+        memset(&c, 0, sizeof(c));
+        c.seg[0].dst = j->h_pkt;       c.seg[0].src = j->d_pkt;
+        c.dyn_bytes = j->d_pkt_off + j->n;
+        c.dyn_cap = j->h_pkt_cap;
+        c.seg[1].dst = j->h_pkt_size;  c.seg[1].src = j->d_pkt_size;  c.seg[1].bytes = sizeof(uint32_t) * j->n;
+        c.seg[2].dst = j->h_pkt_off;   c.seg[2].src = j->d_pkt_off;   c.seg[2].bytes = sizeof(uint32_t) * (j->n + 1);
+        c.seg[3].dst = j->h_overflow;  c.seg[3].src = j->d_overflow;  c.seg[3].bytes = sizeof(uint32_t);
+        c.nseg = 4;
+        if ((r = ffk_copy_segments(&c, j->stream)) < 0)
+            return fail(r, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        e->launches += r;
+    }
     CK(cudaEventRecord(j->done, j->stream));
     j->state = JOB_RUNNING;
     j->fetched = 0;
@@ -505,18 +567,19 @@ static int enc_fetch(ffgpu_encoder *e, EncJob *j)
     if (j->fetched)
         return 0;
     CK(cudaEventSynchronize(j->done));
-    trace_end(&e->trace, j->tk0, j->done, "encode");
     if (*j->h_overflow)
         return fail(FFGPU_INVALIDDATA, "encoded frame too large");   /* ffv1enc_template.c:34-44 */
     total = j->h_pkt_off[j->n];
     if (total > j->h_pkt_cap) {
+        /* the pinned packet buffer was too small for the SM copy: grow it, copy the plain way */
         cudaFreeHost(j->h_pkt);
         j->h_pkt = NULL;
         j->h_pkt_cap = align_up(total + total / 2, 4096);
         CK(cudaHostAlloc(&j->h_pkt, j->h_pkt_cap, cudaHostAllocDefault));
+        CK(cudaMemcpyAsync(j->h_pkt, j->d_pkt, total, cudaMemcpyDeviceToHost, j->stream));
+        CK(cudaStreamSynchronize(j->stream));
     }
-    CK(cudaMemcpyAsync(j->h_pkt, j->d_pkt, total, cudaMemcpyDeviceToHost, j->stream));
-    CK(cudaStreamSynchronize(j->stream));
+    trace_mark(j->stream, "enc pkts", (int)(j - e->jobs), j->n);
     j->fetched = 1;
     j->state = JOB_DRAINING;
     return 0;
@@ -555,6 +618,8 @@ extern "C" int ffgpu_ffv1_encode_send_frame(ffgpu_encoder *e, const ffgpu_pictur
     set = enc_prefix_set(e, key, ps, pic->sar_num, pic->sar_den);
     if (set < 0)
         return set;
+    if (j->n == 0)
+        trace_mark(j->stream, "enc h2d", (int)(j - e->jobs), 0);
     if ((r = upload_picture(&e->P, e->s.pf, e->s.width, e->s.height, pic,
                             j->d_frames + (size_t)j->n * e->P.frame_bytes, j->stream)) < 0)
         return r;
@@ -780,6 +845,7 @@ extern "C" int ffgpu_ffv1_encode_close(ffgpu_encoder *e)
     if (e->dev_ready) {
         cudaSetDevice(e->opt.device);
         cudaDeviceSynchronize();
+        trace_dump();
         for (int i = 0; i <= FFK_ENC_KERNELS; i++)
             if (e->events[i])
                 cudaEventDestroy((cudaEvent_t)e->events[i]);
@@ -811,8 +877,7 @@ struct DecFrameMeta {
 struct DecJob {
     cudaStream_t stream;
     cudaEvent_t done;
-    cudaEvent_t tk0;
-    int n, state, drained, fetched, traced;
+    int n, state, drained, fetched;
     uint8_t *h_pkt, *d_pkt;
     size_t pkt_cap, pkt_used;
     FFDecSlice *h_work, *d_work;
@@ -850,7 +915,6 @@ struct ffgpu_decoder {
     uint64_t launches;
     int profile, profile_next;
     void *events[FFK_DEC_KERNELS + 1];
-    Trace trace;
 };
 
 static void dec_free_job(DecJob *j)
@@ -1001,7 +1065,7 @@ static int dec_device_init(ffgpu_decoder *d)
         DecJob *j = &d->jobs[i];
         const size_t B = (size_t)d->max_batch;
         CK(cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&j->done, trace_on() ? cudaEventDefault : cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&j->done, cudaEventDisableTiming));
         j->pkt_cap = align_up(B * (P->frame_bytes / 2 + 65536) + 256, 4096);
         CK(cudaHostAlloc(&j->h_pkt, j->pkt_cap, cudaHostAllocDefault));
         CK(cudaMalloc(&j->d_pkt, j->pkt_cap));
@@ -1138,16 +1202,10 @@ static void dec_fill_dev(const ffgpu_decoder *d, const DecJob *j, uint8_t *frame
 static int download_picture(const ffgpu_decoder *d, const uint8_t *d_frame, const ffgpu_picture_out *dst,
                             cudaStream_t st)
 {
-    const FFPixFmt *pf = d->s.pf;
-    for (int k = 0; k < pf->nplanes; k++) {
-        int rb, rows;
-        ff_plane_geometry(pf, d->s.width, d->s.height, k, &rb, &rows);
-        if (!dst->data[k] || dst->linesize[k] < rb)
-            return fail(FFGPU_EINVAL, "output plane %d missing or linesize too small", k);
-        CK(cudaMemcpy2DAsync(dst->data[k], dst->linesize[k], d_frame + d->P.plane_off[k], d->P.pitch[k],
-                             rb, rows, cudaMemcpyDeviceToHost, st));
-    }
-    return 0;
+    uint8_t *data[4];
+    for (int k = 0; k < 4; k++)
+        data[k] = (uint8_t *)dst->data[k];
+    return copy_picture(&d->P, d->s.pf, d->s.width, d->s.height, data, dst->linesize, (uint8_t *)d_frame, 0, st);
 }
 
 static int dec_launch(ffgpu_decoder *d, DecJob *j, uint8_t *frames, cudaStream_t st, int download)
@@ -1157,14 +1215,25 @@ static int dec_launch(ffgpu_decoder *d, DecJob *j, uint8_t *frames, cudaStream_t
     dec_fill_dev(d, j, frames, &D);
     if (d->profile_next)
         D.events = d->events;
-    CK(cudaMemcpyAsync(j->d_pkt, j->h_pkt, align_up(j->pkt_used + 64, 16), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(j->d_work, j->h_work, (size_t)j->n * d->max_slices * sizeof(FFDecSlice),
-                       cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(j->d_nslices, j->h_nslices, j->n * sizeof(int), cudaMemcpyHostToDevice, st));
+    {
+        /* packets and work items are read from pinned host memory by the SMs: as copy-engine
+         * transfers they would queue behind the encoder's picture uploads */
+        FFCopyArgs c;
+        memset(&c, 0, sizeof(c));
+        c.seg[0].dst = j->d_pkt;      c.seg[0].src = j->h_pkt;      c.seg[0].bytes = align_up(j->pkt_used + 64, 16);
+        c.seg[1].dst = j->d_work;     c.seg[1].src = j->h_work;
+        c.seg[1].bytes = (size_t)j->n * d->max_slices * sizeof(FFDecSlice);
+        c.seg[2].dst = j->d_nslices;  c.seg[2].src = j->h_nslices;  c.seg[2].bytes = j->n * sizeof(int);
+        c.nseg = 3;
+        if ((r = ffk_copy_segments(&c, st)) < 0)
+            return fail(r, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        d->launches += r;
+    }
     r = ffk_decode_group(&d->P, &D, j->n, st);
     if (r < 0)
         return fail(r, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     d->launches += r;
+    trace_mark(st, "dec k1", (int)(j - d->jobs), j->n);
     CK(cudaMemcpyAsync(j->h_result, j->d_result, (size_t)j->n * d->max_slices * sizeof(FFDecResult),
                        cudaMemcpyDeviceToHost, st));
     if (download)
@@ -1287,11 +1356,11 @@ static int dec_finish_frame(ffgpu_decoder *d, DecJob *j, int i, ffgpu_picture_ou
 static int dec_launch_group(ffgpu_decoder *d, DecJob *j)
 {
     int r;
-    trace_begin(&d->trace, &j->tk0, j->stream, "decode", j->n);
-    j->traced = 0;
+    trace_mark(j->stream, "dec k0", (int)(j - d->jobs), j->n);
     r = dec_launch(d, j, j->d_frames, j->stream, 1);
     if (r < 0)
         return r;
+    trace_mark(j->stream, "dec done", (int)(j - d->jobs), j->n);
     CK(cudaEventRecord(j->done, j->stream));
     j->state = JOB_RUNNING;
     j->drained = 0;
@@ -1402,10 +1471,6 @@ extern "C" int ffgpu_ffv1_decode_receive_frame(ffgpu_decoder *d, ffgpu_picture_o
             return FFGPU_EAGAIN;
         CK(cudaEventSynchronize(j->done));
         j->state = JOB_DRAINING;
-    }
-    if (!j->traced) {
-        trace_end(&d->trace, j->tk0, j->done, "decode");
-        j->traced = 1;
     }
     i = j->drained;
     if (!j->meta[i].has_dst) {
@@ -1548,6 +1613,7 @@ extern "C" int ffgpu_ffv1_decode_close(ffgpu_decoder *d)
     if (d->dev_ready) {
         cudaSetDevice(d->opt.device);
         cudaDeviceSynchronize();
+        trace_dump();
         for (int i = 0; i < MAX_DEPTH; i++)
             dec_free_job(&d->jobs[i]);
         cudaFree(d->d_qt); cudaFree(d->d_tab); cudaFree(d->d_initial); cudaFree(d->d_state_shared);

@@ -557,3 +557,45 @@ extern "C" int ffk_conceal_rect(const FFDevParams *P, uint8_t *dst_frame, const 
     if (!launch_ok()) return FFGPU_EXTERNAL;
     return 1;
 }
+
+/* ---------------- SM-driven copies between mapped host memory and HBM ---------------- */
+/* Bitstreams, work items and result tables are small next to the pictures, but as copy-engine
+ * transfers they queue behind the picture traffic of the other launch groups (≈90 ms per group
+ * of 4K pictures) and stall the kernels that wait for them.  Moved by the SMs through the
+ * mapped pinned buffers they bypass that queue.  All pointers are 16-byte aligned. */
+__global__ void __launch_bounds__(256)
+k_copy_segments(const FFCopyArgs a)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    for (int s = 0; s < a.nseg; s++) {
+        size_t bytes = a.seg[s].bytes;
+        if (s == 0 && a.dyn_bytes) {
+            bytes = *a.dyn_bytes;
+            if (bytes > a.dyn_cap)
+                bytes = 0;                       /* does not fit: the host falls back to a plain copy */
+        }
+        const uint4 *src = (const uint4 *)a.seg[s].src;
+        uint4 *dst = (uint4 *)a.seg[s].dst;
+        const size_t nvec = bytes >> 4;
+        for (size_t i = tid; i < nvec; i += nthreads)
+            dst[i] = src[i];
+        const size_t tail = bytes & 15;
+        if (tid < tail)
+            ((uint8_t *)a.seg[s].dst)[(nvec << 4) + tid] = ((const uint8_t *)a.seg[s].src)[(nvec << 4) + tid];
+    }
+}
+
+extern "C" int ffk_copy_segments(const FFCopyArgs *a, ffk_stream stream)
+{
+    size_t most = a->dyn_bytes ? a->dyn_cap : 0;
+    for (int s = 0; s < a->nseg; s++)
+        if (a->seg[s].bytes > most)
+            most = a->seg[s].bytes;
+    size_t blocks = (most / 16 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_copy_segments<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*a);
+    if (!launch_ok()) return FFGPU_EXTERNAL;
+    return 1;
+}

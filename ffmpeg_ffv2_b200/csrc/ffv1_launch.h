@@ -91,6 +91,23 @@ int ffk_decode_group(const FFDevParams *P, const FFDecDev *D, int nframes, ffk_s
 int ffk_conceal_rect(const FFDevParams *P, uint8_t *dst_frame, const uint8_t *src_frame,
                      int x, int y, int w, int h, int depth_gt8, ffk_stream stream);
 
+/* copies done by the SMs between mapped pinned host memory and device memory (both ways):
+ * up to 4 segments per launch, 16-byte aligned pointers.  If dyn_bytes is set, the size of
+ * segment 0 is read from device memory at run time (0 bytes are copied when it exceeds
+ * dyn_cap, and the caller falls back to a plain copy). */
+typedef struct FFCopySeg {
+    void *dst;
+    const void *src;
+    size_t bytes;
+} FFCopySeg;
+typedef struct FFCopyArgs {
+    FFCopySeg seg[4];
+    int nseg;
+    const uint32_t *dyn_bytes;
+    size_t dyn_cap;
+} FFCopyArgs;
+int ffk_copy_segments(const FFCopyArgs *a, ffk_stream stream);
+
 #ifdef __cplusplus
 }
 #endif
