@@ -193,8 +193,10 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="pictures per step and GPU (0 = default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-groups", type=int, default=1, help="launch groups a step's pictures are split into")
-    ap.add_argument("--e2e-depth", type=int, default=3, help="launch groups in flight (e2e leg)")
+    ap.add_argument("--e2e-groups", type=int, default=4, help="launch groups a step's pictures are split into")
+    ap.add_argument("--e2e-depth", type=int, default=6, help="launch groups in flight (e2e leg)")
+    ap.add_argument("--e2e-host", choices=("c", "python"), default="c",
+                    help="host loop of the e2e measurement: tools/e2e_driver.c or Python threads")
     ap.add_argument("--e2e-repeat", type=int, default=6,
                     help="the e2e leg streams the step's pictures this many times back to back, so "
                          "pipeline fill and drain are amortised like in a long transcode")
@@ -355,7 +357,42 @@ def main():
         enc = F.FFV1Encoder(w, h, fmt, device=local, max_batch=vb, pipeline_depth=args.e2e_depth, **opts)
         dec = F.FFV1Decoder(w, h, enc.extradata, device=local, max_batch=vb, pipeline_depth=args.e2e_depth)
 
+        # The host loop is C (tools/e2e_driver.c): an encoder thread and a decoder thread on the
+        # public C ABI, like the codec threads of a transcoder.  Packets go to the decoder as
+        # soon as the encoder returns them, so H2D of pictures, kernels of both directions and
+        # D2H of decoded pictures overlap.  --e2e-host python keeps the same loop in Python.
+        import ctypes as C
         import queue
+
+        class E2ERun(C.Structure):
+            _fields_ = [("enc", C.c_void_p), ("dec", C.c_void_p), ("nframes", C.c_int), ("nsrc", C.c_int),
+                        ("src", C.POINTER(F.codec.Picture)), ("ndst", C.c_int),
+                        ("dst", C.POINTER(F.codec.PictureOut)), ("timeout_s", C.c_double),
+                        ("pkt", C.POINTER(C.POINTER(C.c_uint8))), ("pkt_size", C.POINTER(C.c_size_t)),
+                        ("decoded", C.c_int), ("damaged", C.c_int), ("error", C.c_int),
+                        ("message", C.c_char * 256), ("produced", C.c_int), ("enc_finished", C.c_int),
+                        ("failed", C.c_int), ("t0", C.c_double)]
+
+        def e2e_step_c():
+            NE = B * args.e2e_repeat
+            run = E2ERun()
+            run.enc, run.dec = enc.h, dec.h
+            run.nframes, run.nsrc, run.ndst = NE, B, B
+            run.src, run.dst = c_src, c_dst
+            run.timeout_s = 120.0
+            pk = (C.POINTER(C.c_uint8) * NE)()
+            sz = (C.c_size_t * NE)()
+            run.pkt, run.pkt_size = pk, sz
+            r = e2e_lib.ffgpu_e2e_run(C.byref(run))
+            if r < 0:
+                raise SystemExit("e2e pipeline failed: %s" % run.message.decode(errors="replace"))
+
+            def collect():                       # untimed: packets of the first and last pass
+                out = [C.string_at(pk[i], sz[i]) for i in list(range(B)) + list(range(NE - B, NE))]
+                e2e_lib.ffgpu_e2e_free_packets(C.byref(run))
+                return out
+            return collect, run.decoded, NE
+
 
         def e2e_step():
             """encoder and decoder run concurrently on two host threads, like the codec threads
@@ -429,7 +466,7 @@ def main():
             td.join()
             if state["err"] is not None:
                 raise SystemExit("e2e pipeline failed: %r" % (state["err"],))
-            return out_pk, state["decoded"]
+            return out_pk[:B] + out_pk[-B:], state["decoded"], len(out_pk)
 
         dsts = []
         for i in range(B):
@@ -441,6 +478,21 @@ def main():
                 po.linesize[k] = pitch
                 arrs.append(a)
             dsts.append((po, arrs))
+        c_dst = (F.codec.PictureOut * B)(*[po for po, _a in dsts])
+        c_src = (F.codec.Picture * B)()
+        for i in range(B):
+            for k, a in enumerate(host_planes[i]):
+                c_src[i].data[k] = a.ctypes.data
+                c_src[i].linesize[k] = a.strides[0]
+            c_src[i].sar_num, c_src[i].sar_den = 0, 1
+        use_c = args.e2e_host == "c"
+        if use_c:
+            from ffmpeg_ffv2_b200 import build as _b
+            e2e_lib = C.CDLL(_b.build_e2e_driver())
+            e2e_lib.ffgpu_e2e_run.restype = C.c_int
+            e2e_lib.ffgpu_e2e_run.argtypes = [C.POINTER(E2ERun)]
+            e2e_lib.ffgpu_e2e_free_packets.restype = None
+            e2e_lib.ffgpu_e2e_free_packets.argtypes = [C.POINTER(E2ERun)]
         e2e_t = 0.0
         e2e_launch0 = 0
         for step in range(args.warmup + args.steps):
@@ -448,14 +500,16 @@ def main():
                 e2e_launch0 = enc.launches + dec.launches
             barrier()
             t0 = time.perf_counter()
-            out_pk, done = e2e_step()
+            ends_pk, done, npk = e2e_step_c() if use_c else e2e_step()
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             barrier()
             if step >= args.warmup:
                 e2e_t += max_over_ranks(dt)
-            assert done == B * args.e2e_repeat and len(out_pk) == done
-        if out_pk[:B] != pkts or out_pk[-B:] != pkts or not all(
+            if callable(ends_pk):
+                ends_pk = ends_pk()
+            assert done == B * args.e2e_repeat and npk == done
+        if ends_pk[:B] != pkts or ends_pk[-B:] != pkts or not all(
                 np.array_equal(ho[i], hf[i % distinct]) for i in range(B)):
             raise SystemExit("PARITY FAILURE: e2e path differs from the device path / the input")
         R = args.e2e_repeat
@@ -466,6 +520,7 @@ def main():
                "ms_per_step": 1e3 * e2e_t / K,
                "api": "ffgpu_ffv1_encode_send_frame/receive_packet + "
                       "ffgpu_ffv1_decode_send_packet/receive_frame, pinned host buffers",
+               "host_loop": "tools/e2e_driver.c (2 threads)" if use_c else "python (2 threads)",
                "frames_per_launch_group": vb, "launch_groups_in_flight": args.e2e_depth,
                "gpu_launches": int(enc.launches + dec.launches - e2e_launch0)}
 

@@ -44,5 +44,22 @@ def build(force=False, verbose=False):
     return OUT
 
 
+def build_e2e_driver(force=False):
+    """tools/libffgpu_e2e.so: the C host loop bench.py times for the end-to-end number
+    (two threads on the public C ABI, tools/e2e_driver.c)"""
+    root = os.path.join(HERE, "..")
+    src = os.path.join(root, "tools", "e2e_driver.c")
+    out = os.path.join(root, "tools", "libffgpu_e2e.so")
+    build(force=force)
+    if not force and not _newer(out, [src, os.path.join(root, "include", "ffgpu.h"), OUT]):
+        return out
+    subprocess.run(["gcc", "-std=gnu11", "-O2", "-fPIC", "-shared", "-Wall", "-Wextra",
+                    "-I", os.path.join(root, "include"), src, "-o", out,
+                    "-L", HERE, "-lffgpu", "-Wl,-rpath,$ORIGIN/../ffmpeg_ffv2_b200", "-lpthread"],
+                   check=True)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_e2e_driver(force="--force" in sys.argv))

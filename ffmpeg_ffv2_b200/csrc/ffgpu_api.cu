@@ -204,6 +204,7 @@ enum { JOB_FREE = 0, JOB_FILLING, JOB_RUNNING, JOB_DRAINING };
 struct EncJob {
     cudaStream_t stream;
     cudaEvent_t done;
+    cudaEvent_t uploaded;       /* the group's pictures have arrived (recorded on up_stream) */
     int n, state, drained, fetched;
     uint8_t *d_frames;
     uint32_t *d_tokens;
@@ -251,6 +252,10 @@ struct ffgpu_encoder {
     uint8_t *d_state_shared;    /* carried-state streams: one arena for all groups */
     PrefixSet sets[NPREFIX_SETS];
     EncJob jobs[MAX_DEPTH];
+    /* all picture uploads go through ONE stream: the H2D engine then serves the groups in
+     * order (with one stream per group it interleaves them, the oldest group finishes last
+     * and in-order packet delivery stalls behind it) */
+    cudaStream_t up_stream;
     int fill, head;             /* ring positions */
     int flushing, eof;
     int64_t picture_number;
@@ -272,6 +277,7 @@ static int enc_free_job(EncJob *j)
     cudaFreeHost(j->h_pkt_off); cudaFreeHost(j->h_overflow); cudaFreeHost(j->h_pkt);
     free(j->pts); free(j->key);
     if (j->done) cudaEventDestroy(j->done);
+    if (j->uploaded) cudaEventDestroy(j->uploaded);
     if (j->stream) cudaStreamDestroy(j->stream);
     memset(j, 0, sizeof(*j));
     return 0;
@@ -322,6 +328,9 @@ static int enc_device_init(ffgpu_encoder *e)
         const size_t B = (size_t)e->max_batch;
         CK(cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&j->done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&j->uploaded, cudaEventDisableTiming));
+        if (!e->up_stream)
+            CK(cudaStreamCreateWithFlags(&e->up_stream, cudaStreamNonBlocking));
         CK(cudaMalloc(&j->d_frames, B * P->frame_bytes));
         CK(cudaMalloc(&j->d_tokens, B * P->frame_tokens * sizeof(uint32_t)));
         if (e->intra)
@@ -527,6 +536,8 @@ static int enc_launch(ffgpu_encoder *e, EncJob *j)
     FFEncDev E;
     int r;
     enc_fill_dev(e, j, j->d_frames, &E);
+    CK(cudaEventRecord(j->uploaded, e->up_stream));
+    CK(cudaStreamWaitEvent(j->stream, j->uploaded, 0));
     CK(cudaMemcpyAsync(j->d_frame_set, j->h_frame_set, j->n, cudaMemcpyHostToDevice, j->stream));
     CK(cudaMemcpyAsync(j->d_frame_key, j->h_frame_key, j->n, cudaMemcpyHostToDevice, j->stream));
     CK(cudaMemsetAsync(j->d_overflow, 0, sizeof(uint32_t), j->stream));
@@ -619,9 +630,9 @@ extern "C" int ffgpu_ffv1_encode_send_frame(ffgpu_encoder *e, const ffgpu_pictur
     if (set < 0)
         return set;
     if (j->n == 0)
-        trace_mark(j->stream, "enc h2d", (int)(j - e->jobs), 0);
+        trace_mark(e->up_stream, "enc h2d", (int)(j - e->jobs), 0);
     if ((r = upload_picture(&e->P, e->s.pf, e->s.width, e->s.height, pic,
-                            j->d_frames + (size_t)j->n * e->P.frame_bytes, j->stream)) < 0)
+                            j->d_frames + (size_t)j->n * e->P.frame_bytes, e->up_stream)) < 0)
         return r;
     j->h_frame_set[j->n] = (uint8_t)set;
     j->h_frame_key[j->n] = (uint8_t)key;
@@ -740,6 +751,8 @@ extern "C" int ffgpu_ffv1_encode_device(ffgpu_encoder *e, const void *d_frames, 
     if (j->state != JOB_FREE)
         return fail(FFGPU_EINVAL, "encode_device while send/receive pictures are pending");
     st = cuda_stream ? (cudaStream_t)cuda_stream : j->stream;
+    /* the previous device batch reads the pinned per-frame tables asynchronously */
+    CK(cudaEventSynchronize(j->done));
     for (int i = 0; i < nframes; i++) {
         const int key = e->opt.gop_size == 0 || (e->picture_number + i) % e->opt.gop_size == 0;
         set = enc_prefix_set(e, key, 3, 0, 1);
@@ -761,6 +774,7 @@ extern "C" int ffgpu_ffv1_encode_device(ffgpu_encoder *e, const void *d_frames, 
     if (r < 0)
         return fail(r, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     e->launches += r;
+    CK(cudaEventRecord(j->done, st));
     return 0;
 }
 
@@ -851,6 +865,7 @@ extern "C" int ffgpu_ffv1_encode_close(ffgpu_encoder *e)
                 cudaEventDestroy((cudaEvent_t)e->events[i]);
         for (int i = 0; i < MAX_DEPTH; i++)
             enc_free_job(&e->jobs[i]);
+        if (e->up_stream) cudaStreamDestroy(e->up_stream);
         cudaFree(e->d_slices); cudaFree(e->d_qt); cudaFree(e->d_tab); cudaFree(e->d_prefix);
         cudaFree(e->d_prefix_bytes); cudaFree(e->d_state_shared); cudaFree(e->d_iota);
     }
@@ -877,6 +892,7 @@ struct DecFrameMeta {
 struct DecJob {
     cudaStream_t stream;
     cudaEvent_t done;
+    cudaEvent_t decoded;        /* kernels finished: the download stream may start */
     int n, state, drained, fetched;
     uint8_t *h_pkt, *d_pkt;
     size_t pkt_cap, pkt_used;
@@ -911,6 +927,7 @@ struct ffgpu_decoder {
     uint32_t *d_iota;
     int have_prev;
     DecJob jobs[MAX_DEPTH];
+    cudaStream_t down_stream;   /* all picture downloads, in group order (see up_stream) */
     int fill, head, flushing;
     uint64_t launches;
     int profile, profile_next;
@@ -925,6 +942,7 @@ static void dec_free_job(DecJob *j)
     cudaFree(j->d_weight); cudaFree(j->d_weight_sorted); cudaFree(j->d_order); cudaFree(j->d_sort_tmp);
     free(j->meta);
     if (j->done) cudaEventDestroy(j->done);
+    if (j->decoded) cudaEventDestroy(j->decoded);
     if (j->stream) cudaStreamDestroy(j->stream);
     memset(j, 0, sizeof(*j));
 }
@@ -1066,6 +1084,9 @@ static int dec_device_init(ffgpu_decoder *d)
         const size_t B = (size_t)d->max_batch;
         CK(cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&j->done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&j->decoded, cudaEventDisableTiming));
+        if (!d->down_stream)
+            CK(cudaStreamCreateWithFlags(&d->down_stream, cudaStreamNonBlocking));
         j->pkt_cap = align_up(B * (P->frame_bytes / 2 + 65536) + 256, 4096);
         CK(cudaHostAlloc(&j->h_pkt, j->pkt_cap, cudaHostAllocDefault));
         CK(cudaMalloc(&j->d_pkt, j->pkt_cap));
@@ -1234,13 +1255,25 @@ static int dec_launch(ffgpu_decoder *d, DecJob *j, uint8_t *frames, cudaStream_t
         return fail(r, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     d->launches += r;
     trace_mark(st, "dec k1", (int)(j - d->jobs), j->n);
-    CK(cudaMemcpyAsync(j->h_result, j->d_result, (size_t)j->n * d->max_slices * sizeof(FFDecResult),
-                       cudaMemcpyDeviceToHost, st));
-    if (download)
+    {
+        FFCopyArgs c;                              /* per-slice results, also by the SMs */
+        memset(&c, 0, sizeof(c));
+        c.seg[0].dst = j->h_result;   c.seg[0].src = j->d_result;
+        c.seg[0].bytes = (size_t)j->n * d->max_slices * sizeof(FFDecResult);
+        c.nseg = 1;
+        if ((r = ffk_copy_segments(&c, st)) < 0)
+            return fail(r, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        d->launches += r;
+    }
+    if (download) {
+        CK(cudaEventRecord(j->decoded, st));
+        CK(cudaStreamWaitEvent(d->down_stream, j->decoded, 0));
         for (int i = 0; i < j->n; i++)
             if (j->meta[i].has_dst &&
-                (r = download_picture(d, j->d_frames + (size_t)i * d->P.frame_bytes, &j->meta[i].dst, st)) < 0)
+                (r = download_picture(d, j->d_frames + (size_t)i * d->P.frame_bytes, &j->meta[i].dst,
+                                      d->down_stream)) < 0)
                 return r;
+    }
     return 0;
 }
 
@@ -1360,8 +1393,8 @@ static int dec_launch_group(ffgpu_decoder *d, DecJob *j)
     r = dec_launch(d, j, j->d_frames, j->stream, 1);
     if (r < 0)
         return r;
-    trace_mark(j->stream, "dec done", (int)(j - d->jobs), j->n);
-    CK(cudaEventRecord(j->done, j->stream));
+    trace_mark(d->down_stream, "dec done", (int)(j - d->jobs), j->n);
+    CK(cudaEventRecord(j->done, d->down_stream));
     j->state = JOB_RUNNING;
     j->drained = 0;
     return 0;
@@ -1560,6 +1593,8 @@ extern "C" int ffgpu_ffv1_decode_device(ffgpu_decoder *d, const uint8_t *const *
     if (nframes > d->max_batch)
         return fail(FFGPU_EINVAL, "nframes %d exceeds max_batch %d", nframes, d->max_batch);
     j = &d->jobs[0];
+    /* the previous device batch reads the pinned staging buffers asynchronously */
+    CK(cudaEventSynchronize(j->done));
     j->n = 0;
     j->pkt_used = 0;
     for (int i = 0; i < nframes; i++) {
@@ -1574,6 +1609,8 @@ extern "C" int ffgpu_ffv1_decode_device(ffgpu_decoder *d, const uint8_t *const *
     st = cuda_stream ? (cudaStream_t)cuda_stream : j->stream;
     d->profile_next = d->profile;
     r = dec_launch(d, j, (uint8_t *)d_frames, st, 0);
+    if (r >= 0)
+        CK(cudaEventRecord(j->done, st));
     d->profile_next = 0;
     j->n = 0;
     j->state = JOB_FREE;
@@ -1616,6 +1653,7 @@ extern "C" int ffgpu_ffv1_decode_close(ffgpu_decoder *d)
         trace_dump();
         for (int i = 0; i < MAX_DEPTH; i++)
             dec_free_job(&d->jobs[i]);
+        if (d->down_stream) cudaStreamDestroy(d->down_stream);
         cudaFree(d->d_qt); cudaFree(d->d_tab); cudaFree(d->d_initial); cudaFree(d->d_state_shared);
         cudaFree(d->d_prev); cudaFree(d->d_iota);
         if (d->prev_ready) cudaEventDestroy(d->prev_ready);

@@ -106,3 +106,13 @@ def test_pixel_path_fails_loudly_without_a_gpu():
     with pytest.raises(f.FFGpuError) as ei:
         enc.encode(planes)
     assert ei.value.code == f.EXTERNAL
+
+
+def test_e2e_driver_builds_and_links_against_the_abi():
+    """tools/e2e_driver.c (bench.py's host loop) uses only include/ffgpu.h entry points"""
+    import ctypes
+    from ffmpeg_ffv2_b200 import build as b
+    lib = ctypes.CDLL(b.build_e2e_driver())
+    assert hasattr(lib, "ffgpu_e2e_run") and hasattr(lib, "ffgpu_e2e_free_packets")
+    src = open(os.path.join(os.path.dirname(__file__), "..", "tools", "e2e_driver.c")).read()
+    assert "oracle" not in src and "ffv1_" not in src.replace("ffgpu_ffv1_", "")
