@@ -522,6 +522,10 @@ static void enc_fill_dev(const ffgpu_encoder *e, const EncJob *j, const uint8_t 
     E->overflow = j->d_overflow;
     E->pkt = j->d_pkt;
     E->state_per_frame = e->intra;
+    {
+        const int q = e->P.set_qidx[0];
+        E->five = e->s.qt[q][3][127] || e->s.qt[q][4][127];
+    }
     E->weight = j->d_weight;
     E->weight_sorted = j->d_weight_sorted;
     E->iota = e->d_iota;

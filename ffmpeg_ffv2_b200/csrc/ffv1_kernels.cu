@@ -66,17 +66,26 @@ k_symbolize(const FFDevParams P, const FFDevSlice *__restrict__ slices,
         atomicAdd(&weight[(size_t)blockIdx.y * P.nslices + blockIdx.x], wsum);
 }
 
-/* Stage A for the planar YCbCr / gray (+alpha) layouts: one CTA per slice, one warp per
- * sample row, 32 consecutive samples per step.  Every lane loads its own sample and the one
- * above it (two coalesced row reads); the left / top-left / top-right neighbours come from
- * the adjacent lanes by warp shuffle, only the lanes at a 32-sample seam or at the slice
- * border issue an extra load.  The context quantiser lives in shared memory. */
-template <bool WIDE>
-__global__ void __launch_bounds__(SYM_THREADS, 3)
+/* Stage A for the planar YCbCr / gray (+alpha) layouts.
+ *
+ * Work unit = SYM_ROWS consecutive rows x TW consecutive samples of one plane of a slice,
+ * taken by one warp; the units of a slice (all planes) form one flat list that the warps of
+ * its CTA(s) stride over, so luma and chroma keep every warp busy.  A lane owns one sample
+ * COLUMN of the unit: it loads rows y0-2 .. y0+SYM_ROWS-1 of that column (coalesced along
+ * x, all loads of a unit in flight together) and keeps them in registers, so T and TT are
+ * the lane's own values and L / LT / RT / LL come from the neighbouring lanes by shuffle.
+ * The outermost lanes of the warp are halo columns (HL on the left, one on the right): they
+ * only feed the shuffles, which removes every seam special case; what is left of the border
+ * rules of ffv1enc.c:287-288 are three selects (x == 0, x == 1, x == w-1).  The context
+ * quantiser lives in shared memory. */
+template <bool WIDE, bool FIVE>
+__global__ void __launch_bounds__(SYM_THREADS, 4)
 k_symbolize_planar(const FFDevParams P, const FFDevSlice *__restrict__ slices,
                    const uint8_t *__restrict__ frames, const int16_t *__restrict__ qt,
                    uint32_t *__restrict__ tokens, uint32_t *__restrict__ weight)
 {
+    constexpr int HL = FIVE ? 2 : 1;
+    constexpr int TW = 32 - HL - 1;
     __shared__ int16_t sq[FF_QT_STRIDE];
     {
         const uint32_t *src = (const uint32_t *)(qt + (size_t)P.set_qidx[0] * FF_QT_STRIDE);
@@ -84,94 +93,97 @@ k_symbolize_planar(const FFDevParams P, const FFDevSlice *__restrict__ slices,
             ((uint32_t *)sq)[i] = src[i];
     }
     __syncthreads();
-    const FFDevSlice sl = slices[blockIdx.x];
+    const FFDevSlice *slp = &slices[blockIdx.x];
     const uint8_t *frame = frames + (size_t)blockIdx.y * P.frame_bytes;
-    uint32_t *tok = tokens + (size_t)blockIdx.y * P.frame_tokens + sl.tok_off;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nrows_step = (SYM_THREADS / 32) * gridDim.z;
-    const int five = sq[FF_MAX_CTX_INPUTS * 256];
+    uint32_t *tok = tokens + (size_t)blockIdx.y * P.frame_tokens + slp->tok_off;
+    const int lane = threadIdx.x & 31;
+    const int wid = blockIdx.z * (SYM_THREADS / 32) + (threadIdx.x >> 5);
+    const int nwarps = (SYM_THREADS / 32) * gridDim.z;
     const int shift = P.packed_lsb ? 0 : 16 - P.sbits;
     const int cbits = P.cbits;
-    uint32_t wsum = 0, base = 0;
+    const int sx = slp->x, sy = slp->y;
+    uint32_t wsum = 0;
 
-    /* sample xx of the row starting at rowp: u8 with a byte step, or u16 (LSB- or MSB-aligned);
-     * wrapped to int16 like the reference's sample buffer (ffv1enc.c:291-305) */
-#define SAMPLE(rowp, xx) (WIDE ? (int)(int16_t)(((const uint16_t *)(rowp))[xx] >> shift) \
-                               : (int)(rowp)[(xx) * step])
-    /* each warp takes groups of SYM_ROWS consecutive rows: the SYM_ROWS + 1 row loads of a
-     * step are independent and all in flight together (memory-level parallelism), and the
-     * row above a sample is the previous row of the same group */
-    for (int k = 0; k < P.ncoded; k++) {
+    /* flat unit list: plane k owns ucount[k] = tiles x row groups consecutive units */
+    int ucount[FF_MAX_PLANES], nunits = 0;
+#pragma unroll
+    for (int k = 0; k < FF_MAX_PLANES; k++) {
+        ucount[k] = 0;
+        if (k < P.ncoded)
+            ucount[k] = ((slp->seg_w[k] + TW - 1) / TW) * ((slp->seg_lines[k] + SYM_ROWS - 1) / SYM_ROWS);
+        nunits += ucount[k];
+    }
+
+    for (int u = wid; u < nunits; u += nwarps) {
+        int k = 0, r = u;
+#pragma unroll
+        for (int q = 0; q < FF_MAX_PLANES - 1; q++)
+            if (k == q && r >= ucount[q]) {
+                r -= ucount[q];
+                k = q + 1;
+            }
+        uint32_t base = 0;
+        for (int q = 0; q < k; q++)
+            base += (uint32_t)slp->seg_w[q] * slp->seg_lines[q];
+        const int w = slp->seg_w[k], h = slp->seg_lines[k];
+        const int ntiles = (w + TW - 1) / TW;
+        const int g = r / ntiles, tile = r - g * ntiles;
+        const int y0 = g * SYM_ROWS;
+        const int x = tile * TW - HL + lane;
         const int mem = P.cp[k].mem, step = P.cp[k].step;
-        const int w = sl.seg_w[k], h = sl.seg_lines[k];
         const int ctx_base = P.set_base[P.cp[k].set];
-        const size_t pitch = (size_t)P.pitch[mem];
-        const uint8_t *pbase = frame + P.plane_off[mem] + (size_t)(sl.y >> P.cp[k].vs) * pitch +
-                               (size_t)(sl.x >> P.cp[k].hs) * step + P.cp[k].off;
-        const int ngroups = (h + SYM_ROWS - 1) / SYM_ROWS;
-        for (int g = blockIdx.z * (SYM_THREADS / 32) + warp; g < ngroups; g += nrows_step) {
-            const int y0 = g * SYM_ROWS;
-            const uint8_t *rtop = pbase + (size_t)(y0 - 1) * pitch;    /* row y0-1 */
-            uint32_t *trow = tok + base + (uint32_t)y0 * w;
-            for (int x0 = 0; x0 < w; x0 += 32) {
-                const int x = x0 + lane;
-                const bool valid = x < w;
-                int v[SYM_ROWS + 1];                 /* rows y0-1 .. y0+SYM_ROWS-1 at column x */
+        const ptrdiff_t pitch = P.pitch[mem];
+        /* sample (x, y0-2) of the plane rectangle; only dereferenced where it exists */
+        const uint8_t *col = frame + P.plane_off[mem] + P.cp[k].off +
+                             ((ptrdiff_t)(sy >> P.cp[k].vs) + y0 - 2) * pitch +
+                             ((ptrdiff_t)(sx >> P.cp[k].hs) + x) * (WIDE ? 2 : step);
+        const bool in_x = x >= 0 && x < w;
+        int v[SYM_ROWS + 2];
 #pragma unroll
-                for (int j = 0; j <= SYM_ROWS; j++) {
-                    const int yy = y0 - 1 + j;
-                    v[j] = (valid && yy >= 0 && yy < h) ? SAMPLE(rtop + (size_t)j * pitch, x) : 0;
-                }
+        for (int j = 0; j < SYM_ROWS + 2; j++) {
+            const int yy = y0 - 2 + j;
+            int s = 0;
+            /* row y0-2 is only needed by TT (5-input contexts) and by LT at x == 0 */
+            if (in_x && yy >= 0 && yy < h && (FIVE || j > 0 || tile == 0)) {
+                if (WIDE)
+                    s = (int)(int16_t)(*(const uint16_t *)(col + j * pitch) >> shift);
+                else
+                    s = col[j * pitch];
+            }
+            v[j] = s;
+        }
+        const bool first = x == 0, last = x == w - 1;
+        const bool out = lane >= HL && lane < 31 && x < w;
+        uint32_t *trow = tok + base + (uint32_t)y0 * w + x;
 #pragma unroll
-                for (int j = 1; j <= SYM_ROWS; j++) {
-                    const int y = y0 + j - 1;
-                    if (y >= h)
-                        break;
-                    const uint8_t *r0 = rtop + (size_t)j * pitch;
-                    const uint8_t *r1 = r0 - pitch, *r2 = r1 - pitch;
-                    const int cur = v[j], T = v[j - 1];
-                    int L = __shfl_up_sync(0xffffffffu, cur, 1);
-                    int LT = __shfl_up_sync(0xffffffffu, T, 1);
-                    int RT = __shfl_down_sync(0xffffffffu, T, 1);
-                    int LL = five ? __shfl_up_sync(0xffffffffu, cur, 2) : 0;
-                    if (valid) {
-                        if (x == 0) {                /* left border: ffv1enc.c:287 */
-                            L = T;
-                            LT = y >= 2 ? SAMPLE(r2, 0) : 0;
-                        } else if (lane == 0) {      /* seam between two 32-sample steps */
-                            L = SAMPLE(r0, x - 1);
-                            LT = y >= 1 ? SAMPLE(r1, x - 1) : 0;
-                        }
-                        if (x + 1 >= w)              /* right border: ffv1enc.c:288 */
-                            RT = T;
-                        else if (lane == 31)
-                            RT = y >= 1 ? SAMPLE(r1, x + 1) : 0;
-                        int ctx = sq[(L - LT) & 0xFF] + sq[256 + ((LT - T) & 0xFF)] +
-                                  sq[512 + ((T - RT) & 0xFF)];
-                        if (five) {
-                            if (x < 2)
-                                LL = x == 1 ? (y >= 1 ? SAMPLE(r1, 0) : 0) : 0;
-                            else if (lane < 2)
-                                LL = SAMPLE(r0, x - 2);
-                            const int TT = y >= 2 ? SAMPLE(r2, x) : 0;
-                            ctx += sq[768 + ((LL - L) & 0xFF)] + sq[1024 + ((TT - T) & 0xFF)];
-                        }
-                        int diff = cur - ff_median3(L, L + T - LT, T);
-                        const int neg = ctx < 0;
-                        ctx = neg ? -ctx : ctx;
-                        diff = ff_fold(neg ? -diff : diff, cbits);
-                        const uint32_t t = ((uint32_t)diff << FF_TOKEN_CTX_BITS) | (uint32_t)(ctx_base + ctx);
-                        trow[(j - 1) * w + x] = t;
-                        wsum += ff_token_weight(t);
-                    }
-                }
+        for (int j = 0; j < SYM_ROWS; j++) {
+            if (y0 + j >= h)
+                break;
+            const int cur = v[j + 2], T = v[j + 1], TT = v[j];
+            int L = __shfl_up_sync(0xffffffffu, cur, 1);
+            int LT = __shfl_up_sync(0xffffffffu, T, 1);
+            int RT = __shfl_down_sync(0xffffffffu, T, 1);
+            int LL = FIVE ? __shfl_up_sync(0xffffffffu, cur, 2) : 0;
+            if (FIVE)                              /* x == 1: sample[-1] = T of column 0; x == 0: 0 */
+                LL = x >= 2 ? LL : (x == 1 ? LT : 0);
+            L = first ? T : L;                     /* left border: ffv1enc.c:287 */
+            LT = first ? TT : LT;
+            RT = last ? T : RT;                    /* right border: ffv1enc.c:288 */
+            int ctx = sq[(L - LT) & 0xFF] + sq[256 + ((LT - T) & 0xFF)] + sq[512 + ((T - RT) & 0xFF)];
+            if (FIVE)
+                ctx += sq[768 + ((LL - L) & 0xFF)] + sq[1024 + ((TT - T) & 0xFF)];
+            int diff = cur - ff_median3(L, L + T - LT, T);
+            const int neg = ctx < 0;
+            ctx = neg ? -ctx : ctx;
+            diff = ff_fold(neg ? -diff : diff, cbits);
+            const uint32_t t = ((uint32_t)diff << FF_TOKEN_CTX_BITS) | (uint32_t)(ctx_base + ctx);
+            if (out) {
+                trow[j * w] = t;
+                wsum += ff_token_weight(t);
             }
         }
-        base += (uint32_t)w * h;
     }
-#undef SAMPLE
-    /* per-warp reduction + one atomic per warp: no block-wide barrier at the end, so warps
-     * with fewer rows retire early */
+    /* per-warp reduction + one atomic per warp: no block-wide barrier at the end */
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
         wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
@@ -313,18 +325,28 @@ extern "C" int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nfr
         if (E->weight)
             cudaMemsetAsync(E->weight, 0, sizeof(uint32_t) * (size_t)nframes * P->nslices, st);
         if (P->colorspace == 0) {
-            /* rows of the largest plane per z-block: 8 warps take 8 rows per pass */
-            /* one pass: 8 warps x SYM_ROWS rows per z-block */
-            int zr = (P->height / P->nv + 8 * SYM_ROWS - 1) / (8 * SYM_ROWS);
+            /* about 14 units per warp: enough to amortise the CTA prologue, fine enough to
+             * balance the warps (a C2 slice has 108 units -> one CTA of 8 warps) */
+            const int five = E->five;
+            const int tw = five ? 29 : 30;
+            const int sw = (P->width + P->nh - 1) / P->nh + 1, sh = (P->height + P->nv - 1) / P->nv + 1;
+            long units = 0;
+            for (int k = 0; k < P->ncoded; k++) {
+                const int wk = ((sw - 1) >> P->cp[k].hs) + 1, hk = ((sh - 1) >> P->cp[k].vs) + 1;
+                units += (long)((wk + tw - 1) / tw) * ((hk + SYM_ROWS - 1) / SYM_ROWS);
+            }
+            int zr = (int)((units + 8 * 14 - 1) / (8 * 14));
             if (zr < 1) zr = 1;
-            if (zr > 64) zr = 64;
+            if (zr > 1024) zr = 1024;
             dim3 g2(P->nslices, nframes, zr);
-            if (P->sbits > 8)
-                k_symbolize_planar<true><<<g2, SYM_THREADS, 0, st>>>(*P, E->slices, E->frames, E->qt,
-                                                                     E->tokens, E->weight);
-            else
-                k_symbolize_planar<false><<<g2, SYM_THREADS, 0, st>>>(*P, E->slices, E->frames, E->qt,
-                                                                      E->tokens, E->weight);
+#define SYM_LAUNCH(W, F) k_symbolize_planar<W, F><<<g2, SYM_THREADS, 0, st>>>(*P, E->slices, E->frames, E->qt, \
+                                                                              E->tokens, E->weight)
+            if (P->sbits > 8) {
+                if (five) SYM_LAUNCH(true, true); else SYM_LAUNCH(true, false);
+            } else {
+                if (five) SYM_LAUNCH(false, true); else SYM_LAUNCH(false, false);
+            }
+#undef SYM_LAUNCH
         } else {
             k_symbolize<<<grid, SYM_THREADS, 0, st>>>(*P, E->slices, E->frames, E->qt, E->tokens, E->weight);
         }

@@ -34,6 +34,7 @@ typedef struct FFEncDev {
     uint32_t *overflow;             /* [1] sticky flag                                  */
     uint8_t *pkt;                   /* packed output of the whole group                 */
     int state_per_frame;            /* 1: state[frame][slice] (intra), 0: state[slice]   */
+    int five;                       /* the encoder's quant table uses 5 context inputs   */
     /* longest-first scheduling of stage B: per-slice decision counts from stage A, sorted */
     uint32_t *weight;               /* [nframes][nslices]                               */
     uint32_t *weight_sorted;        /* scratch                                          */
