@@ -32,6 +32,7 @@
 #define CODE_THREADS FF_CODE_THREADS
 #define SYM_THREADS  256
 #define SYM_ROWS     4      /* rows a warp symbolizes per step (stage A, planar) */
+#define SYM_CHUNK    16     /* rows of a work unit (a multiple of SYM_ROWS)      */
 
 static inline int launch_ok(void)
 {
@@ -68,16 +69,24 @@ k_symbolize(const FFDevParams P, const FFDevSlice *__restrict__ slices,
 
 /* Stage A for the planar YCbCr / gray (+alpha) layouts.
  *
- * Work unit = SYM_ROWS consecutive rows x TW consecutive samples of one plane of a slice,
- * taken by one warp; the units of a slice (all planes) form one flat list that the warps of
- * its CTA(s) stride over, so luma and chroma keep every warp busy.  A lane owns one sample
- * COLUMN of the unit: it loads rows y0-2 .. y0+SYM_ROWS-1 of that column (coalesced along
- * x, all loads of a unit in flight together) and keeps them in registers, so T and TT are
- * the lane's own values and L / LT / RT / LL come from the neighbouring lanes by shuffle.
- * The outermost lanes of the warp are halo columns (HL on the left, one on the right): they
- * only feed the shuffles, which removes every seam special case; what is left of the border
- * rules of ffv1enc.c:287-288 are three selects (x == 0, x == 1, x == w-1).  The context
- * quantiser lives in shared memory. */
+ * Work unit = a strip of SYM_CHUNK rows x TW samples of one plane of a slice, taken by one
+ * warp; the units of a slice (all planes) form one flat list that the warps of its CTA(s)
+ * pull from a shared counter, so luma and chroma keep every warp busy.  A lane owns one
+ * sample COLUMN of the strip and walks down it SYM_ROWS rows at a time: the row loads of a
+ * step are independent (all in flight together, coalesced along x), the two rows above are
+ * carried in registers, so T and TT are the lane's own values and L / LT / RT / LL come from
+ * the neighbouring lanes by shuffle.  The outermost lanes of the warp are halo columns (HL on
+ * the left, one on the right): they only feed the shuffles, which removes every seam special
+ * case; what is left of the border rules of ffv1enc.c:287-288 are three selects (x == 0,
+ * x == 1, x == w-1).  The context quantiser and the per-plane geometry live in shared memory. */
+struct SymPlane {
+    const uint8_t *origin;      /* sample (0,0) of the plane's slice rectangle */
+    int w, h, ntiles, ucount;
+    float inv_tiles;
+    uint32_t base;              /* first token of the plane inside the slice */
+    int ctx_base, pitch, step;
+};
+
 template <bool WIDE, bool FIVE>
 __global__ void __launch_bounds__(SYM_THREADS, 4)
 k_symbolize_planar(const FFDevParams P, const FFDevSlice *__restrict__ slices,
@@ -87,102 +96,122 @@ k_symbolize_planar(const FFDevParams P, const FFDevSlice *__restrict__ slices,
     constexpr int HL = FIVE ? 2 : 1;
     constexpr int TW = 32 - HL - 1;
     __shared__ int16_t sq[FF_QT_STRIDE];
+    __shared__ SymPlane sp[FF_MAX_PLANES];
+    __shared__ int s_next, s_nunits;
     {
         const uint32_t *src = (const uint32_t *)(qt + (size_t)P.set_qidx[0] * FF_QT_STRIDE);
         for (int i = threadIdx.x; i < FF_QT_STRIDE / 2; i += SYM_THREADS)
             ((uint32_t *)sq)[i] = src[i];
     }
+    if (threadIdx.x == 0) {
+        const FFDevSlice *slp = &slices[blockIdx.x];
+        const uint8_t *frame = frames + (size_t)blockIdx.y * P.frame_bytes;
+        uint32_t base = 0;
+        int n = 0;
+        for (int k = 0; k < FF_MAX_PLANES; k++) {
+            SymPlane q;
+            memset(&q, 0, sizeof(q));
+            if (k < P.ncoded) {
+                const int mem = P.cp[k].mem;
+                q.w = slp->seg_w[k];
+                q.h = slp->seg_lines[k];
+                q.ntiles = (q.w + TW - 1) / TW;
+                q.ucount = q.ntiles * ((q.h + SYM_CHUNK - 1) / SYM_CHUNK);
+                q.inv_tiles = 1.0f / (float)(q.ntiles > 0 ? q.ntiles : 1);
+                q.base = base;
+                q.ctx_base = P.set_base[P.cp[k].set];
+                q.pitch = P.pitch[mem];
+                q.step = WIDE ? 2 : P.cp[k].step;
+                q.origin = frame + P.plane_off[mem] + P.cp[k].off +
+                           (size_t)(slp->y >> P.cp[k].vs) * q.pitch + (size_t)(slp->x >> P.cp[k].hs) * q.step;
+                base += (uint32_t)q.w * q.h;
+                n += q.ucount;
+            }
+            sp[k] = q;
+        }
+        s_nunits = n;
+        s_next = 0;
+    }
     __syncthreads();
-    const FFDevSlice *slp = &slices[blockIdx.x];
-    const uint8_t *frame = frames + (size_t)blockIdx.y * P.frame_bytes;
-    uint32_t *tok = tokens + (size_t)blockIdx.y * P.frame_tokens + slp->tok_off;
+    uint32_t *tok = tokens + (size_t)blockIdx.y * P.frame_tokens + slices[blockIdx.x].tok_off;
     const int lane = threadIdx.x & 31;
-    const int wid = blockIdx.z * (SYM_THREADS / 32) + (threadIdx.x >> 5);
-    const int nwarps = (SYM_THREADS / 32) * gridDim.z;
     const int shift = P.packed_lsb ? 0 : 16 - P.sbits;
     const int cbits = P.cbits;
-    const int sx = slp->x, sy = slp->y;
+    const int nunits = s_nunits;
     uint32_t wsum = 0;
 
-    /* flat unit list: plane k owns ucount[k] = tiles x row groups consecutive units */
-    int ucount[FF_MAX_PLANES], nunits = 0;
-#pragma unroll
-    for (int k = 0; k < FF_MAX_PLANES; k++) {
-        ucount[k] = 0;
-        if (k < P.ncoded)
-            ucount[k] = ((slp->seg_w[k] + TW - 1) / TW) * ((slp->seg_lines[k] + SYM_ROWS - 1) / SYM_ROWS);
-        nunits += ucount[k];
-    }
-
-    for (int u = wid; u < nunits; u += nwarps) {
-        int k = 0, r = u;
+#define SYM_LOAD(ptr) (WIDE ? (int)(int16_t)(*(const uint16_t *)(ptr) >> shift) : (int)*(ptr))
+    for (;;) {
+        int u = 0;
+        if (lane == 0)
+            u = atomicAdd(&s_next, 1);
+        u = __shfl_sync(0xffffffffu, u, 0) * gridDim.z + blockIdx.z;
+        if (u >= nunits)
+            break;
+        int k = 0;
 #pragma unroll
         for (int q = 0; q < FF_MAX_PLANES - 1; q++)
-            if (k == q && r >= ucount[q]) {
-                r -= ucount[q];
+            if (k == q && u >= sp[q].ucount) {
+                u -= sp[q].ucount;
                 k = q + 1;
             }
-        uint32_t base = 0;
-        for (int q = 0; q < k; q++)
-            base += (uint32_t)slp->seg_w[q] * slp->seg_lines[q];
-        const int w = slp->seg_w[k], h = slp->seg_lines[k];
-        const int ntiles = (w + TW - 1) / TW;
-        const int g = r / ntiles, tile = r - g * ntiles;
-        const int y0 = g * SYM_ROWS;
+        const int w = sp[k].w, h = sp[k].h, ntiles = sp[k].ntiles;
+        const int chunk = (int)(((float)u + 0.5f) * sp[k].inv_tiles);
+        const int tile = u - chunk * ntiles;
+        const int y0 = chunk * SYM_CHUNK;
+        const int yend = min(y0 + SYM_CHUNK, h);
         const int x = tile * TW - HL + lane;
-        const int mem = P.cp[k].mem, step = P.cp[k].step;
-        const int ctx_base = P.set_base[P.cp[k].set];
-        const ptrdiff_t pitch = P.pitch[mem];
-        /* sample (x, y0-2) of the plane rectangle; only dereferenced where it exists */
-        const uint8_t *col = frame + P.plane_off[mem] + P.cp[k].off +
-                             ((ptrdiff_t)(sy >> P.cp[k].vs) + y0 - 2) * pitch +
-                             ((ptrdiff_t)(sx >> P.cp[k].hs) + x) * (WIDE ? 2 : step);
+        const int ctx_base = sp[k].ctx_base;
+        const ptrdiff_t pitch = sp[k].pitch;
         const bool in_x = x >= 0 && x < w;
+        /* column x, row y0-2; only dereferenced where the sample exists */
+        const uint8_t *p = sp[k].origin + (ptrdiff_t)(y0 - 2) * pitch + (ptrdiff_t)x * sp[k].step;
         int v[SYM_ROWS + 2];
-#pragma unroll
-        for (int j = 0; j < SYM_ROWS + 2; j++) {
-            const int yy = y0 - 2 + j;
-            int s = 0;
-            /* row y0-2 is only needed by TT (5-input contexts) and by LT at x == 0 */
-            if (in_x && yy >= 0 && yy < h && (FIVE || j > 0 || tile == 0)) {
-                if (WIDE)
-                    s = (int)(int16_t)(*(const uint16_t *)(col + j * pitch) >> shift);
-                else
-                    s = col[j * pitch];
-            }
-            v[j] = s;
-        }
+        /* row y0-2 is only needed by TT (5-input contexts) and by LT at x == 0 */
+        v[0] = (in_x && y0 >= 2 && (FIVE || tile == 0)) ? SYM_LOAD(p) : 0;
+        v[1] = (in_x && y0 >= 1) ? SYM_LOAD(p + pitch) : 0;
+        p += 2 * pitch;
         const bool first = x == 0, last = x == w - 1;
         const bool out = lane >= HL && lane < 31 && x < w;
-        uint32_t *trow = tok + base + (uint32_t)y0 * w + x;
+        uint32_t *trow = tok + sp[k].base + (uint32_t)y0 * w + x;
+        for (int y = y0; y < yend; y += SYM_ROWS) {
 #pragma unroll
-        for (int j = 0; j < SYM_ROWS; j++) {
-            if (y0 + j >= h)
-                break;
-            const int cur = v[j + 2], T = v[j + 1], TT = v[j];
-            int L = __shfl_up_sync(0xffffffffu, cur, 1);
-            int LT = __shfl_up_sync(0xffffffffu, T, 1);
-            int RT = __shfl_down_sync(0xffffffffu, T, 1);
-            int LL = FIVE ? __shfl_up_sync(0xffffffffu, cur, 2) : 0;
-            if (FIVE)                              /* x == 1: sample[-1] = T of column 0; x == 0: 0 */
-                LL = x >= 2 ? LL : (x == 1 ? LT : 0);
-            L = first ? T : L;                     /* left border: ffv1enc.c:287 */
-            LT = first ? TT : LT;
-            RT = last ? T : RT;                    /* right border: ffv1enc.c:288 */
-            int ctx = sq[(L - LT) & 0xFF] + sq[256 + ((LT - T) & 0xFF)] + sq[512 + ((T - RT) & 0xFF)];
-            if (FIVE)
-                ctx += sq[768 + ((LL - L) & 0xFF)] + sq[1024 + ((TT - T) & 0xFF)];
-            int diff = cur - ff_median3(L, L + T - LT, T);
-            const int neg = ctx < 0;
-            ctx = neg ? -ctx : ctx;
-            diff = ff_fold(neg ? -diff : diff, cbits);
-            const uint32_t t = ((uint32_t)diff << FF_TOKEN_CTX_BITS) | (uint32_t)(ctx_base + ctx);
-            if (out) {
-                trow[j * w] = t;
-                wsum += ff_token_weight(t);
+            for (int j = 0; j < SYM_ROWS; j++)
+                v[j + 2] = (in_x && y + j < yend) ? SYM_LOAD(p + j * pitch) : 0;
+#pragma unroll
+            for (int j = 0; j < SYM_ROWS; j++) {
+                if (y + j >= yend)
+                    break;
+                const int cur = v[j + 2], T = v[j + 1], TT = v[j];
+                int L = __shfl_up_sync(0xffffffffu, cur, 1);
+                int LT = __shfl_up_sync(0xffffffffu, T, 1);
+                int RT = __shfl_down_sync(0xffffffffu, T, 1);
+                int LL = FIVE ? __shfl_up_sync(0xffffffffu, cur, 2) : 0;
+                if (FIVE)                          /* x == 1: sample[-1] = T of column 0; x == 0: 0 */
+                    LL = x >= 2 ? LL : (x == 1 ? LT : 0);
+                L = first ? T : L;                 /* left border: ffv1enc.c:287 */
+                LT = first ? TT : LT;
+                RT = last ? T : RT;                /* right border: ffv1enc.c:288 */
+                int ctx = sq[(L - LT) & 0xFF] + sq[256 + ((LT - T) & 0xFF)] + sq[512 + ((T - RT) & 0xFF)];
+                if (FIVE)
+                    ctx += sq[768 + ((LL - L) & 0xFF)] + sq[1024 + ((TT - T) & 0xFF)];
+                int diff = cur - ff_median3(L, L + T - LT, T);
+                const int neg = ctx < 0;
+                ctx = neg ? -ctx : ctx;
+                diff = ff_fold(neg ? -diff : diff, cbits);
+                const uint32_t t = ((uint32_t)diff << FF_TOKEN_CTX_BITS) | (uint32_t)(ctx_base + ctx);
+                if (out) {
+                    trow[j * w] = t;
+                    wsum += ff_token_weight(t);
+                }
             }
+            v[0] = v[SYM_ROWS];
+            v[1] = v[SYM_ROWS + 1];
+            p += SYM_ROWS * pitch;
+            trow += SYM_ROWS * w;
         }
     }
+#undef SYM_LOAD
     /* per-warp reduction + one atomic per warp: no block-wide barrier at the end */
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
@@ -325,17 +354,18 @@ extern "C" int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nfr
         if (E->weight)
             cudaMemsetAsync(E->weight, 0, sizeof(uint32_t) * (size_t)nframes * P->nslices, st);
         if (P->colorspace == 0) {
-            /* about 14 units per warp: enough to amortise the CTA prologue, fine enough to
-             * balance the warps (a C2 slice has 108 units -> one CTA of 8 warps) */
+            /* about 4 units per warp: fine enough for the shared counter to balance the
+             * warps, coarse enough to amortise the CTA prologue (a C2 slice has 32 units ->
+             * one CTA of 8 warps) */
             const int five = E->five;
             const int tw = five ? 29 : 30;
             const int sw = (P->width + P->nh - 1) / P->nh + 1, sh = (P->height + P->nv - 1) / P->nv + 1;
             long units = 0;
             for (int k = 0; k < P->ncoded; k++) {
                 const int wk = ((sw - 1) >> P->cp[k].hs) + 1, hk = ((sh - 1) >> P->cp[k].vs) + 1;
-                units += (long)((wk + tw - 1) / tw) * ((hk + SYM_ROWS - 1) / SYM_ROWS);
+                units += (long)((wk + tw - 1) / tw) * ((hk + SYM_CHUNK - 1) / SYM_CHUNK);
             }
-            int zr = (int)((units + 8 * 14 - 1) / (8 * 14));
+            int zr = (int)((units + 8 * 4 - 1) / (8 * 4));
             if (zr < 1) zr = 1;
             if (zr > 1024) zr = 1024;
             dim3 g2(P->nslices, nframes, zr);
