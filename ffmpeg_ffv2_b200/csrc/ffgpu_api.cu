@@ -1209,7 +1209,6 @@ static void dec_fill_dev(const ffgpu_decoder *d, const DecJob *j, uint8_t *frame
     D->max_ctx = d->max_ctx;
     D->state_per_frame = d->intra;
     D->qt_count = d->s.qt_count;
-    D->gate_div = getenv("FFGPU_GATE_DIV") ? atoi(getenv("FFGPU_GATE_DIV")) : 1;
     D->gate_wait = getenv("FFGPU_GATE_WAIT") ? atoi(getenv("FFGPU_GATE_WAIT")) : FF_NEW_WAIT;
     D->hdr.micro_version = d->s.micro_version;
     D->hdr.qt_count = d->s.qt_count;

@@ -488,7 +488,7 @@ __global__ void k_dec_fill_state(uint4 *__restrict__ state, size_t vec_per_frame
         p[i] = pattern;
 }
 
-__global__ void __launch_bounds__(CODE_THREADS)
+__global__ void __launch_bounds__(CODE_THREADS, 1)
 k_decode(const FFDevParams P, const FFDecDev D, int nframes)
 {
     for (int i = threadIdx.x; i < (int)sizeof(FFRacTables) / 4; i += CODE_THREADS)
@@ -526,7 +526,6 @@ k_decode(const FFDevParams P, const FFDecDev D, int nframes)
             C.lines = D.lines + (size_t)gid * P.ncoded * 2 * D.line_stride;
             C.line_stride = D.line_stride;
             C.frame = D.frames + (size_t)f * P.frame_bytes;
-            C.gate_div = D.gate_div;
             C.gate_wait = D.gate_wait;
             ff_decode_slice(P, w, D.pkt, C, &r, 0);
         }

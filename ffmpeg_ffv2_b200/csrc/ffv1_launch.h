@@ -75,7 +75,7 @@ typedef struct FFDecDev {
     int state_per_frame;
     int qt_count;                   /* quant table sets of the stream                   */
     FFDecHdr hdr;                   /* constants for device-side slice header parsing   */
-    int gate_div, gate_wait;        /* sample set-up gating of the decode loop          */
+    int gate_wait;                  /* sample set-up gating of the decode loop          */
     uint32_t *weight;               /* [nframes*max_slices] slice byte counts            */
     uint32_t *weight_sorted;
     const uint32_t *iota;

@@ -327,6 +327,11 @@ __device__ __forceinline__ uint32_t ff_lds8(uint32_t sa)
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(sa));
     return v;
 }
+/* identity the assembler cannot see through (must be called by a converged warp) */
+__device__ __forceinline__ uint32_t ff_opaque(uint32_t v)
+{
+    return __shfl_sync(__activemask(), v, (int)(threadIdx.x & 31));
+}
 __device__ __forceinline__ void ff_sts8(uint32_t sa, uint32_t v)
 {
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(sa), "r"(v) : "memory");
@@ -357,9 +362,15 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
     (void)tab_; (void)row_;
 
 #if defined(__CUDA_ARCH__)
-    const uint32_t row_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_rows[threadIdx.x * FF_ROW_WORDS]);
-    const uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_tab);
-    const uint32_t stab_sa = (uint32_t)__cvta_generic_to_shared(ff_s_stab);
+    uint32_t row_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_rows[threadIdx.x * FF_ROW_WORDS]);
+    uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_tab);
+    uint32_t stab_sa = (uint32_t)__cvta_generic_to_shared(ff_s_stab);
+    /* a shuffle from the own lane is opaque to ptxas: otherwise it rematerialises the
+     * shared-window base (S2R CgaCtaId + shifts, a dozen instructions) in front of every
+     * decision instead of keeping three registers */
+    row_sa = ff_opaque(row_sa);
+    tab_sa = ff_opaque(tab_sa);
+    stab_sa = ff_opaque(stab_sa);
     uint32_t srow = stab_sa, slot = 0;
     const uint32_t nchunks = (n + 3) >> 2;
     for (uint32_t ch = 0; ch < FF_TOK_AHEAD; ch++) {
@@ -776,7 +787,7 @@ typedef struct FFDecCtx {
     int32_t *lines;             /* [ncoded][2][line_stride] scratch                   */
     int      line_stride;
     uint8_t *frame;             /* output picture                                     */
-    int gate_div, gate_wait;    /* sample set-up gating: 1/gate_div of the lanes, max wait */
+    int gate_wait;              /* sample set-up gating: longest idle wait, in iterations */
 } FFDecCtx;
 
 FFGPU_HD int ff_wrap_sample(const FFDevParams &P, int v)
@@ -1079,8 +1090,10 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
 #define FF_PREV(xx) (usepic ? (havep ? FF_PIC(prow, xx) : 0) : prev[xx])
 #define FF_PREV2(xx) (usepic ? (havepp ? FF_PIC(pprow, xx) : 0) : cur[xx])
 #if defined(__CUDA_ARCH__)
-    const uint32_t row_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_rows[threadIdx.x * FF_ROW_WORDS]);
-    const uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_tab);
+    uint32_t row_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_rows[threadIdx.x * FF_ROW_WORDS]);
+    uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_tab);
+    row_sa = ff_opaque(row_sa);                      /* see ff_encode_slice_range */
+    tab_sa = ff_opaque(tab_sa);
 #endif
     c.buf = pkt + d.pkt_off;
     c.low = d.low;
@@ -1103,18 +1116,22 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
         /* The sample set-up below is the expensive, divergent part of the loop.  The lanes
          * of a warp finish their symbols at different iterations, so running it whenever ANY
          * lane needs a new sample executes it almost every iteration for a handful of lanes.
-         * Instead a lane that needs a sample waits (idles) until a quarter of the active
-         * lanes need one, or until it has waited FF_NEW_WAIT iterations. */
+         * Instead a lane that needs a sample idles until every active lane needs one, or
+         * until the longest-waiting lane has idled D.gate_wait iterations (`waited` counts
+         * the iterations since the last set-up in which some lane was waiting; it is the
+         * same in every lane). */
         {
             const unsigned act = __activemask();
             const unsigned need = __ballot_sync(act, need_new);
-            const int go = __popc(need) * D.gate_div >= __popc(act) ||
-                           __any_sync(act, need_new && waited >= D.gate_wait);
-            if (need_new && !go) {
-                waited++;
-                continue;
+            if (need) {
+                if (need == act || waited >= D.gate_wait)
+                    waited = 0;
+                else {
+                    waited++;
+                    if (need_new)
+                        continue;
+                }
             }
-            waited = 0;
         }
 #endif
         if (need_new) {

@@ -237,7 +237,7 @@ extern "C" int ffv1emul_decode(void *h, const uint8_t *pkt_in, int size, uint8_t
         FFDecCtx D;
         D.qt_all = d->qt.data(); D.tab = &d->s.cur_tab; D.rstate = rs; D.vstate = vs;
         D.lines = d->lines.data(); D.line_stride = line_stride; D.frame = frame;
-        D.gate_div = 1; D.gate_wait = FF_NEW_WAIT;
+        D.gate_wait = FF_NEW_WAIT;
         alignas(16) uint32_t row[FF_ROW_WORDS];
         ff_decode_slice(P, work[i], pkt.data(), D, &res[i], row);
         if (P.ac != FF_AC_GOLOMB && P.version > 2) {
