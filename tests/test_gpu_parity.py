@@ -185,6 +185,57 @@ CONFIGS_FULL = [
 ]
 
 
+def test_incompressible_pictures_outgrow_the_staging_buffers():
+    """noise compresses to ~65 % of raw: the packets of a group exceed the encoder's pinned
+    packet buffer (sized for raw/4 per picture -> the SM copy is skipped and the plain copy
+    fallback runs) and the decoder's packet arena (raw/2 per picture -> a group is launched
+    early); both must still give the oracle's packets and the input pictures"""
+    F = gpu()
+    w, h, fmt = 1280, 720, "yuv420p10le"
+    kw = dict(slices=16, gop_size=1)
+    frames = [synth.noise(fmt, w, h, i) for i in range(7)]
+    ref = cc.Encoder("oracle", w, h, fmt, **kw)
+    want = [ref.encode(f) for f in frames]
+    raw = sum(a.nbytes for a in frames[0])
+    assert min(len(p) for p in want) > raw // 2 + 65536
+    enc = F.FFV1Encoder(w, h, fmt, max_batch=3, pipeline_depth=2, **kw)
+    got, i = [], 0
+    while True:
+        if i < len(frames):
+            if enc.send_frame(frames[i], pts=i):
+                i += 1
+                continue
+        elif i == len(frames):
+            enc.send_frame(None)
+            i += 1
+        r = enc.receive_packet()
+        if r == F.EOF:
+            break
+        if r is not None:
+            got.append(r)
+    assert [g[0] for g in got] == want
+    dec = F.FFV1Decoder(w, h, enc.extradata, max_batch=3, pipeline_depth=2)
+    out, i = [], 0
+    while True:
+        if i < len(want):
+            if dec.send_packet(want[i], pts=i, dst=dec.alloc_picture()):
+                i += 1
+                continue
+        elif i == len(want):
+            dec.send_packet(None)
+            i += 1
+        r = dec.receive_frame()
+        if r == F.EOF:
+            break
+        if r is not None:
+            out.append(r)
+    assert [po.pts for po, _ in out] == list(range(len(frames)))
+    for (po, arrs), src in zip(out, frames):
+        assert po.damaged_slices == 0
+        for a, b in zip(arrs, src):
+            assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("name,w,h,fmt,kw,nframes", CONFIGS_FULL)
 def test_full_size_roundtrip_and_oracle(name, w, h, fmt, kw, nframes):
     """at BASELINE sizes: packet md5 == oracle (the oracle finishes a 4K frame in seconds),
