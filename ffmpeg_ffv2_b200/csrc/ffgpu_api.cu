@@ -557,7 +557,8 @@ static int enc_launch(ffgpu_encoder *e, EncJob *j)
         FFCopyArgs c;
         memset(&c, 0, sizeof(c));
         c.seg[0].dst = j->h_pkt;       c.seg[0].src = j->d_pkt;
-        c.dyn_bytes = j->d_pkt_off + j->n;
+        c.dyn_bytes = j->d_pkt_off + j->n;       /* total of the group, in 16-byte units */
+        c.dyn_shift = 4;
         c.dyn_cap = j->h_pkt_cap;
         c.seg[1].dst = j->h_pkt_size;  c.seg[1].src = j->d_pkt_size;  c.seg[1].bytes = sizeof(uint32_t) * j->n;
         c.seg[2].dst = j->h_pkt_off;   c.seg[2].src = j->d_pkt_off;   c.seg[2].bytes = sizeof(uint32_t) * (j->n + 1);
@@ -584,7 +585,7 @@ static int enc_fetch(ffgpu_encoder *e, EncJob *j)
     CK(cudaEventSynchronize(j->done));
     if (*j->h_overflow)
         return fail(FFGPU_INVALIDDATA, "encoded frame too large");   /* ffv1enc_template.c:34-44 */
-    total = j->h_pkt_off[j->n];
+    total = (size_t)j->h_pkt_off[j->n] << 4;
     if (total > j->h_pkt_cap) {
         /* the pinned packet buffer was too small for the SM copy: grow it, copy the plain way */
         cudaFreeHost(j->h_pkt);
@@ -691,7 +692,7 @@ extern "C" int ffgpu_ffv1_encode_receive_packet(ffgpu_encoder *e, uint8_t *pkt, 
     i = j->drained;
     if (j->h_pkt_size[i] > cap)
         return fail(FFGPU_ENOSPC, "packet buffer too small: need %u bytes", j->h_pkt_size[i]);
-    memcpy(pkt, j->h_pkt + j->h_pkt_off[i], j->h_pkt_size[i]);
+    memcpy(pkt, j->h_pkt + ((size_t)j->h_pkt_off[i] << 4), j->h_pkt_size[i]);
     if (size) *size = j->h_pkt_size[i];
     if (key_frame) *key_frame = j->key[i];
     if (pts) *pts = j->pts[i];
@@ -807,7 +808,7 @@ extern "C" int ffgpu_ffv1_encode_device_result(ffgpu_encoder *e, int frame, cons
         return fail(FFGPU_EINVAL, "frame index out of range");
     if ((r = enc_device_sizes(e, j)) < 0)
         return r;
-    if (d_pkt) *d_pkt = j->d_pkt + j->h_pkt_off[frame];
+    if (d_pkt) *d_pkt = j->d_pkt + ((size_t)j->h_pkt_off[frame] << 4);
     if (pkt_size) *pkt_size = j->h_pkt_size[frame];
     return 0;
 }
@@ -1092,6 +1093,8 @@ static int dec_device_init(ffgpu_decoder *d)
         if (!d->down_stream)
             CK(cudaStreamCreateWithFlags(&d->down_stream, cudaStreamNonBlocking));
         j->pkt_cap = align_up(B * (P->frame_bytes / 2 + 65536) + 256, 4096);
+        if (j->pkt_cap > 0xFFFF0000u)              /* work items address the arena with 32 bits; */
+            j->pkt_cap = 0xFFFF0000u;              /* a full arena launches the group early      */
         CK(cudaHostAlloc(&j->h_pkt, j->pkt_cap, cudaHostAllocDefault));
         CK(cudaMalloc(&j->d_pkt, j->pkt_cap));
         CK(cudaHostAlloc(&j->h_work, B * d->max_slices * sizeof(FFDecSlice), cudaHostAllocDefault));

@@ -302,14 +302,16 @@ k_pack_slice_scan(const FFDevParams P, const FFEncDev E)
         E.pkt_size[f] = total;
 }
 
-/* over the pictures of the group: exclusive scan of packet sizes (16-byte aligned starts) */
+/* over the pictures of the group: exclusive scan of packet sizes.  Packets start 16-byte
+ * aligned and pkt_off counts 16-BYTE UNITS: a group of incompressible 4K pictures packs to
+ * more than 4 GiB */
 __global__ void __launch_bounds__(1024)
 k_pack_frame_scan(const FFEncDev E, int nframes)
 {
     typedef cub::BlockScan<uint32_t, 1024> Scan;
     __shared__ typename Scan::TempStorage tmp;
     const int f = threadIdx.x;
-    uint32_t v = f < nframes ? ((E.pkt_size[f] + 15u) & ~15u) : 0;
+    uint32_t v = f < nframes ? ((E.pkt_size[f] + 15u) >> 4) : 0;
     uint32_t off, total;
     Scan(tmp).ExclusiveSum(v, off, total);
     if (f < nframes)
@@ -331,7 +333,7 @@ k_pack_gather(const FFDevParams P, const FFEncDev E)
     const FFDevSlice sl = E.slices[s];
     ff_pack_slice(P, s, E.bs + (size_t)f * P.frame_bs + sl.bs_off,
                   E.slice_bytes[(size_t)f * P.nslices + s],
-                  E.pkt + E.pkt_off[f] + E.slice_off[(size_t)f * P.nslices + s], crc_tab);
+                  E.pkt + ((size_t)E.pkt_off[f] << 4) + E.slice_off[(size_t)f * P.nslices + s], crc_tab);
 }
 
 extern "C" int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nframes, ffk_stream stream)
@@ -622,7 +624,7 @@ k_copy_segments(const FFCopyArgs a)
     for (int s = 0; s < a.nseg; s++) {
         size_t bytes = a.seg[s].bytes;
         if (s == 0 && a.dyn_bytes) {
-            bytes = *a.dyn_bytes;
+            bytes = (size_t)*a.dyn_bytes << a.dyn_shift;
             if (bytes > a.dyn_cap)
                 bytes = 0;                       /* does not fit: the host falls back to a plain copy */
         }

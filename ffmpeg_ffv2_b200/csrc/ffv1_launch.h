@@ -30,7 +30,7 @@ typedef struct FFEncDev {
     uint32_t *slice_bytes;          /* [nframes][nslices]                               */
     uint32_t *slice_off;            /* [nframes][nslices] offset inside the frame packet */
     uint32_t *pkt_size;             /* [nframes]                                        */
-    uint32_t *pkt_off;              /* [nframes + 1] offset inside the packed output     */
+    uint32_t *pkt_off;              /* [nframes + 1] offset inside the packed output, in 16-byte units */
     uint32_t *overflow;             /* [1] sticky flag                                  */
     uint8_t *pkt;                   /* packed output of the whole group                 */
     int state_per_frame;            /* 1: state[frame][slice] (intra), 0: state[slice]   */
@@ -104,7 +104,8 @@ typedef struct FFCopySeg {
 typedef struct FFCopyArgs {
     FFCopySeg seg[4];
     int nseg;
-    const uint32_t *dyn_bytes;
+    const uint32_t *dyn_bytes;      /* size of segment 0 in units of 1 << dyn_shift bytes */
+    int dyn_shift;
     size_t dyn_cap;
 } FFCopyArgs;
 int ffk_copy_segments(const FFCopyArgs *a, ffk_stream stream);
