@@ -74,7 +74,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -84,14 +84,21 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def halt(self):
+        """stop sampling, keep the samples (a later start() adds to them)"""
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.t.join(timeout=2)
+            self.proc = None
+
     def stop(self):
-        if not self.proc:
+        if not self.proc and not self.lines:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
+        self.halt()
         sm, mx, reasons = [], [], set()
         for l in self.lines:
             f = [x.strip() for x in l.split(",")]
@@ -317,7 +324,7 @@ def main():
                 kern[k] = kern.get(k, 0.0) + v
     barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
+    sampler.halt()                     # resumed around the timed e2e steps below
     gpu_launches = enc.launches + dec.launches - launches0
     enc.profile(False)
     dec.profile(False)
@@ -498,6 +505,7 @@ def main():
         for step in range(args.warmup + args.steps):
             if step == args.warmup:
                 e2e_launch0 = enc.launches + dec.launches
+                sampler.start()
             barrier()
             t0 = time.perf_counter()
             ends_pk, done, npk = e2e_step_c() if use_c else e2e_step()
@@ -523,6 +531,8 @@ def main():
                "host_loop": "tools/e2e_driver.c (2 threads)" if use_c else "python (2 threads)",
                "frames_per_launch_group": vb, "launch_groups_in_flight": args.e2e_depth,
                "gpu_launches": int(enc.launches + dec.launches - e2e_launch0)}
+
+    clocks = sampler.stop()            # samples of both timed regions (device-resident + e2e)
 
     # ---- PCIe context: plain pinned copies of 1 GiB, both directions ----
     pcie = None
