@@ -4,11 +4,14 @@
  *
  * Execution model
  *   A handle owns `pipeline_depth` launch groups.  A group collects up to `max_batch`
- *   pictures (encoder) or packets (decoder), uploads them on its own CUDA stream,
- *   enqueues the kernel chain once for the whole group and downloads the results; the
- *   host thread meanwhile fills the next group, so H2D, kernels and D2H of different
- *   groups overlap.  Streams whose adaptive states carry from frame to frame
- *   (gop_size > 1) run one picture per group on a single stream, in order.
+ *   pictures (encoder) or packets (decoder) and enqueues its kernel chain once, on its
+ *   own CUDA stream; the host thread meanwhile fills the next group, so H2D, kernels and
+ *   D2H of different groups overlap.  Pictures cross PCIe on one upload stream (encoder)
+ *   and one download stream (decoder) per handle, ordered against the group streams by
+ *   events, so the copy engines serve the groups in order; packets, work items and
+ *   result tables are moved by the SMs through mapped pinned memory (k_copy_segments)
+ *   and do not queue behind the picture DMA.  Streams whose adaptive states carry from
+ *   frame to frame (gop_size > 1) run one picture per group, in order.
  *
  * There is no CPU pixel path anywhere in this file: without a CUDA device every
  * pixel-path entry point fails with FFGPU_EXTERNAL.

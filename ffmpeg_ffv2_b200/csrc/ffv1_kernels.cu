@@ -3,7 +3,7 @@
  *
  * The work is integer, byte-granular and, inside a slice, a strict dependence chain
  * (adaptive probability states + range coder low/range).  Parallelism therefore comes from
- *   - samples            (stage A: one thread per sample, HBM-bound, coalesced along x)
+ *   - samples            (stage A: one lane per sample column of a strip, coalesced along x)
  *   - slices x pictures  (stage B / decode: one thread per slice; a launch group holds
  *                         max_batch pictures so that tens of thousands of independent
  *                         coders are resident on the 148 SMs)
