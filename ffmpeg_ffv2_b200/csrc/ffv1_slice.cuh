@@ -1055,8 +1055,10 @@ FFGPU_HD int ff_line_next(const FFDevParams &P, const FFDecSlice &d, FFLineIt *i
 FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, const uint8_t *pkt,
                                     const FFDecCtx &D, FFDecResult *res, uint32_t *row_)
 {
+#if !defined(__CUDA_ARCH__)                          /* host build: tables through pointers */
     const FFRacTables *tab_ = D.tab;
     const int16_t *qt_all_ = D.qt_all;
+#endif
     const uint32_t mask = (1u << P.cbits) - 1;
     const int use32 = P.use32;
     /* how a finished sample reaches the picture: 0 at the end of the line (RGB), 1 one byte,
@@ -1077,7 +1079,7 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
     const uint8_t *prow = D.frame, *pprow = D.frame;   /* picture rows y-1 and y-2 (planar modes) */
     int ostep = 0, havep = 0, havepp = 0, usepic = 0;
     int sbase = 0;
-    (void)tab_; (void)row_; (void)qt_all_; (void)waited;
+    (void)row_; (void)waited;
 
     /* planar YCbCr, full-resolution planes: the previous lines are read back from the output
      * picture itself (what decode_plane just stored, ffv1dec.c:142-161), so no separate line
