@@ -86,6 +86,7 @@ SYMBOLS = [
     ("ffgpu_ffv1_decode_receive_frame", C.c_int, [C.c_void_p, C.POINTER(PictureOut)]),
     ("ffgpu_ffv1_decode_device", C.c_int, [C.c_void_p, C.POINTER(C.c_char_p),
                                            C.POINTER(C.c_size_t), C.c_int, C.c_void_p, C.c_void_p]),
+    ("ffgpu_ffv1_decode_device_status", C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int]),
     ("ffgpu_ffv1_decode_close", C.c_int, [C.c_void_p]),
     ("ffgpu_ffv1_frame_layout", C.c_size_t, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_size_t),
                                              C.POINTER(C.c_int), C.POINTER(C.c_int),
@@ -383,6 +384,16 @@ class FFV1Decoder:
         r = lib().ffgpu_ffv1_decode_device(self.h, arr, sizes, n, C.c_void_p(d_ptr), C.c_void_p(stream))
         if r < 0:
             raise FFGpuError("decode_device", r, _err())
+        self._n_device = n
+
+    def device_status(self):
+        """damaged-slice count per picture of the last decode_device() batch (waits for it)"""
+        n = getattr(self, "_n_device", 0)
+        arr = (C.c_int * max(n, 1))()
+        r = lib().ffgpu_ffv1_decode_device_status(self.h, arr, n)
+        if r < 0:
+            raise FFGpuError("decode_device_status", r, _err())
+        return list(arr)[:n]
 
     def close(self):
         if getattr(self, "h", None):

@@ -30,6 +30,7 @@
 
 #define NPREFIX_SETS 8
 #define MAX_DEPTH    8
+#define DEC_WIDE_POOL 16        /* picture-wide line scratches per decode group (see FFDecDev) */
 
 static thread_local char g_err[512];
 
@@ -448,6 +449,9 @@ extern "C" size_t ffgpu_ffv1_encoder_max_packet(const ffgpu_encoder *e)
 
 extern "C" uint64_t ffgpu_ffv1_encoder_launches(const ffgpu_encoder *e) { return e->launches; }
 
+struct EncJob;
+static int enc_launch(ffgpu_encoder *e, EncJob *j);
+
 /* find or build the prefix set for (key, picture structure, SAR) */
 static int enc_prefix_set(ffgpu_encoder *e, int key, int ps, int sn, int sd)
 {
@@ -461,7 +465,16 @@ static int enc_prefix_set(ffgpu_encoder *e, int key, int ps, int sn, int sd)
             slot = i;
     }
     if (slot < 0) {
-        /* cache full: wait for everything in flight, then start over */
+        /* cache full.  Pictures already queued in the group being filled hold indices into
+         * the current sets: launch that group first, then wait for everything in flight and
+         * start over */
+        EncJob *f = &e->jobs[e->fill];
+        if (f->state == JOB_FILLING && f->n > 0) {
+            int r = enc_launch(e, f);
+            if (r < 0)
+                return r;
+            e->fill = (e->fill + 1) % e->depth;
+        }
         CK(cudaDeviceSynchronize());
         memset(e->sets, 0, sizeof(e->sets));
         slot = 0;
@@ -628,15 +641,18 @@ extern "C" int ffgpu_ffv1_encode_send_frame(ffgpu_encoder *e, const ffgpu_pictur
         return fail(FFGPU_EOF, "send_frame after flush");
     if (j->state == JOB_RUNNING || j->state == JOB_DRAINING)
         return FFGPU_EAGAIN;                       /* every group is busy: receive first */
-    if (j->state == JOB_FREE) {
-        j->state = JOB_FILLING;
-        j->n = 0;
-    }
     key = e->opt.gop_size == 0 || e->picture_number % e->opt.gop_size == 0;
     ps = !pic->interlaced_frame ? 3 : 1 + !pic->top_field_first;   /* ffv1enc.c:944-947 */
     set = enc_prefix_set(e, key, ps, pic->sar_num, pic->sar_den);
     if (set < 0)
         return set;
+    j = &e->jobs[e->fill];                         /* a full prefix cache launches the filling group */
+    if (j->state == JOB_RUNNING || j->state == JOB_DRAINING)
+        return FFGPU_EAGAIN;
+    if (j->state == JOB_FREE) {
+        j->state = JOB_FILLING;
+        j->n = 0;
+    }
     if (j->n == 0)
         trace_mark(e->up_stream, "enc h2d", (int)(j - e->jobs), 0);
     if ((r = upload_picture(&e->P, e->s.pf, e->s.width, e->s.height, pic,
@@ -789,6 +805,9 @@ extern "C" int ffgpu_ffv1_encode_device(ffgpu_encoder *e, const void *d_frames, 
 static int enc_device_sizes(ffgpu_encoder *e, EncJob *j)
 {
     (void)e;
+    /* the batch may have run on the handle's own non-blocking stream, which the legacy
+     * default stream of the copies below does not wait for */
+    CK(cudaEventSynchronize(j->done));
     CK(cudaMemcpy(j->h_pkt_size, j->d_pkt_size, sizeof(uint32_t) * j->n, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(j->h_pkt_off, j->d_pkt_off, sizeof(uint32_t) * (j->n + 1), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(j->h_overflow, j->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost));
@@ -902,12 +921,15 @@ struct DecJob {
     cudaEvent_t done;
     cudaEvent_t decoded;        /* kernels finished: the download stream may start */
     int n, state, drained, fetched;
+    int n_device;               /* pictures of the last ffgpu_ffv1_decode_device() batch */
     uint8_t *h_pkt, *d_pkt;
     size_t pkt_cap, pkt_used;
     FFDecSlice *h_work, *d_work;
     int *h_nslices, *d_nslices;
     uint8_t *d_state;
     int32_t *d_lines;
+    int32_t *d_wide_lines;      /* picture-wide scratch pool for slices wider than their grid cell */
+    uint32_t *d_wide_used;
     uint8_t *d_frames;
     FFDecResult *d_result, *h_result;
     uint32_t *d_weight, *d_weight_sorted, *d_order;
@@ -946,6 +968,7 @@ static void dec_free_job(DecJob *j)
 {
     cudaFreeHost(j->h_pkt); cudaFree(j->d_pkt); cudaFreeHost(j->h_work); cudaFree(j->d_work);
     cudaFreeHost(j->h_nslices); cudaFree(j->d_nslices); cudaFree(j->d_state); cudaFree(j->d_lines);
+    cudaFree(j->d_wide_lines); cudaFree(j->d_wide_used);
     cudaFree(j->d_frames); cudaFree(j->d_result); cudaFreeHost(j->h_result);
     cudaFree(j->d_weight); cudaFree(j->d_weight_sorted); cudaFree(j->d_order); cudaFree(j->d_sort_tmp);
     free(j->meta);
@@ -1025,7 +1048,13 @@ static int dec_size_states(ffgpu_decoder *d, const uint8_t *pkt, size_t size)
             if (d->s.ctx_count[tmp[i].qidx[k]] > need)
                 need = d->s.ctx_count[tmp[i].qidx[k]];
     free(tmp);
-    d->hs.device_parse = 1;            /* from now on only slice 0 is parsed on the host */
+    /* from now on only slice 0 is parsed on the host -- unless the stream carries initial
+     * state tables: the state reset picks them by the slice's quant_table_index
+     * (ffv1.c:182-207), which must then be known before the kernels run */
+    d->hs.device_parse = 1;
+    for (int i = 0; i < d->s.qt_count; i++)
+        if (d->s.initial[i])
+            d->hs.device_parse = 0;
     d->max_ctx = need;
     d->P.total_ctx = d->P.nsets * need;
     for (int k = 0; k < d->P.nsets; k++)
@@ -1107,6 +1136,10 @@ static int dec_device_init(ffgpu_decoder *d)
         if (d->intra)
             CK(cudaMalloc(&j->d_state, B * state_frame));
         CK(cudaMalloc(&j->d_lines, B * d->max_slices * P->ncoded * 2 * d->line_stride * sizeof(int32_t)));
+        if (d->line_stride < d->s.width + 8) {
+            CK(cudaMalloc(&j->d_wide_lines, (size_t)DEC_WIDE_POOL * P->ncoded * 2 * (d->s.width + 8) * sizeof(int32_t)));
+            CK(cudaMalloc(&j->d_wide_used, sizeof(uint32_t)));
+        }
         CK(cudaMalloc(&j->d_frames, B * P->frame_bytes));
         CK(cudaMemset(j->d_frames, 0, B * P->frame_bytes));
         CK(cudaMalloc(&j->d_result, B * d->max_slices * sizeof(FFDecResult)));
@@ -1209,6 +1242,10 @@ static void dec_fill_dev(const ffgpu_decoder *d, const DecJob *j, uint8_t *frame
     D->state = d->intra ? j->d_state : d->d_state_shared;
     D->lines = j->d_lines;
     D->line_stride = d->line_stride;
+    D->wide_lines = j->d_wide_lines;
+    D->wide_stride = d->s.width + 8;
+    D->wide_count = j->d_wide_lines ? DEC_WIDE_POOL : 0;
+    D->wide_used = j->d_wide_used;
     D->frames = frames;
     D->result = j->d_result;
     D->max_slices = d->max_slices;
@@ -1332,13 +1369,13 @@ static int dec_add_packet(ffgpu_decoder *d, DecJob *j, const uint8_t *pkt, size_
     return 0;
 }
 
-/* after a group has finished: damage bookkeeping (ffv1dec.c:351-359, :940-969) */
-static int dec_finish_frame(ffgpu_decoder *d, DecJob *j, int i, ffgpu_picture_out *out)
+/* per-slice damage of picture i of a finished group: CRC / header failures found on the
+ * device and the end-of-slice check of ffv1dec.c:351-359.  Returns the damaged-slice count. */
+static int dec_mark_damage(ffgpu_decoder *d, DecJob *j, int i)
 {
     DecFrameMeta *m = &j->meta[i];
     const FFDevParams *P = &d->P;
-    uint8_t *frame = j->d_frames + (size_t)i * P->frame_bytes;
-    int damaged = 0, r;
+    int damaged = 0;
     for (int s = 0; s < m->nslices; s++) {
         const FFDecSlice *w = &j->h_work[(size_t)i * d->max_slices + s];
         const FFDecResult *res = &j->h_result[(size_t)i * d->max_slices + s];
@@ -1350,6 +1387,9 @@ static int dec_finish_frame(ffgpu_decoder *d, DecJob *j, int i, ffgpu_picture_ou
             }
             m->rect[s].x = res->x; m->rect[s].y = res->y;
             m->rect[s].w = res->w; m->rect[s].h = res->h;
+        } else if (!w->skip && (res->flags & FF_RES_HDR_BAD)) {
+            m->damaged[s] = 1;                     /* no picture-wide scratch left for it */
+            d->hs.damaged[s] = 1;
         }
         if (!(res->flags & FF_RES_NOT_DECODED) && P->ac != FF_AC_GOLOMB && P->version > 2) {
             const int v = (int)res->size - (int)res->end_pos - 2 - 5 * P->ec;
@@ -1360,6 +1400,17 @@ static int dec_finish_frame(ffgpu_decoder *d, DecJob *j, int i, ffgpu_picture_ou
         }
         damaged += m->damaged[s];
     }
+    return damaged;
+}
+
+/* after a group has finished: damage bookkeeping (ffv1dec.c:351-359, :940-969) */
+static int dec_finish_frame(ffgpu_decoder *d, DecJob *j, int i, ffgpu_picture_out *out)
+{
+    DecFrameMeta *m = &j->meta[i];
+    const FFDevParams *P = &d->P;
+    uint8_t *frame = j->d_frames + (size_t)i * P->frame_bytes;
+    int damaged, r;
+    damaged = dec_mark_damage(d, j, i);
     if (damaged && d->have_prev) {
         const uint8_t *prev = i > 0 ? j->d_frames + (size_t)(i - 1) * P->frame_bytes : d->d_prev;
         if (i == 0)
@@ -1621,9 +1672,30 @@ extern "C" int ffgpu_ffv1_decode_device(ffgpu_decoder *d, const uint8_t *const *
     if (r >= 0)
         CK(cudaEventRecord(j->done, st));
     d->profile_next = 0;
+    j->n_device = r >= 0 ? nframes : 0;
     j->n = 0;
     j->state = JOB_FREE;
     return r;
+}
+
+extern "C" int ffgpu_ffv1_decode_device_status(ffgpu_decoder *d, int *damaged_slices, int nframes)
+{
+    DecJob *j;
+    int total = 0;
+    if (!d || !d->dev_ready)
+        return fail(FFGPU_EINVAL, "no device batch");
+    cudaSetDevice(d->opt.device);
+    j = &d->jobs[0];
+    if (nframes > j->n_device)
+        nframes = j->n_device;
+    CK(cudaEventSynchronize(j->done));             /* kernels + result table copy have finished */
+    for (int i = 0; i < nframes; i++) {
+        const int n = dec_mark_damage(d, j, i);
+        if (damaged_slices)
+            damaged_slices[i] = n;
+        total += n;
+    }
+    return total;
 }
 
 extern "C" int ffgpu_ffv1_decoder_profile(ffgpu_decoder *d, int enable)

@@ -529,7 +529,19 @@ k_decode(const FFDevParams P, const FFDecDev D, int nframes)
             C.line_stride = D.line_stride;
             C.frame = D.frames + (size_t)f * P.frame_bytes;
             C.gate_wait = D.gate_wait;
-            ff_decode_slice(P, w, D.pkt, C, &r, 0);
+            if (w.w + 8 > D.line_stride) {
+                /* rectangle wider than the grid cell: picture-wide scratch from the pool */
+                const uint32_t slot_w = D.wide_used ? atomicAdd(D.wide_used, 1u) : 0xFFFFFFFFu;
+                if (slot_w < (uint32_t)D.wide_count) {
+                    C.lines = D.wide_lines + (size_t)slot_w * P.ncoded * 2 * D.wide_stride;
+                    C.line_stride = D.wide_stride;
+                } else {
+                    C.lines = 0;
+                    r.flags |= FF_RES_HDR_BAD | FF_RES_NOT_DECODED;
+                }
+            }
+            if (C.lines)
+                ff_decode_slice(P, w, D.pkt, C, &r, 0);
         }
     }
     D.result[gid] = r;
@@ -564,6 +576,8 @@ extern "C" int ffk_decode_group(const FFDevParams *P, const FFDecDev *D, int nfr
         k_dec_init_state<<<g0, 256, 0, st>>>(*P, *D, P->ac == FF_AC_GOLOMB);
     }
     mark(D->events, FFK_DEC_INIT_STATE + 1, st);
+    if (D->wide_used)
+        cudaMemsetAsync(D->wide_used, 0, sizeof(uint32_t), st);
     const int total = nframes * D->max_slices;
     if (D->weight && D->order) {
         size_t tmp = D->sort_tmp_bytes;

@@ -68,6 +68,13 @@ typedef struct FFDecDev {
     uint8_t *state;                 /* [nstate_frames][max_slices][total_ctx][32 | 8]   */
     int32_t *lines;                 /* [nframes*max_slices][ncoded][2][line_stride]     */
     int line_stride;
+    /* a v3 slice header may name any rectangle of the picture (ffv1dec.c:176-184), wider than
+     * the grid cell `lines` was sized for: such slices take a picture-wide scratch from this
+     * small pool (wide_used is zeroed per launch); when it runs dry the slice is reported
+     * damaged instead of writing past its scratch */
+    int32_t *wide_lines;            /* [wide_count][ncoded][2][wide_stride]             */
+    int wide_stride, wide_count;
+    uint32_t *wide_used;
     uint8_t *frames;                /* [nframes][frame_bytes] output pictures           */
     FFDecResult *result;            /* [nframes][max_slices]                            */
     int max_slices;

@@ -188,6 +188,15 @@ int ffgpu_ffv1_decode_device(ffgpu_decoder *dec, const uint8_t *const *pkts,
                              const size_t *pkt_sizes, int nframes, void *d_frames,
                              void *cuda_stream);
 
+/* Damage report of the last ffgpu_ffv1_decode_device() batch (the send/receive path reports
+ * the same through ffgpu_picture_out.damaged_slices): waits for the batch, then
+ * damaged_slices[i] = slices of picture i with a CRC mismatch, an invalid slice header or a
+ * bytestream-end mismatch (ffv1dec.c:905-922, :296-300, :351-359).  Device batches are NOT
+ * concealed (there is no previous picture the library owns); a caller that needs the
+ * reference's concealment copies the damaged pictures' predecessor itself or uses
+ * send_packet/receive_frame.  Returns the total number of damaged slices or a negative error. */
+int ffgpu_ffv1_decode_device_status(ffgpu_decoder *dec, int *damaged_slices, int nframes);
+
 int ffgpu_ffv1_decode_close(ffgpu_decoder *dec);
 
 /* ---- shared helpers ---- */

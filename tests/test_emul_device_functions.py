@@ -85,3 +85,37 @@ def test_damaged_packets():
             assert out["oracle"][1] == out["emul"][1]
             for a, b in zip(out["oracle"][0], out["emul"][0]):
                 assert np.array_equal(a, b)
+
+
+def test_wide_slice_header_decodes_like_the_reference():
+    """a slice header naming a rectangle wider than its grid cell (hand-coded with
+    tests/ffv1_bits.py): product device functions == reference == oracle"""
+    import numpy as np
+    import ffv1_bits as fb
+    import random
+    if not cc.available("ref"):
+        pytest.skip("oracle/_ref not built")
+    w, h, fmt = 192, 96, "yuv420p"
+    enc = cc.Encoder("ref", w, h, fmt, slices=24, coder=-2, level=3, gop_size=1)
+    p0 = enc.encode(synth.smooth(fmt, w, h, 0))
+    p1 = enc.encode(synth.smooth(fmt, w, h, 1))
+    sl = fb.split_v3_packet(p1)
+    assert len(sl) == 24 and fb.wrap_slice(p1[sl[3][0]:sl[3][0] + sl[3][1]]) == \
+        p1[sl[3][0]:sl[3][0] + sl[3][1] + 8]          # the helper's trailer/CRC == the reference's
+    rc = fb.RangeEncoder(*fb.default_tables())
+    st = [128] * 32
+    for v in (0, 1, 3, 0, 0, 0, 3, 0, 1):
+        rc.put_symbol(st, v)
+    rnd = random.Random(5)
+    st2 = [[128] * 32 for _ in range(8)]
+    for _ in range(6000):
+        rc.put_symbol(st2[rnd.randrange(8)], rnd.choice((0, 0, 0, 1, -1, 2, -3, 7, -20)), True)
+    bad = p1[:sl[0][1] + 8] + fb.wrap_slice(rc.terminate(1))
+    outs = {}
+    for which in ("ref", "oracle", "emul"):
+        d = cc.Decoder(which, w, h, enc.extradata)
+        d.decode(p0)
+        outs[which] = [a.copy() for a in d.decode(bad)]
+    for which in ("oracle", "emul"):
+        for a, b in zip(outs["ref"], outs[which]):
+            assert np.array_equal(a, b), which

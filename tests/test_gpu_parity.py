@@ -354,3 +354,97 @@ def test_device_resident_batch():
     for i in range(n):
         for (off, pitch, rows, rb), a in zip(planes, srcs[i]):
             assert np.array_equal(back[i, off:off + pitch * rows].reshape(rows, pitch)[:, :rb], a)
+
+
+def _wide_slice_packet(w, h, fmt):
+    """a 2-slice packet on a 6x4-slice stream: the real slice 0 plus a hand-coded slice whose
+    header claims 4 of the 6 grid columns of row 1 (ffv1dec.c:176-184 accepts any rectangle
+    inside the picture)"""
+    import random
+    import ffv1_bits as fb
+    kw = dict(slices=24, coder=-2, level=3, gop_size=1)
+    which = "ref" if cc.available("ref") else "oracle"
+    enc = cc.Encoder(which, w, h, fmt, **kw)
+    assert (enc.info["num_h_slices"], enc.info["num_v_slices"]) == (6, 4)
+    p0 = enc.encode(synth.smooth(fmt, w, h, 0))
+    p1 = enc.encode(synth.smooth(fmt, w, h, 1))
+    sl = fb.split_v3_packet(p1)
+    rc = fb.RangeEncoder(*fb.default_tables())
+    st = [128] * 32
+    for v in (0, 1, 3, 0, 0, 0, 3, 0, 1):      # sx sy sw-1 sh-1 | qidx x2 | ps | sar
+        rc.put_symbol(st, v)
+    rnd = random.Random(5)
+    st2 = [[128] * 32 for _ in range(8)]
+    for _ in range(6000):                      # arbitrary but well-formed range-coded payload
+        rc.put_symbol(st2[rnd.randrange(8)], rnd.choice((0, 0, 0, 1, -1, 2, -3, 7, -20)), True)
+    return enc.extradata, p0, p1[:sl[0][1] + 8] + fb.wrap_slice(rc.terminate(1)), which
+
+
+def test_slice_header_wider_than_its_grid_cell():
+    """with more than 16 slices the per-slice line scratch is one grid cell
+    wide; a header that names a wider rectangle must decode like the reference (picture-wide
+    scratch from the pool), not write past the scratch"""
+    F = gpu()
+    w, h, fmt = 192, 96, "yuv420p"
+    xd, p0, bad, which = _wide_slice_packet(w, h, fmt)
+    ref = cc.Decoder(which, w, h, xd)
+    dec = F.FFV1Decoder(w, h, xd)
+    ref.decode(p0)
+    dec.decode(p0)
+    for _ in range(3):                         # a few times: the pool counter is per launch
+        want = [a.copy() for a in ref.decode(bad)]
+        got = dec.decode(bad)
+        for a, b in zip(want, got):
+            assert np.array_equal(a, b)
+    # 20 such packets in ONE launch group exhaust the 16-entry pool: still no overrun, the
+    # slices that found no scratch are reported damaged
+    dec2 = F.FFV1Decoder(w, h, xd, max_batch=24, pipeline_depth=1)
+    n, i, got = 20, 0, 0
+    while True:
+        if i < n:
+            if dec2.send_packet(bad, pts=i, dst=dec2.alloc_picture()):
+                i += 1
+                continue
+        elif i == n:
+            dec2.send_packet(None)
+            i += 1
+        r = dec2.receive_frame()
+        if r == F.EOF:
+            break
+        if r is not None:
+            got += 1
+    assert got == n
+
+
+def test_more_prefix_sets_than_cache_slots_in_one_group():
+    """> 8 distinct (key, picture structure, SAR) combinations inside one
+    launch group used to recycle prefix slots that queued pictures still referenced"""
+    F = gpu()
+    w, h, fmt = 160, 120, "yuv420p10le"
+    kw = dict(slices=4, gop_size=1)
+    frames = [synth.testsrc2_like(fmt, w, h, i) for i in range(24)]
+    sars = [(i + 1, 1 + (i % 3)) for i in range(12)]
+    which = "ref" if cc.available("ref") else "oracle"
+    enc = F.FFV1Encoder(w, h, fmt, max_batch=32, pipeline_depth=2, **kw)
+    got, i = [], 0
+    while True:
+        if i < len(frames):
+            if enc.send_frame(frames[i], pts=i, sar=sars[i % len(sars)]):
+                i += 1
+                continue
+        elif i == len(frames):
+            enc.send_frame(None)
+            i += 1
+        r = enc.receive_packet()
+        if r == F.EOF:
+            break
+        if r is not None:
+            got.append(r[0])
+    assert len(got) == len(frames)
+    # every packet decodes to its picture and carries ITS sample aspect ratio
+    dec = F.FFV1Decoder(w, h, enc.extradata)
+    for i, p in enumerate(got):
+        out = dec.decode(p)
+        for a, b in zip(out, frames[i]):
+            assert np.array_equal(a, b)
+        assert (dec.last.sar_num, dec.last.sar_den) == sars[i % len(sars)], i
