@@ -124,6 +124,17 @@ def make_frames(wl, count, first_index=0, stride=1):
             for i in range(count)]
 
 
+def enc_samples(fmt, w, h):
+    """coded samples per picture"""
+    import synth
+    f = synth.fmt_info(fmt)
+    cw, ch = -(-w >> f["hs"]), -(-h >> f["vs"])
+    if f["layout"] in ("planar", "ya8"):
+        n = w * h + (2 * cw * ch if f["chroma"] and f["layout"] == "planar" else 0)
+        return n + (w * h if f["alpha"] else 0)
+    return (3 + f["alpha"]) * w * h
+
+
 def cpu_codec_kind():
     import cpucodec as cc
     return ("ref", "reference") if cc.available("ref") else ("oracle", "port")
@@ -296,6 +307,7 @@ def main():
         raise SystemExit("PARITY FAILURE: decoded pictures differ from the input")
     pkt_bytes = sum(len(p) for p in pkts)
     raw_bytes = sum(rb * rows for (_o, _p, rows, rb) in planes)
+    decisions_total, decisions_heaviest = enc.decisions()
 
     # ---- value: inputs resident in HBM, CUDA events on the launching stream ----
     enc.profile(True)
@@ -353,6 +365,27 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kern[dom]}
+
+    # ---- the serial side of the path: binary decisions (SURVEY 8d "cycles per bin") ----
+    nsamples = enc_samples(fmt, w, h) * B
+    decisions = None
+    if decisions_total:
+        mhz = 1965.0
+        slots = 148 * 4 * mhz * 1e3            # warp-instruction issue slots per millisecond
+        decisions = {
+            "per_sample": decisions_total / nsamples,
+            "per_step": int(decisions_total),
+            "heaviest_slice": int(decisions_heaviest),
+            "slices_per_step": int(B * enc.info["num_h_slices"] * enc.info["num_v_slices"]),
+            # throughput view: issue slots the whole GPU spends per decision (1 slot = one warp
+            # instruction on one of the 148 x 4 schedulers at the maximum SM clock)
+            "code_issue_slots_per_decision": kern.get("code", 0.0) * slots / decisions_total,
+            "decode_issue_slots_per_decision": kern.get("decode", 0.0) * slots / decisions_total,
+            # latency view: the launch cannot be shorter than its heaviest slice, a strictly
+            # serial chain of decisions on one lane
+            "code_cycles_per_decision_if_bound_by_heaviest": kern.get("code", 0.0) * mhz * 1e3 / max(decisions_heaviest, 1),
+            "decode_cycles_per_decision_if_bound_by_heaviest": kern.get("decode", 0.0) * mhz * 1e3 / max(decisions_heaviest, 1),
+        }
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
     e2e = None
@@ -597,6 +630,7 @@ def main():
         "pixel_GBps": value * raw_bytes / 1e9,
         "packet_bytes_per_picture": pkt_bytes / B, "raw_bytes_per_picture": raw_bytes,
         "kernel_ms_per_step": kern, "wall_ms_per_step": 1e3 * wall / K,
+        "decisions": decisions,
         "roofline": roofline, "gpu_launches": int(gpu_launches), "clocks": clocks,
         "e2e": e2e, "cpu_baseline": cpu, "pcie": pcie,
     }

@@ -24,10 +24,24 @@ def sources():
            [os.path.join(HERE, "..", "include", "ffgpu.h")]
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant/defines: development builds for A/B runs (build/libffgpu_<variant>.so, loaded
+    through the FFGPU_LIB environment variable); the product is the plain build"""
+    global OUT
+    if variant:
+        saved = OUT
+        OUT = os.path.join(HERE, "build", "libffgpu_%s.so" % variant)
+        try:
+            return _build(True, verbose, "build/" + variant, list(defines))
+        finally:
+            OUT = saved
+    return _build(force, verbose, "build", [])
+
+
+def _build(force, verbose, objsub, defines):
     if not force and not _newer(OUT, sources()):
         return OUT
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, objsub)
     os.makedirs(objdir, exist_ok=True)
     run = lambda cmd: subprocess.run(cmd, check=True, stdout=None if verbose else subprocess.PIPE,
                                      stderr=subprocess.STDOUT)
@@ -37,7 +51,7 @@ def build(force=False, verbose=False):
     objs = [host_o]
     for cu in ("ffv1_kernels.cu", "ffgpu_api.cu"):
         o = os.path.join(objdir, cu.replace(".cu", ".o"))
-        run([NVCC] + ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+        run([NVCC] + ARCH + defines + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
                              "-c", os.path.join(CSRC, cu), "-o", o])
         objs.append(o)
     run([NVCC] + ARCH + ["-shared", "-cudart", "static", "-o", OUT] + objs)

@@ -13,7 +13,8 @@ EXTERNAL = -542398533
 
 
 def lib_path():
-    return os.path.join(_HERE, "libffgpu.so")
+    # FFGPU_LIB: development hook for A/B runs of differently built libraries
+    return os.environ.get("FFGPU_LIB") or os.path.join(_HERE, "libffgpu.so")
 
 
 class FFGpuError(RuntimeError):
@@ -29,6 +30,7 @@ class EncOptions(C.Structure):
         ("coder", C.c_int), ("context", C.c_int), ("slicecrc", C.c_int),
         ("strict_std_compliance", C.c_int), ("bits_per_raw_sample", C.c_int),
         ("device", C.c_int), ("max_batch", C.c_int), ("pipeline_depth", C.c_int),
+        ("ndevices", C.c_int), ("devices", C.c_int * 16),
     ]
 
 
@@ -44,7 +46,7 @@ class DecOptions(C.Structure):
     _fields_ = [
         ("width", C.c_int), ("height", C.c_int), ("extradata", C.c_char_p),
         ("extradata_size", C.c_int), ("device", C.c_int), ("max_batch", C.c_int),
-        ("pipeline_depth", C.c_int),
+        ("pipeline_depth", C.c_int), ("ndevices", C.c_int), ("devices", C.c_int * 16),
     ]
 
 
@@ -69,6 +71,7 @@ SYMBOLS = [
     ("ffgpu_ffv1_encode_receive_packet", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t,
                                                    C.POINTER(C.c_size_t), C.POINTER(C.c_int),
                                                    C.POINTER(C.c_int64)]),
+    ("ffgpu_ffv1_encode_packet_ready", C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),
     ("ffgpu_ffv1_encode_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     ("ffgpu_ffv1_encode_device_result", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p),
                                                   C.POINTER(C.c_size_t)]),
@@ -97,6 +100,7 @@ SYMBOLS = [
     ("ffgpu_ffv1_encoder_kernel_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
     ("ffgpu_ffv1_decoder_profile", C.c_int, [C.c_void_p, C.c_int]),
     ("ffgpu_ffv1_decoder_kernel_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
+    ("ffgpu_ffv1_encoder_decisions", C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     ("ffgpu_last_error", C.c_char_p, []),
     ("ffgpu_abi_version", C.c_int, []),
 ]
@@ -158,11 +162,11 @@ class FFV1Encoder:
 
     def __init__(self, width, height, pix_fmt, slices=0, level=-99, gop_size=12, coder=0, context=0,
                  slicecrc=-1, strict=0, bits_per_raw_sample=0, device=0, max_batch=0,
-                 pipeline_depth=0):
+                 pipeline_depth=0, devices=()):
         self._fmt = pix_fmt.encode()
         self.opt = EncOptions(width, height, self._fmt, slices, level, gop_size, coder, context,
                               slicecrc, strict, bits_per_raw_sample, device, max_batch,
-                              pipeline_depth)
+                              pipeline_depth, len(devices), (C.c_int * 16)(*devices))
         self.h = C.c_void_p()
         r = lib().ffgpu_ffv1_encode_init(C.byref(self.h), C.byref(self.opt))
         if r < 0:
@@ -258,6 +262,15 @@ class FFV1Encoder:
             raise FFGpuError("encoder_kernel_ms", n, _err())
         return dict(zip(self.ENC_KERNELS, list(ms)[:n]))
 
+    def decisions(self):
+        """(total binary decisions, decisions of the heaviest slice) of the last device batch"""
+        tot = C.c_uint64()
+        mx = C.c_uint32()
+        r = lib().ffgpu_ffv1_encoder_decisions(self.h, C.byref(tot), C.byref(mx))
+        if r < 0:
+            raise FFGpuError("encoder_decisions", r, _err())
+        return tot.value, mx.value
+
     def device_result(self, frame):
         p = C.c_void_p()
         n = C.c_size_t()
@@ -278,10 +291,11 @@ class FFV1Encoder:
 class FFV1Decoder:
     """Mirror of ff_ffv1_decoder (ffv1dec.c:1087)."""
 
-    def __init__(self, width, height, extradata=b"", device=0, max_batch=0, pipeline_depth=0):
+    def __init__(self, width, height, extradata=b"", device=0, max_batch=0, pipeline_depth=0,
+                 devices=()):
         self._ex = bytes(extradata)
         self.opt = DecOptions(width, height, self._ex, len(self._ex), device, max_batch,
-                              pipeline_depth)
+                              pipeline_depth, len(devices), (C.c_int * 16)(*devices))
         self.h = C.c_void_p()
         r = lib().ffgpu_ffv1_decode_init(C.byref(self.h), C.byref(self.opt))
         if r < 0:

@@ -136,6 +136,21 @@ extern "C" size_t ffgpu_ffv1_frame_layout(const char *pix_fmt, int width, int he
     return off;
 }
 
+/* Slice coders per warp.  A launch with fewer work items than the GPU has resident lanes
+ * (148 SMs x 16 warps x 32 lanes) spreads them out, down to one slice per warp: unrelated
+ * slices in one warp execute each other's divergent paths, which only pays off when the
+ * lanes are needed.  FFGPU_LANE_STRIDE overrides (1, 2, 4, ... 32). */
+static int coder_lane_stride(long items)
+{
+    const char *env = getenv("FFGPU_LANE_STRIDE");
+    int s = 32;
+    if (env && atoi(env) >= 1 && atoi(env) <= 32)
+        return atoi(env);
+    while (s > 1 && items * s > 148L * 16 * 32)
+        s >>= 1;
+    return s;
+}
+
 /* quant tables in the layout the kernels index: [table][5*256 + flag] */
 static void flatten_qt(const FFStream *s, int16_t *q)
 {
@@ -153,7 +168,8 @@ static void flatten_qt(const FFStream *s, int16_t *q)
 static int copy_picture(const FFDevParams *P, const FFPixFmt *pf, int w, int h, uint8_t *const data[4],
                         const int linesize[4], uint8_t *d_frame, int to_device, cudaStream_t st)
 {
-    const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    const cudaMemcpyKind kind = cudaMemcpyDefault;      /* host or device planes: taken from the pointers */
+    (void)to_device;
     int k = 0;
     while (k < pf->nplanes) {
         int rb, rows;
@@ -188,6 +204,167 @@ static int copy_picture(const FFDevParams *P, const FFPixFmt *pf, int w, int h, 
             k++;
         }
     }
+    return 0;
+}
+
+
+/* ====================================================================== */
+/* pageable caller memory: pinned staging + a small pool of copy threads   */
+/* ====================================================================== */
+/* AVFrames are ordinary (pageable) memory.  A cudaMemcpyAsync on such a pointer is staged by
+ * the driver and blocks the calling thread -- for a download until the kernels before it have
+ * finished -- which would serialise the launch-group pipeline.  Pictures in pageable memory
+ * therefore cross through pinned staging buffers owned by the handle: the host side of the
+ * copy is a plain memcpy, split over a few worker threads (one core moves ~10 GB/s, a 4K
+ * 10-bit picture is 25 MB), and the PCIe side is one linear asynchronous copy per picture.
+ * Pinned, registered or device pointers skip all of this.  FFGPU_COPY_THREADS (default 4,
+ * 1 = the calling thread only) sizes the pool. */
+enum { MEM_PAGEABLE = 0, MEM_PINNED, MEM_DEVICE };
+
+static int mem_kind(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return MEM_PAGEABLE;
+    }
+    if (a.type == cudaMemoryTypeUnregistered)
+        return MEM_PAGEABLE;
+    return a.type == cudaMemoryTypeHost ? MEM_PINNED : MEM_DEVICE;
+}
+
+struct CopyTask {
+    uint8_t *dst;
+    const uint8_t *src;
+    size_t dst_pitch, src_pitch, rowbytes;
+    int rows;
+};
+
+#define POOL_MAX_THREADS 16
+#define POOL_MAX_CHUNKS  64
+static struct {
+    pthread_once_t once;
+    pthread_mutex_t use;            /* one parallel copy at a time; others copy inline */
+    pthread_mutex_t lock;
+    pthread_cond_t wake, done;
+    pthread_t thr[POOL_MAX_THREADS];
+    int nthreads;
+    CopyTask chunk[POOL_MAX_CHUNKS];
+    int nchunks, next, finished;
+    uint64_t generation;
+} g_pool = { PTHREAD_ONCE_INIT, PTHREAD_MUTEX_INITIALIZER, PTHREAD_MUTEX_INITIALIZER,
+             PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, {0}, 0, {{0}}, 0, 0, 0, 0 };
+
+static void copy_rows(const CopyTask *t)
+{
+    if (t->dst_pitch == t->src_pitch && t->rowbytes == t->dst_pitch) {
+        memcpy(t->dst, t->src, (size_t)t->rows * t->rowbytes);
+        return;
+    }
+    for (int y = 0; y < t->rows; y++)
+        memcpy(t->dst + (size_t)y * t->dst_pitch, t->src + (size_t)y * t->src_pitch, t->rowbytes);
+}
+
+static void *pool_worker(void *)
+{
+    uint64_t seen = 0;
+    pthread_mutex_lock(&g_pool.lock);
+    for (;;) {
+        while (g_pool.generation == seen || g_pool.next >= g_pool.nchunks) {
+            seen = g_pool.generation;
+            pthread_cond_wait(&g_pool.wake, &g_pool.lock);
+        }
+        const int c = g_pool.next++;
+        pthread_mutex_unlock(&g_pool.lock);
+        copy_rows(&g_pool.chunk[c]);
+        pthread_mutex_lock(&g_pool.lock);
+        if (++g_pool.finished == g_pool.nchunks)
+            pthread_cond_signal(&g_pool.done);
+    }
+    return NULL;
+}
+
+static void pool_start(void)
+{
+    const char *env = getenv("FFGPU_COPY_THREADS");
+    int n = env ? atoi(env) : 4;
+    if (n < 1) n = 1;
+    if (n > POOL_MAX_THREADS) n = POOL_MAX_THREADS;
+    for (int i = 0; i < n - 1; i++) {              /* the calling thread is one of the n */
+        if (pthread_create(&g_pool.thr[g_pool.nthreads], NULL, pool_worker, NULL) != 0)
+            break;
+        pthread_detach(g_pool.thr[g_pool.nthreads]);
+        g_pool.nthreads++;
+    }
+}
+
+/* copy the planes described by tasks[], in parallel when the pool is free */
+static void par_copy(const CopyTask *tasks, int ntasks)
+{
+    pthread_once(&g_pool.once, pool_start);
+    if (g_pool.nthreads == 0 || pthread_mutex_trylock(&g_pool.use) != 0) {
+        for (int i = 0; i < ntasks; i++)
+            copy_rows(&tasks[i]);
+        return;
+    }
+    pthread_mutex_lock(&g_pool.lock);
+    g_pool.nchunks = 0;
+    for (int i = 0; i < ntasks; i++) {
+        /* about 1 MB per chunk, at most POOL_MAX_CHUNKS / ntasks chunks per plane */
+        const size_t bytes = (size_t)tasks[i].rows * tasks[i].rowbytes;
+        int parts = (int)(bytes >> 20) + 1;
+        const int most = POOL_MAX_CHUNKS / ntasks;
+        if (parts > most) parts = most;
+        if (parts > tasks[i].rows) parts = tasks[i].rows > 0 ? tasks[i].rows : 1;
+        for (int k = 0; k < parts; k++) {
+            CopyTask c = tasks[i];
+            const int y0 = (int)((long)tasks[i].rows * k / parts), y1 = (int)((long)tasks[i].rows * (k + 1) / parts);
+            c.dst += (size_t)y0 * c.dst_pitch;
+            c.src += (size_t)y0 * c.src_pitch;
+            c.rows = y1 - y0;
+            g_pool.chunk[g_pool.nchunks++] = c;
+        }
+    }
+    g_pool.next = 0;
+    g_pool.finished = 0;
+    g_pool.generation++;
+    pthread_cond_broadcast(&g_pool.wake);
+    while (g_pool.next < g_pool.nchunks) {         /* the caller works too */
+        const int c = g_pool.next++;
+        pthread_mutex_unlock(&g_pool.lock);
+        copy_rows(&g_pool.chunk[c]);
+        pthread_mutex_lock(&g_pool.lock);
+        g_pool.finished++;
+    }
+    while (g_pool.finished < g_pool.nchunks)
+        pthread_cond_wait(&g_pool.done, &g_pool.lock);
+    pthread_mutex_unlock(&g_pool.lock);
+    pthread_mutex_unlock(&g_pool.use);
+}
+
+/* a picture between caller planes and a staging buffer in the device layout */
+static int stage_picture(const FFDevParams *P, const FFPixFmt *pf, int w, int h, uint8_t *const data[4],
+                         const int linesize[4], uint8_t *stage, int to_stage)
+{
+    CopyTask t[4];
+    int n = 0;
+    for (int k = 0; k < pf->nplanes; k++) {
+        int rb, rows;
+        ff_plane_geometry(pf, w, h, k, &rb, &rows);
+        if (!data[k] || linesize[k] < rb)
+            return fail(FFGPU_EINVAL, "picture plane %d missing or linesize too small", k);
+        if (to_stage) {
+            t[n].dst = stage + P->plane_off[k]; t[n].dst_pitch = (size_t)P->pitch[k];
+            t[n].src = data[k];                 t[n].src_pitch = (size_t)linesize[k];
+        } else {
+            t[n].dst = data[k];                 t[n].dst_pitch = (size_t)linesize[k];
+            t[n].src = stage + P->plane_off[k]; t[n].src_pitch = (size_t)P->pitch[k];
+        }
+        t[n].rowbytes = (size_t)rb;
+        t[n].rows = rows;
+        n++;
+    }
+    par_copy(t, n);
     return 0;
 }
 
@@ -226,6 +403,7 @@ struct EncJob {
     uint32_t *h_pkt_size, *h_pkt_off, *h_overflow;
     uint8_t *h_pkt;
     size_t h_pkt_cap;
+    uint8_t *h_stage;           /* pinned staging for pictures in pageable memory (lazily) */
     int64_t *pts;
     int *key;
 };
@@ -266,6 +444,11 @@ struct ffgpu_encoder {
     uint64_t launches;
     int profile;                        /* record events around every kernel of device batches */
     void *events[FFK_ENC_KERNELS + 1];
+    /* more than one GPU: this handle only routes; sub[i] is a complete encoder on devices[i].
+     * Picture k belongs to sub[(k / chunk) % nsub]; packets are returned in that order. */
+    int nsub, chunk, send_blocked;
+    ffgpu_encoder *sub[FFGPU_MAX_DEVICES];
+    uint64_t in_count, out_count;
 };
 
 static int enc_free_job(EncJob *j)
@@ -279,6 +462,7 @@ static int enc_free_job(EncJob *j)
     cudaFree(j->d_weight); cudaFree(j->d_weight_sorted); cudaFree(j->d_order); cudaFree(j->d_sort_tmp);
     cudaFreeHost(j->h_frame_set); cudaFreeHost(j->h_frame_key); cudaFreeHost(j->h_pkt_size);
     cudaFreeHost(j->h_pkt_off); cudaFreeHost(j->h_overflow); cudaFreeHost(j->h_pkt);
+    cudaFreeHost(j->h_stage);
     free(j->pts); free(j->key);
     if (j->done) cudaEventDestroy(j->done);
     if (j->uploaded) cudaEventDestroy(j->uploaded);
@@ -425,6 +609,23 @@ extern "C" int ffgpu_ffv1_encode_init(ffgpu_encoder **penc, const ffgpu_enc_opti
     }
     if (e->depth > MAX_DEPTH)
         e->depth = MAX_DEPTH;
+    if (opt->ndevices > 1) {
+        ffgpu_enc_options so = e->opt;
+        if (opt->ndevices > FFGPU_MAX_DEVICES) {
+            ffgpu_ffv1_encode_close(e);
+            return fail(FFGPU_EINVAL, "ndevices %d exceeds %d", opt->ndevices, FFGPU_MAX_DEVICES);
+        }
+        so.ndevices = 0;
+        e->chunk = e->intra ? 1 : opt->gop_size;
+        for (int i = 0; i < opt->ndevices; i++) {
+            so.device = opt->devices[i];
+            if ((r = ffgpu_ffv1_encode_init(&e->sub[i], &so)) < 0) {
+                ffgpu_ffv1_encode_close(e);
+                return r;
+            }
+            e->nsub = i + 1;
+        }
+    }
     *penc = e;
     return 0;
 }
@@ -447,7 +648,13 @@ extern "C" size_t ffgpu_ffv1_encoder_max_packet(const ffgpu_encoder *e)
     return e->P.pkt_stride;
 }
 
-extern "C" uint64_t ffgpu_ffv1_encoder_launches(const ffgpu_encoder *e) { return e->launches; }
+extern "C" uint64_t ffgpu_ffv1_encoder_launches(const ffgpu_encoder *e)
+{
+    uint64_t n = e->launches;
+    for (int i = 0; i < e->nsub; i++)
+        n += e->sub[i]->launches;
+    return n;
+}
 
 struct EncJob;
 static int enc_launch(ffgpu_encoder *e, EncJob *j);
@@ -617,8 +824,83 @@ static int enc_fetch(ffgpu_encoder *e, EncJob *j)
     return 0;
 }
 
+/* launch the group being filled although it is not full (the caller cannot send more) */
+static int enc_kick(ffgpu_encoder *e)
+{
+    if (e->dev_ready) {
+        EncJob *j = &e->jobs[e->fill];
+        if (j->state == JOB_FILLING && j->n > 0) {
+            int r;
+            cudaSetDevice(e->opt.device);
+            if ((r = enc_launch(e, j)) < 0)
+                return r;
+            e->fill = (e->fill + 1) % e->depth;
+        }
+    }
+    return 0;
+}
+
+static int enc_receive(ffgpu_encoder *e, uint8_t *pkt, size_t cap, size_t *size, int *key_frame,
+                       int64_t *pts, int block);
+
+/* ---- routing over several GPUs ---- */
+static ffgpu_encoder *menc_owner(ffgpu_encoder *p, uint64_t k)
+{
+    return p->sub[(k / (uint64_t)p->chunk) % (uint64_t)p->nsub];
+}
+
+static int menc_send(ffgpu_encoder *p, const ffgpu_picture *pic)
+{
+    int r;
+    if (!pic) {
+        for (int i = 0; i < p->nsub; i++)
+            if ((r = ffgpu_ffv1_encode_send_frame(p->sub[i], NULL)) < 0)
+                return r;
+        p->flushing = 1;
+        return 0;
+    }
+    if (p->flushing)
+        return fail(FFGPU_EOF, "send_frame after flush");
+    r = ffgpu_ffv1_encode_send_frame(menc_owner(p, p->in_count), pic);
+    if (r == 0)
+        p->in_count++;
+    else if (r == FFGPU_EAGAIN)
+        p->send_blocked = 1;
+    return r;
+}
+
+static int menc_receive(ffgpu_encoder *p, uint8_t *pkt, size_t cap, size_t *size, int *key_frame, int64_t *pts)
+{
+    ffgpu_encoder *s;
+    int r;
+    if (p->out_count == p->in_count) {
+        if (!p->flushing)
+            return FFGPU_EAGAIN;
+        for (int i = 0; i < p->nsub; i++)          /* every sub-encoder ends its own flush */
+            enc_receive(p->sub[i], pkt, cap, size, key_frame, pts, 0);
+        p->flushing = 0;
+        return FFGPU_EOF;
+    }
+    s = menc_owner(p, p->out_count);
+    r = enc_receive(s, pkt, cap, size, key_frame, pts, 0);
+    if (r == FFGPU_EAGAIN && (p->send_blocked || p->flushing)) {
+        /* the caller cannot send (another GPU's queue is full) and the packet that is due
+         * sits in a group that waits for more pictures: launch it and wait */
+        if ((r = enc_kick(s)) < 0)
+            return r;
+        r = enc_receive(s, pkt, cap, size, key_frame, pts, 1);
+    }
+    if (r == 0 && pkt) {
+        p->out_count++;
+        p->send_blocked = 0;
+    }
+    return r;
+}
+
 extern "C" int ffgpu_ffv1_encode_send_frame(ffgpu_encoder *e, const ffgpu_picture *pic)
 {
+    if (e && e->nsub)
+        return menc_send(e, pic);
     if (e)
         cudaSetDevice(e->opt.device);        /* the current device is per host thread */
     EncJob *j;
@@ -655,8 +937,20 @@ extern "C" int ffgpu_ffv1_encode_send_frame(ffgpu_encoder *e, const ffgpu_pictur
     }
     if (j->n == 0)
         trace_mark(e->up_stream, "enc h2d", (int)(j - e->jobs), 0);
-    if ((r = upload_picture(&e->P, e->s.pf, e->s.width, e->s.height, pic,
-                            j->d_frames + (size_t)j->n * e->P.frame_bytes, e->up_stream)) < 0)
+    if (mem_kind(pic->data[0]) == MEM_PAGEABLE) {
+        /* an ordinary AVFrame: host memcpy into pinned staging, one linear DMA from there */
+        uint8_t *data[4], *st;
+        if (!j->h_stage)
+            CK(cudaHostAlloc(&j->h_stage, (size_t)e->max_batch * e->P.frame_bytes, cudaHostAllocDefault));
+        st = j->h_stage + (size_t)j->n * e->P.frame_bytes;
+        for (int k = 0; k < 4; k++)
+            data[k] = (uint8_t *)pic->data[k];
+        if ((r = stage_picture(&e->P, e->s.pf, e->s.width, e->s.height, data, pic->linesize, st, 1)) < 0)
+            return r;
+        CK(cudaMemcpyAsync(j->d_frames + (size_t)j->n * e->P.frame_bytes, st, e->P.frame_bytes,
+                           cudaMemcpyHostToDevice, e->up_stream));
+    } else if ((r = upload_picture(&e->P, e->s.pf, e->s.width, e->s.height, pic,
+                                   j->d_frames + (size_t)j->n * e->P.frame_bytes, e->up_stream)) < 0)
         return r;
     j->h_frame_set[j->n] = (uint8_t)set;
     j->h_frame_key[j->n] = (uint8_t)key;
@@ -674,6 +968,22 @@ extern "C" int ffgpu_ffv1_encode_send_frame(ffgpu_encoder *e, const ffgpu_pictur
 
 extern "C" int ffgpu_ffv1_encode_receive_packet(ffgpu_encoder *e, uint8_t *pkt, size_t cap,
                                                 size_t *size, int *key_frame, int64_t *pts)
+{
+    if (e && e->nsub)
+        return menc_receive(e, pkt, cap, size, key_frame, pts);
+    return enc_receive(e, pkt, cap, size, key_frame, pts, 0);
+}
+
+extern "C" int ffgpu_ffv1_encode_packet_ready(ffgpu_encoder *e, size_t *size)
+{
+    if (e && e->nsub)
+        return menc_receive(e, NULL, 0, size, NULL, NULL);
+    return enc_receive(e, NULL, 0, size, NULL, NULL, 0);
+}
+
+/* block != 0: wait for the oldest running group instead of returning FFGPU_EAGAIN */
+static int enc_receive(ffgpu_encoder *e, uint8_t *pkt, size_t cap, size_t *size, int *key_frame,
+                       int64_t *pts, int block)
 {
     if (e)
         cudaSetDevice(e->opt.device);        /* the current device is per host thread */
@@ -699,7 +1009,7 @@ extern "C" int ffgpu_ffv1_encode_receive_packet(ffgpu_encoder *e, uint8_t *pkt, 
     if (j->state == JOB_RUNNING) {
         /* block only if the caller cannot make progress otherwise */
         const EncJob *f = &e->jobs[e->fill];
-        const int must_wait = e->flushing || f->state == JOB_RUNNING || f->state == JOB_DRAINING;
+        const int must_wait = block || e->flushing || f->state == JOB_RUNNING || f->state == JOB_DRAINING;
         if (!must_wait && cudaEventQuery(j->done) == cudaErrorNotReady)
             return FFGPU_EAGAIN;
         if ((r = enc_fetch(e, j)) < 0) {
@@ -709,6 +1019,10 @@ extern "C" int ffgpu_ffv1_encode_receive_packet(ffgpu_encoder *e, uint8_t *pkt, 
         }
     }
     i = j->drained;
+    if (!pkt) {                                    /* peek: size of the packet that is due */
+        if (size) *size = j->h_pkt_size[i];
+        return 0;
+    }
     if (j->h_pkt_size[i] > cap)
         return fail(FFGPU_ENOSPC, "packet buffer too small: need %u bytes", j->h_pkt_size[i]);
     memcpy(pkt, j->h_pkt + ((size_t)j->h_pkt_off[i] << 4), j->h_pkt_size[i]);
@@ -730,6 +1044,16 @@ extern "C" int ffgpu_ffv1_encode_frame(ffgpu_encoder *e, const ffgpu_picture *pi
     int r;
     if (!e || !pic)
         return fail(FFGPU_EINVAL, "null argument");
+    if (e->nsub) {
+        if (e->in_count != e->out_count)
+            return fail(FFGPU_EINVAL, "encode_frame while send/receive pictures are pending");
+        r = ffgpu_ffv1_encode_frame(menc_owner(e, e->in_count), pic, pkt, cap, size, key_frame);
+        if (r >= 0) {
+            e->in_count++;
+            e->out_count++;
+        }
+        return r;
+    }
     if ((r = enc_device_init(e)) < 0)
         return r;
     for (int i = 0; i < e->depth; i++)
@@ -765,6 +1089,8 @@ extern "C" int ffgpu_ffv1_encode_device(ffgpu_encoder *e, const void *d_frames, 
     int r, set;
     if (!e || !d_frames || nframes <= 0)
         return fail(FFGPU_EINVAL, "bad argument");
+    if (e->nsub)
+        return fail(FFGPU_EINVAL, "device-resident batches live on one GPU: open one handle per device");
     if ((r = enc_device_init(e)) < 0)
         return r;
     if (nframes > e->max_batch)
@@ -852,6 +1178,37 @@ extern "C" int ffgpu_ffv1_encode_device_fetch(ffgpu_encoder *e, int frame, uint8
     return 0;
 }
 
+extern "C" int ffgpu_ffv1_encoder_decisions(ffgpu_encoder *e, uint64_t *total, uint32_t *heaviest)
+{
+    EncJob *j;
+    uint32_t *w;
+    size_t n;
+    uint64_t sum = 0;
+    uint32_t mx = 0;
+    if (!e || !e->dev_ready)
+        return fail(FFGPU_EINVAL, "no device batch");
+    cudaSetDevice(e->opt.device);
+    j = &e->jobs[0];
+    n = (size_t)j->n * e->P.nslices;
+    CK(cudaEventSynchronize(j->done));
+    w = (uint32_t *)malloc(n * sizeof(uint32_t) + 4);
+    if (!w)
+        return fail(FFGPU_ENOMEM, "out of memory");
+    if (cudaMemcpy(w, j->d_weight, n * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        free(w);
+        return fail(FFGPU_EXTERNAL, "CUDA: copy of the decision counts failed");
+    }
+    for (size_t i = 0; i < n && e->P.ac != FF_AC_GOLOMB; i++) {
+        sum += w[i];
+        if (w[i] > mx)
+            mx = w[i];
+    }
+    free(w);
+    if (total) *total = sum;
+    if (heaviest) *heaviest = mx;
+    return 0;
+}
+
 /* profiling of the device-batch path: per-kernel CUDA-event times of the last group */
 extern "C" int ffgpu_ffv1_encoder_profile(ffgpu_encoder *e, int enable)
 {
@@ -883,6 +1240,8 @@ extern "C" int ffgpu_ffv1_encode_close(ffgpu_encoder *e)
 {
     if (!e)
         return 0;
+    for (int i = 0; i < e->nsub; i++)
+        ffgpu_ffv1_encode_close(e->sub[i]);
     if (e->dev_ready) {
         cudaSetDevice(e->opt.device);
         cudaDeviceSynchronize();
@@ -911,6 +1270,7 @@ struct DecFrameMeta {
     int64_t pts;
     int nslices;
     int has_dst;
+    int staged;                 /* dst is pageable memory: the picture comes through h_stage */
     ffgpu_picture_out dst;
     uint8_t damaged[FF_MAX_SLICES];
     FFSliceRect rect[FF_MAX_SLICES];
@@ -930,7 +1290,9 @@ struct DecJob {
     int32_t *d_lines;
     int32_t *d_wide_lines;      /* picture-wide scratch pool for slices wider than their grid cell */
     uint32_t *d_wide_used;
+    uint32_t *d_touched;        /* lazily created states: one bit per (work item, context) */
     uint8_t *d_frames;
+    uint8_t *h_stage;           /* pinned staging for destinations in pageable memory (lazily) */
     FFDecResult *d_result, *h_result;
     uint32_t *d_weight, *d_weight_sorted, *d_order;
     void *d_sort_tmp;
@@ -947,6 +1309,9 @@ struct ffgpu_decoder {
     int have_params;
     int intra;
     int max_batch, depth, max_slices, max_ctx, line_stride;
+    int lazy_states;            /* state rows are created on first touch (see FFDecDev.touched) */
+    int generic;
+    int any_five;
     int dev_ready;
     int16_t *d_qt;
     FFRacTables *d_tab;
@@ -962,14 +1327,18 @@ struct ffgpu_decoder {
     uint64_t launches;
     int profile, profile_next;
     void *events[FFK_DEC_KERNELS + 1];
+    /* more than one GPU (intra-only streams): packet k is decoded by sub[k % nsub] */
+    int nsub, send_blocked;
+    ffgpu_decoder *sub[FFGPU_MAX_DEVICES];
+    uint64_t in_count, out_count;
 };
 
 static void dec_free_job(DecJob *j)
 {
     cudaFreeHost(j->h_pkt); cudaFree(j->d_pkt); cudaFreeHost(j->h_work); cudaFree(j->d_work);
     cudaFreeHost(j->h_nslices); cudaFree(j->d_nslices); cudaFree(j->d_state); cudaFree(j->d_lines);
-    cudaFree(j->d_wide_lines); cudaFree(j->d_wide_used);
-    cudaFree(j->d_frames); cudaFree(j->d_result); cudaFreeHost(j->h_result);
+    cudaFree(j->d_wide_lines); cudaFree(j->d_wide_used); cudaFree(j->d_touched);
+    cudaFree(j->d_frames); cudaFree(j->d_result); cudaFreeHost(j->h_result); cudaFreeHost(j->h_stage);
     cudaFree(j->d_weight); cudaFree(j->d_weight_sorted); cudaFree(j->d_order); cudaFree(j->d_sort_tmp);
     free(j->meta);
     if (j->done) cudaEventDestroy(j->done);
@@ -1101,6 +1470,16 @@ static int dec_device_init(ffgpu_decoder *d)
     }
     if (!d->intra)
         CK(cudaMalloc(&d->d_state_shared, state_frame));
+    /* every frame a key frame, all states start at 128, and the stream runs through the
+     * specialised planar decoder: no arena fill, rows are created on first touch */
+    d->generic = getenv("FFGPU_DEC_GENERIC") != NULL;      /* development: A/B against the generic decoder */
+    d->lazy_states = d->intra && !any_initial && !d->generic && ff_decode_planar_mode(P) != 0;
+    /* 5-input contexts: only tables the arena was sized for can be named by a slice header
+     * (-context 0 streams carry the large 5-input table too, but never use it) */
+    d->any_five = 0;
+    for (int i = 0; i < d->s.qt_count; i++)
+        if (d->s.ctx_count[i] <= d->max_ctx)
+            d->any_five |= d->s.qt[i][3][127] || d->s.qt[i][4][127];
     CK(cudaMalloc(&d->d_prev, P->frame_bytes));
     CK(cudaMemset(d->d_prev, 0, P->frame_bytes));
     CK(cudaEventCreateWithFlags(&d->prev_ready, cudaEventDisableTiming));
@@ -1135,6 +1514,8 @@ static int dec_device_init(ffgpu_decoder *d)
         CK(cudaMalloc(&j->d_nslices, B * sizeof(int)));
         if (d->intra)
             CK(cudaMalloc(&j->d_state, B * state_frame));
+        if (d->lazy_states)
+            CK(cudaMalloc(&j->d_touched, B * d->max_slices * (size_t)((P->total_ctx + 31) / 32) * sizeof(uint32_t)));
         CK(cudaMalloc(&j->d_lines, B * d->max_slices * P->ncoded * 2 * d->line_stride * sizeof(int32_t)));
         if (d->line_stride < d->s.width + 8) {
             CK(cudaMalloc(&j->d_wide_lines, (size_t)DEC_WIDE_POOL * P->ncoded * 2 * (d->s.width + 8) * sizeof(int32_t)));
@@ -1190,6 +1571,25 @@ extern "C" int ffgpu_ffv1_decode_init(ffgpu_decoder **pdec, const ffgpu_dec_opti
         }
     }
     d->hs.max_slices = d->s.nh * d->s.nv;
+    if (opt->ndevices > 1) {
+        if (opt->ndevices > FFGPU_MAX_DEVICES) {
+            ffgpu_ffv1_decode_close(d);
+            return fail(FFGPU_EINVAL, "ndevices %d exceeds %d", opt->ndevices, FFGPU_MAX_DEVICES);
+        }
+        d->opt.device = opt->devices[0];
+        if (d->have_params && d->intra) {
+            ffgpu_dec_options so = *opt;
+            so.ndevices = 0;
+            for (int i = 0; i < opt->ndevices; i++) {
+                so.device = opt->devices[i];
+                if ((r = ffgpu_ffv1_decode_init(&d->sub[i], &so)) < 0) {
+                    ffgpu_ffv1_decode_close(d);
+                    return r;
+                }
+                d->nsub = i + 1;
+            }
+        }
+    }
     *pdec = d;
     return 0;
 }
@@ -1228,7 +1628,13 @@ extern "C" void ffgpu_ffv1_decoder_info(const ffgpu_decoder *d, int info[8])
     info[4] = d->s.nv; info[5] = d->s.ec; info[6] = d->s.bits; info[7] = d->s.colorspace;
 }
 
-extern "C" uint64_t ffgpu_ffv1_decoder_launches(const ffgpu_decoder *d) { return d->launches; }
+extern "C" uint64_t ffgpu_ffv1_decoder_launches(const ffgpu_decoder *d)
+{
+    uint64_t n = d->launches;
+    for (int i = 0; i < d->nsub; i++)
+        n += d->sub[i]->launches;
+    return n;
+}
 
 static void dec_fill_dev(const ffgpu_decoder *d, const DecJob *j, uint8_t *frames, FFDecDev *D)
 {
@@ -1253,6 +1659,11 @@ static void dec_fill_dev(const ffgpu_decoder *d, const DecJob *j, uint8_t *frame
     D->state_per_frame = d->intra;
     D->qt_count = d->s.qt_count;
     D->gate_wait = getenv("FFGPU_GATE_WAIT") ? atoi(getenv("FFGPU_GATE_WAIT")) : FF_NEW_WAIT;
+    D->touched = j->d_touched;
+    D->touched_words = (d->P.total_ctx + 31) / 32;
+    D->any_five = d->any_five;
+    D->generic = d->generic;
+    D->lane_stride = 1;                            /* set per launch from the number of work items */
     D->hdr.micro_version = d->s.micro_version;
     D->hdr.qt_count = d->s.qt_count;
     D->hdr.ctx_cap = d->max_ctx;
@@ -1280,6 +1691,7 @@ static int dec_launch(ffgpu_decoder *d, DecJob *j, uint8_t *frames, cudaStream_t
     FFDecDev D;
     int r;
     dec_fill_dev(d, j, frames, &D);
+    D.lane_stride = coder_lane_stride((long)j->n * d->max_slices);
     if (d->profile_next)
         D.events = d->events;
     {
@@ -1314,11 +1726,21 @@ static int dec_launch(ffgpu_decoder *d, DecJob *j, uint8_t *frames, cudaStream_t
     if (download) {
         CK(cudaEventRecord(j->decoded, st));
         CK(cudaStreamWaitEvent(d->down_stream, j->decoded, 0));
-        for (int i = 0; i < j->n; i++)
-            if (j->meta[i].has_dst &&
-                (r = download_picture(d, j->d_frames + (size_t)i * d->P.frame_bytes, &j->meta[i].dst,
-                                      d->down_stream)) < 0)
+        for (int i = 0; i < j->n; i++) {
+            if (!j->meta[i].has_dst)
+                continue;
+            if (j->meta[i].staged) {
+                /* an ordinary AVFrame: one linear DMA into pinned staging now, the host
+                 * memcpy into the frame when the picture is handed back */
+                if (!j->h_stage)
+                    CK(cudaHostAlloc(&j->h_stage, (size_t)d->max_batch * d->P.frame_bytes, cudaHostAllocDefault));
+                CK(cudaMemcpyAsync(j->h_stage + (size_t)i * d->P.frame_bytes,
+                                   j->d_frames + (size_t)i * d->P.frame_bytes, d->P.frame_bytes,
+                                   cudaMemcpyDeviceToHost, d->down_stream));
+            } else if ((r = download_picture(d, j->d_frames + (size_t)i * d->P.frame_bytes, &j->meta[i].dst,
+                                             d->down_stream)) < 0)
                 return r;
+        }
     }
     return 0;
 }
@@ -1362,6 +1784,7 @@ static int dec_add_packet(ffgpu_decoder *d, DecJob *j, const uint8_t *pkt, size_
     if (dst) {
         m->dst = *dst;
         m->has_dst = 1;
+        m->staged = mem_kind(dst->data[0]) == MEM_PAGEABLE;
     }
     j->h_nslices[j->n] = n;
     j->pkt_used = off + size;
@@ -1423,10 +1846,17 @@ static int dec_finish_frame(ffgpu_decoder *d, DecJob *j, int i, ffgpu_picture_ou
                     return fail(r, "conceal launch failed");
                 d->launches += r;
             }
-        if (m->has_dst && (r = download_picture(d, frame, &m->dst, j->stream)) < 0)
+        if (m->has_dst && m->staged)
+            CK(cudaMemcpyAsync(j->h_stage + (size_t)i * P->frame_bytes, frame, P->frame_bytes,
+                               cudaMemcpyDeviceToHost, j->stream));
+        else if (m->has_dst && (r = download_picture(d, frame, &m->dst, j->stream)) < 0)
             return r;
         CK(cudaStreamSynchronize(j->stream));
     }
+    if (m->has_dst && m->staged &&
+        (r = stage_picture(P, d->s.pf, d->s.width, d->s.height, m->dst.data, m->dst.linesize,
+                           j->h_stage + (size_t)i * P->frame_bytes, 0)) < 0)
+        return r;
     if (i == j->n - 1) {
         /* keep the last picture of the group for the next group's concealment; the copy is
          * only awaited by the (rare) concealment path itself */
@@ -1460,9 +1890,76 @@ static int dec_launch_group(ffgpu_decoder *d, DecJob *j)
     return 0;
 }
 
+static int dec_receive(ffgpu_decoder *d, ffgpu_picture_out *out, int block);
+
+/* launch the group being filled although it is not full (the caller cannot send more) */
+static int dec_kick(ffgpu_decoder *d)
+{
+    if (d->dev_ready) {
+        DecJob *j = &d->jobs[d->fill];
+        if (j->state == JOB_FILLING && j->n > 0) {
+            int r;
+            cudaSetDevice(d->opt.device);
+            if ((r = dec_launch_group(d, j)) < 0)
+                return r;
+            d->fill = (d->fill + 1) % d->depth;
+        }
+    }
+    return 0;
+}
+
+/* ---- routing over several GPUs ---- */
+static int mdec_send(ffgpu_decoder *p, const uint8_t *pkt, size_t size, int64_t pts, const ffgpu_picture_out *dst)
+{
+    int r;
+    if (!pkt) {
+        for (int i = 0; i < p->nsub; i++)
+            if ((r = ffgpu_ffv1_decode_send_packet(p->sub[i], NULL, 0, 0, NULL)) < 0)
+                return r;
+        p->flushing = 1;
+        return 0;
+    }
+    if (p->flushing)
+        return fail(FFGPU_EOF, "send_packet after flush");
+    r = ffgpu_ffv1_decode_send_packet(p->sub[p->in_count % (uint64_t)p->nsub], pkt, size, pts, dst);
+    if (r == 0)
+        p->in_count++;
+    else if (r == FFGPU_EAGAIN)
+        p->send_blocked = 1;
+    return r;
+}
+
+static int mdec_receive(ffgpu_decoder *p, ffgpu_picture_out *out)
+{
+    ffgpu_decoder *s;
+    int r;
+    if (p->out_count == p->in_count) {
+        if (!p->flushing)
+            return FFGPU_EAGAIN;
+        for (int i = 0; i < p->nsub; i++)
+            dec_receive(p->sub[i], out, 0);        /* every sub-decoder ends its own flush */
+        p->flushing = 0;
+        return FFGPU_EOF;
+    }
+    s = p->sub[p->out_count % (uint64_t)p->nsub];
+    r = dec_receive(s, out, 0);
+    if (r == FFGPU_EAGAIN && (p->send_blocked || p->flushing)) {
+        if ((r = dec_kick(s)) < 0)
+            return r;
+        r = dec_receive(s, out, 1);
+    }
+    if (r == 0) {
+        p->out_count++;
+        p->send_blocked = 0;
+    }
+    return r;
+}
+
 extern "C" int ffgpu_ffv1_decode_send_packet(ffgpu_decoder *d, const uint8_t *pkt, size_t size,
                                               int64_t pts, const ffgpu_picture_out *dst)
 {
+    if (d && d->nsub)
+        return mdec_send(d, pkt, size, pts, dst);
     if (d)
         cudaSetDevice(d->opt.device);        /* the current device is per host thread */
     DecJob *j;
@@ -1536,6 +2033,14 @@ extern "C" int ffgpu_ffv1_decode_send_packet(ffgpu_decoder *d, const uint8_t *pk
 
 extern "C" int ffgpu_ffv1_decode_receive_frame(ffgpu_decoder *d, ffgpu_picture_out *out)
 {
+    if (d && d->nsub)
+        return mdec_receive(d, out);
+    return dec_receive(d, out, 0);
+}
+
+/* block != 0: wait for the oldest running group instead of returning FFGPU_EAGAIN */
+static int dec_receive(ffgpu_decoder *d, ffgpu_picture_out *out, int block)
+{
     if (d)
         cudaSetDevice(d->opt.device);        /* the current device is per host thread */
     DecJob *j;
@@ -1559,7 +2064,7 @@ extern "C" int ffgpu_ffv1_decode_receive_frame(ffgpu_decoder *d, ffgpu_picture_o
     }
     if (j->state == JOB_RUNNING) {
         const DecJob *f = &d->jobs[d->fill];
-        const int must_wait = d->flushing || f->state == JOB_RUNNING || f->state == JOB_DRAINING;
+        const int must_wait = block || d->flushing || f->state == JOB_RUNNING || f->state == JOB_DRAINING;
         if (!must_wait && cudaEventQuery(j->done) == cudaErrorNotReady)
             return FFGPU_EAGAIN;
         CK(cudaEventSynchronize(j->done));
@@ -1595,6 +2100,16 @@ extern "C" int ffgpu_ffv1_decode_frame(ffgpu_decoder *d, const uint8_t *pkt, siz
         *got_frame = 0;
     if (!d || !pkt || !out)
         return fail(FFGPU_EINVAL, "null argument");
+    if (d->nsub) {
+        if (d->in_count != d->out_count)
+            return fail(FFGPU_EINVAL, "decode_frame while send/receive packets are pending");
+        r = ffgpu_ffv1_decode_frame(d->sub[d->in_count % (uint64_t)d->nsub], pkt, size, out, got_frame);
+        if (r >= 0) {
+            d->in_count++;
+            d->out_count++;
+        }
+        return r;
+    }
     if (d->dev_ready)
         for (int i = 0; i < d->depth; i++)
             if (d->jobs[i].state != JOB_FREE)
@@ -1628,6 +2143,8 @@ extern "C" int ffgpu_ffv1_decode_device(ffgpu_decoder *d, const uint8_t *const *
     int r;
     if (!d || !pkts || !sizes || nframes <= 0 || !d_frames)
         return fail(FFGPU_EINVAL, "bad argument");
+    if (d->nsub)
+        return fail(FFGPU_EINVAL, "device-resident batches live on one GPU: open one handle per device");
     if (d->dev_ready)
         for (int i = 0; i < d->depth; i++)
             if (d->jobs[i].state != JOB_FREE)
@@ -1725,6 +2242,8 @@ extern "C" int ffgpu_ffv1_decode_close(ffgpu_decoder *d)
 {
     if (!d)
         return 0;
+    for (int i = 0; i < d->nsub; i++)
+        ffgpu_ffv1_decode_close(d->sub[i]);
     for (int i = 0; i <= FFK_DEC_KERNELS; i++)
         if (d->events[i])
             cudaEventDestroy((cudaEvent_t)d->events[i]);

@@ -490,7 +490,16 @@ __global__ void k_dec_fill_state(uint4 *__restrict__ state, size_t vec_per_frame
         p[i] = pattern;
 }
 
-__global__ void __launch_bounds__(CODE_THREADS, 1)
+/* SMODE 0: every stream (Golomb-Rice, RGB, MSB-aligned containers) through the generic slice
+ * functions; SMODE 1 / 2: range-coded planar YCbCr / gray, 8-bit / LSB-packed 16-bit samples,
+ * through ff_decode_slice_range_planar.  D.lane_stride > 1 spreads the work items over the
+ * warps (one slice per `lane_stride` lanes): streams with a handful of large slices then run
+ * one slice per warp, without the cost of 32 unrelated slices diverging in one warp. */
+#ifndef FF_DEC_MINBLOCKS
+#define FF_DEC_MINBLOCKS 1
+#endif
+template <int SMODE, bool FIVE>
+__global__ void __launch_bounds__(CODE_THREADS, FF_DEC_MINBLOCKS)
 k_decode(const FFDevParams P, const FFDecDev D, int nframes)
 {
     for (int i = threadIdx.x; i < (int)sizeof(FFRacTables) / 4; i += CODE_THREADS)
@@ -501,16 +510,28 @@ k_decode(const FFDevParams P, const FFDecDev D, int nframes)
     for (int i = threadIdx.x; i < 256; i += CODE_THREADS)
         s_crc[i] = ff_crc_table_entry(i);
     __syncthreads();
-    const int tid = blockIdx.x * CODE_THREADS + threadIdx.x;
-    if (tid >= nframes * D.max_slices)
+    /* the planar path keeps every lane of a warp inside the decode loop (lanes without a
+     * slice idle there), so nothing returns before the call */
+    int tid = blockIdx.x * CODE_THREADS + threadIdx.x;
+    bool have = true;
+    if (D.lane_stride > 1) {
+        have = tid % D.lane_stride == 0;
+        tid /= D.lane_stride;
+    }
+    have = have && tid < nframes * D.max_slices;
+    if (SMODE == 0 && !have)
         return;
-    const int gid = D.order ? (int)D.order[tid] : tid;       /* largest slices first */
+    const int gid = have ? (D.order ? (int)D.order[tid] : tid) : 0;   /* largest slices first */
     const int f = gid / D.max_slices, s = gid - f * D.max_slices;
     FFDecResult r;
+    FFDecSlice w;
+    FFDecCtx C;
+    bool live = false;
     r.end_pos = 0; r.overread = 0; r.error = 0; r.flags = FF_RES_NOT_DECODED;
     r.x = r.y = r.w = r.h = 0; r.size = 0; r.pad[0] = r.pad[1] = r.pad[2] = 0;
-    if (s < D.nslices[f]) {
-        FFDecSlice w = D.work[gid];
+    C.lines = 0;
+    if (have && s < D.nslices[f]) {
+        w = D.work[gid];
         r.x = w.x; r.y = w.y; r.w = w.w; r.h = w.h;
         if (w.parse && !w.skip) {
             ff_dec_slice_header(P, D.hdr, &w, D.pkt, &ff_s_tab, s_crc, &r);
@@ -520,7 +541,6 @@ k_decode(const FFDevParams P, const FFDecDev D, int nframes)
         if (!w.skip) {
             r.flags &= ~FF_RES_NOT_DECODED;
             const size_t slot = (size_t)(D.state_per_frame ? f : 0) * D.max_slices + s;
-            FFDecCtx C;
             C.qt_all = D.qt;
             C.tab = &ff_s_tab;
             C.rstate = D.state + slot * P.total_ctx * FF_CONTEXT_SIZE;
@@ -529,6 +549,8 @@ k_decode(const FFDevParams P, const FFDecDev D, int nframes)
             C.line_stride = D.line_stride;
             C.frame = D.frames + (size_t)f * P.frame_bytes;
             C.gate_wait = D.gate_wait;
+            C.touched = D.touched ? D.touched + (size_t)gid * D.touched_words : (uint32_t *)0;
+            C.any_five = D.any_five;
             if (w.w + 8 > D.line_stride) {
                 /* rectangle wider than the grid cell: picture-wide scratch from the pool */
                 const uint32_t slot_w = D.wide_used ? atomicAdd(D.wide_used, 1u) : 0xFFFFFFFFu;
@@ -540,11 +562,18 @@ k_decode(const FFDevParams P, const FFDecDev D, int nframes)
                     r.flags |= FF_RES_HDR_BAD | FF_RES_NOT_DECODED;
                 }
             }
-            if (C.lines)
-                ff_decode_slice(P, w, D.pkt, C, &r, 0);
+            live = C.lines != 0;
         }
     }
-    D.result[gid] = r;
+    if (SMODE == 0) {
+        if (live)
+            ff_decode_slice(P, w, D.pkt, C, &r, 0);
+    } else {
+        __syncwarp();
+        ff_decode_slice_range_planar<SMODE ? SMODE : 1, FIVE>(P, w, D.pkt, C, &r, 0, live);
+    }
+    if (have)
+        D.result[gid] = r;
 }
 
 extern "C" size_t ffk_sort_tmp_bytes(int n)
@@ -561,8 +590,12 @@ extern "C" int ffk_decode_group(const FFDevParams *P, const FFDecDev *D, int nfr
     if (nframes <= 0)
         return FFGPU_EINVAL;
     dim3 g0(D->max_slices, nframes);
+    const int total = nframes * D->max_slices;
     mark(D->events, 0, st);
-    if (!D->initial &&
+    if (D->touched) {
+        /* states are created on first touch inside k_decode: clear the touched bits only */
+        cudaMemsetAsync(D->touched, 0, (size_t)total * D->touched_words * sizeof(uint32_t), st);
+    } else if (!D->initial &&
         ((size_t)D->max_slices * P->total_ctx * (P->ac == FF_AC_GOLOMB ? 8 : FF_CONTEXT_SIZE)) % 16 == 0) {
         const int golomb = P->ac == FF_AC_GOLOMB;
         const size_t vec = (size_t)D->max_slices * P->total_ctx * (golomb ? 8 : FF_CONTEXT_SIZE) / 16;
@@ -578,7 +611,6 @@ extern "C" int ffk_decode_group(const FFDevParams *P, const FFDecDev *D, int nfr
     mark(D->events, FFK_DEC_INIT_STATE + 1, st);
     if (D->wide_used)
         cudaMemsetAsync(D->wide_used, 0, sizeof(uint32_t), st);
-    const int total = nframes * D->max_slices;
     if (D->weight && D->order) {
         size_t tmp = D->sort_tmp_bytes;
         k_dec_keys<<<(total + 255) / 256, 256, 0, st>>>(*D, nframes);
@@ -586,8 +618,22 @@ extern "C" int ffk_decode_group(const FFDevParams *P, const FFDecDev *D, int nfr
                                                   D->order, total, 0, 32, st);
     }
     mark(D->events, FFK_DEC_SORT + 1, st);
-    k_decode<<<(total + CODE_THREADS - 1) / CODE_THREADS, CODE_THREADS,
-               (size_t)D->qt_count * FF_QT_STRIDE * sizeof(int16_t), st>>>(*P, *D, nframes);
+    {
+        const int stride = D->lane_stride > 1 ? D->lane_stride : 1;
+        const long threads = (long)total * stride;
+        const unsigned blocks = (unsigned)((threads + CODE_THREADS - 1) / CODE_THREADS);
+        const size_t smem = (size_t)D->qt_count * FF_QT_STRIDE * sizeof(int16_t);
+        const int planar = D->generic ? 0 : ff_decode_planar_mode(P);
+#define DEC_LAUNCH(M, F) k_decode<M, F><<<blocks, CODE_THREADS, smem, st>>>(*P, *D, nframes)
+        if (planar == 1) {
+            if (D->any_five) DEC_LAUNCH(1, true); else DEC_LAUNCH(1, false);
+        } else if (planar == 2) {
+            if (D->any_five) DEC_LAUNCH(2, true); else DEC_LAUNCH(2, false);
+        } else {
+            DEC_LAUNCH(0, false);
+        }
+#undef DEC_LAUNCH
+    }
     mark(D->events, FFK_DECODE + 1, st);
     if (!launch_ok()) return FFGPU_EXTERNAL;
     return 3;

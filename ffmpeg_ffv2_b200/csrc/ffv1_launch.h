@@ -83,6 +83,13 @@ typedef struct FFDecDev {
     int qt_count;                   /* quant table sets of the stream                   */
     FFDecHdr hdr;                   /* constants for device-side slice header parsing   */
     int gate_wait;                  /* sample set-up gating of the decode loop          */
+    /* lazily created adaptive states (intra-only streams without initial-state tables):
+     * one bit per (work item, context), zeroed per launch instead of filling the state arena */
+    uint32_t *touched;              /* [nframes*max_slices][touched_words] or NULL      */
+    int touched_words;
+    int any_five;                   /* some quant table uses 5 context inputs           */
+    int lane_stride;                /* 1: every lane decodes a slice; 32: one slice per warp */
+    int generic;                    /* 1: use the generic slice decoder even where the planar one applies */
     uint32_t *weight;               /* [nframes*max_slices] slice byte counts            */
     uint32_t *weight_sorted;
     const uint32_t *iota;

@@ -14,8 +14,10 @@
 
 #if defined(__CUDACC__)
 #define FFGPU_HD __host__ __device__ __forceinline__
+#define FFGPU_HD_COLD static __host__ __device__ __noinline__   /* once per slice: keep it out of line */
 #else
 #define FFGPU_HD static inline
+#define FFGPU_HD_COLD static inline
 #endif
 
 /* adaptive-probability transition tables: one_state / zero_state (256 B each) */

@@ -332,6 +332,12 @@ __device__ __forceinline__ uint32_t ff_opaque(uint32_t v)
 {
     return __shfl_sync(__activemask(), v, (int)(threadIdx.x & 31));
 }
+__device__ __forceinline__ int ff_lds16s(uint32_t sa)
+{
+    int v;
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(sa));
+    return v;
+}
 __device__ __forceinline__ void ff_sts8(uint32_t sa, uint32_t v)
 {
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(sa), "r"(v) : "memory");
@@ -788,6 +794,9 @@ typedef struct FFDecCtx {
     int      line_stride;
     uint8_t *frame;             /* output picture                                     */
     int gate_wait;              /* sample set-up gating: longest idle wait, in iterations */
+    uint32_t *touched;          /* one bit per context of the slice: its state row exists.   */
+                                /* NULL: every row was initialised before the slice started  */
+    int any_five;               /* some quant table of the stream uses 5 context inputs      */
 } FFDecCtx;
 
 FFGPU_HD int ff_wrap_sample(const FFDevParams &P, int v)
@@ -943,7 +952,7 @@ FFGPU_HD void ff_store_line_rgb(const FFDevParams &P, uint8_t *frame, int X0, in
 /* ff_init_range_decoder + decode_slice_header (ffv1dec.c:167-244) + the Golomb hand-over
  * (ffv1dec.c:312-319) + the slice CRC check (ffv1dec.c:905-922) for slices the host left to
  * the device.  Fills the coder state / rectangle / quant table indices of the work item. */
-FFGPU_HD void ff_dec_slice_header(const FFDevParams &P, const FFDecHdr &H, FFDecSlice *w,
+FFGPU_HD_COLD void ff_dec_slice_header(const FFDevParams &P, const FFDecHdr &H, FFDecSlice *w,
                                   const uint8_t *pkt, const FFRacTables *tab,
                                   const uint32_t *crc_tab, FFDecResult *res)
 {
@@ -1371,13 +1380,360 @@ FFGPU_HD void ff_decode_slice_golomb(const FFDevParams &P, const FFDecSlice &d, 
 
 }
 
+/* ------------------------------------------------------------------ */
+/* decoder, planar YCbCr / gray, range coder: the specialised hot path   */
+/* ------------------------------------------------------------------ */
+/* Same algorithm and loop shape as ff_decode_slice_range (one binary decision per iteration,
+ * gated per-sample set-up), specialised at compile time for the sample container
+ * (SMODE 1: one byte, 2: little-endian u16 packed at the LSB) and for 3- or 5-input contexts,
+ * and trimmed for instruction count, the quantity that bounds a launch with tens of
+ * thousands of resident slice decoders:
+ *   - every line is described by three byte pointers (previous line, line before that,
+ *     output row) that are set up once per line; the first lines point at a zeroed row, so
+ *     the sample loop has no "is there a line above" selects;
+ *   - subsampled planes keep their private two-line ring (see ff_decode_slice_range) but in
+ *     the picture's own sample container, so one load path serves both cases;
+ *   - the next bitstream byte is fetched right after the previous one was consumed, so the
+ *     renormalisation never waits for a global load;
+ *   - adaptive state rows are created on first touch (D.touched, one bit per context of the
+ *     slice) instead of by a kernel that fills the whole arena: ff_ffv1_clear_slice_state
+ *     (ffv1.c:182-207) without the memset traffic.  Only for streams whose every frame is a
+ *     key frame and that carry no initial-state tables. */
+#if defined(__CUDA_ARCH__)
+#define FF_UNLIKELY(c) __builtin_expect(!!(c), 0)
+#else
+#define FF_UNLIKELY(c) (c)
+#endif
+/* samples of the previous line fetched ahead of their use (2 or 4) */
+#ifndef FF_DEC_AHEAD
+#define FF_DEC_AHEAD 4
+#endif
+template <int SMODE> struct FFPix;
+template <> struct FFPix<1> { typedef uint8_t type; };
+template <> struct FFPix<2> { typedef uint16_t type; };
+
+/* A sample of a previous line, wrapped to the coder's int16.  On the device the load is an
+ * explicit ld.global with the sign extension done by the load unit: written in C the
+ * extension becomes a separate instruction that the compiler schedules right behind the
+ * load, and the warp then waits out the whole memory latency of a value it only needs four
+ * samples later (21 % of all stall samples of the kernel in the first profile). */
+template <int SMODE>
+FFGPU_HD int ff_pix_load(const uint8_t *p)
+{
+#if defined(__CUDA_ARCH__)
+    int v;
+    if (SMODE == 1)
+        asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    else
+        asm volatile("ld.global.s16 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    if (SMODE == 1)
+        return (int)*p;
+    return (int)(int16_t)*(const uint16_t *)p;
+#endif
+}
+
+template <int SMODE, bool FIVE>
+FFGPU_HD void ff_decode_slice_range_planar(const FFDevParams &P, const FFDecSlice &d, const uint8_t *pkt,
+                                           const FFDecCtx &D, FFDecResult *res, uint32_t *row_, int live)
+{
+#if !defined(__CUDA_ARCH__)
+    const FFRacTables *tab_ = D.tab;
+    const int16_t *qt_all_ = D.qt_all;
+#endif
+    typedef typename FFPix<SMODE>::type pix_t;
+    const uint32_t mask = (1u << P.cbits) - 1;
+    const uint8_t *buf = pkt + d.pkt_off;
+    int low = d.low, range = d.range, overread = d.overread;
+    uint32_t pos = d.pos;
+    const uint32_t end = d.size;
+    uint32_t nbyte;                                   /* buf[pos], fetched ahead */
+    FFLineIt it;
+    /* state: 1 the lane needs the next sample set up, 2 it is inside a symbol, 0 its slice is
+     * finished (or it never had one) */
+    unsigned state = 1;
+    int x = -1, w = 0, err = 0, cur_ctx = -1;
+    int five = 0, sign = 0, e = 0, mi = 0, slot = 0;
+    uint32_t a = 0;
+    int T = 0, LT = 0, L = 0, LL = 0, RT = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+    int qo = 0, sbase = 0, step = (int)sizeof(pix_t);
+    (void)q2; (void)q3;
+    /* byte pointers of the current line: previous line, the line before it, output row, and
+     * (subsampled planes) the private copy of the line being decoded */
+    const uint8_t *pl = D.frame, *ppl = D.frame;
+    uint8_t *ol = D.frame, *ll = 0;
+    uint8_t *const scratch = (uint8_t *)D.lines;
+    const size_t lbytes = (size_t)D.line_stride * sizeof(int32_t);    /* one scratch line */
+    (void)row_;
+#if defined(__CUDA_ARCH__)
+    const int gate_wait = D.gate_wait;
+    int waited = 0;
+    uint32_t row_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_rows[threadIdx.x * FF_ROW_WORDS]);
+    uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_tab);
+    uint32_t qt_sa = (uint32_t)__cvta_generic_to_shared(ff_s_qt);
+    row_sa = ff_opaque(row_sa);                      /* see ff_encode_slice_range */
+    tab_sa = ff_opaque(tab_sa);
+    qt_sa = ff_opaque(qt_sa);
+    uint32_t q_sa = qt_sa;                           /* quant table set of the current line */
+#define FF_QTL(i) ff_lds16s(q_sa + 2u * (uint32_t)(i))
+#else
+#define FF_QTL(i) FF_QT(qo, i)
+#endif
+
+    /* zero rows: line 0 of plane 0's scratch is the row "above the slice" of every
+     * full-resolution plane; subsampled planes start from two zeroed private lines */
+    for (int k = 0; k < (live ? P.ncoded : 0); k++) {
+        const int sub = P.cp[k].hs || P.cp[k].vs;
+        if (k && !sub)
+            continue;
+        const int pw = ff_crshift(d.w, P.cp[k].hs);
+        const int nw = (pw * 2 + 3) / 4 + 1;
+        for (int l = 0; l < (sub ? 2 : 1); l++) {
+            uint32_t *z = (uint32_t *)(scratch + ((size_t)k * 2 + l) * lbytes);
+            for (int i = 0; i < nw; i++)
+                z[i] = 0;
+        }
+    }
+    nbyte = live ? buf[pos] : 0;
+    if (!live || !ff_line_first(P, d, &it))
+        state = 0;
+
+    for (;;) {
+        int s, r1, bit, done, diff;
+#if defined(__CUDA_ARCH__)
+        {
+            /* Set-up gating, see ff_decode_slice_range.  Two warp-wide votes tell whether
+             * some lane needs a sample and whether some lane is inside a symbol; lanes whose
+             * slice is finished stay in the loop and vote for neither, so no active mask has
+             * to be tracked and the whole warp leaves together.  While both kinds exist the
+             * lanes that need a sample idle, at most gate_wait iterations.  `waited` is the
+             * same in every lane. */
+            const bool any_need = __any_sync(0xffffffffu, state == 1);
+            const bool any_busy = __any_sync(0xffffffffu, state == 2);
+            if (!any_need && !any_busy)
+                break;
+            const bool hold = any_need && any_busy && waited < gate_wait;
+            waited = hold ? waited + 1 : 0;
+            if (state == 0 || (hold && state == 1))
+                continue;
+        }
+#else
+        if (state == 0)
+            break;
+#endif
+        if (state == 1) {
+            int ctx;
+            if (x < 0 || x == w) {
+                if (x == w && !ff_line_next(P, d, &it)) {
+                    state = 0;
+                    continue;
+                }
+                {
+                    const FFDevPlane cp = P.cp[it.k];
+                    const int sub = cp.hs || cp.vs;
+                    uint8_t *row = D.frame + P.plane_off[cp.mem] +
+                                   (size_t)((d.y >> cp.vs) + it.y) * P.pitch[cp.mem] +
+                                   (size_t)(d.x >> cp.hs) * cp.step + cp.off;
+                    w = it.w;
+                    qo = d.qidx[cp.set] * FF_QT_STRIDE;
+#if defined(__CUDA_ARCH__)
+                    q_sa = qt_sa + 2u * (uint32_t)qo;
+#endif
+                    five = FIVE ? FF_QT(qo, FF_MAX_CTX_INPUTS * 256) : 0;
+                    sbase = P.set_base[cp.set];
+                    ol = row;
+                    /* bytes between samples: 2 only for the interleaved gray+alpha layout,
+                     * whose planes are never subsampled; the zero row is sized for it */
+                    step = SMODE == 1 ? cp.step : 2;
+                    if (sub) {
+                        uint8_t *l0 = scratch + (size_t)it.k * 2 * lbytes;
+                        ll = (it.y & 1) ? l0 + lbytes : l0;
+                        pl = (it.y & 1) ? l0 : l0 + lbytes;
+                        ppl = ll;                     /* still holds line y-2 (or zeros) */
+                    } else {
+                        ll = 0;
+                        pl = it.y >= 1 ? row - P.pitch[cp.mem] : scratch;
+                        ppl = it.y >= 2 ? row - 2 * (size_t)P.pitch[cp.mem] : scratch;
+                    }
+                }
+                x = 0;
+                T = ff_pix_load<SMODE>(pl);
+                LT = ff_pix_load<SMODE>(ppl);
+                L = T;
+                LL = 0;
+                /* look-ahead on the previous line: q0.. = prev[min(x+1.., w-1)] */
+                q0 = ff_pix_load<SMODE>(pl + (size_t)ff_min(1, w - 1) * step);
+                q1 = ff_pix_load<SMODE>(pl + (size_t)ff_min(2, w - 1) * step);
+#if FF_DEC_AHEAD == 4
+                q2 = ff_pix_load<SMODE>(pl + (size_t)ff_min(3, w - 1) * step);
+                q3 = ff_pix_load<SMODE>(pl + (size_t)ff_min(4, w - 1) * step);
+#endif
+                if (overread > 2) {                  /* is_input_end at line start */
+                    err = 1;
+                    state = 0;
+                    continue;
+                }
+            } else if (!(x & 1023) && overread > 2) {
+                err = 1;
+                state = 0;
+                continue;
+            }
+            RT = q0;
+            q0 = q1;
+#if FF_DEC_AHEAD == 4
+            q1 = q2;
+            q2 = q3;
+            q3 = ff_pix_load<SMODE>(pl + (size_t)ff_min(x + 5, w - 1) * step);
+#else
+            q1 = ff_pix_load<SMODE>(pl + (size_t)ff_min(x + 3, w - 1) * step);
+#endif
+            ctx = FF_QTL((L - LT) & 0xFF) + FF_QTL(256 + ((LT - T) & 0xFF)) +
+                  FF_QTL(512 + ((T - RT) & 0xFF));
+            if (FIVE && five) {
+                const int TT = ff_pix_load<SMODE>(ppl + (size_t)x * step);
+                ctx += FF_QTL(768 + ((LL - L) & 0xFF)) + FF_QTL(1024 + ((TT - T) & 0xFF));
+            }
+            sign = ctx < 0;
+            ctx = sbase + (sign ? -ctx : ctx);
+            if (ctx != cur_ctx) {
+                if (cur_ctx >= 0)
+                    ff_row_store(FF_ROWW, D.rstate + (size_t)cur_ctx * FF_CONTEXT_SIZE);
+                if (D.touched) {
+                    const uint32_t tw = D.touched[ctx >> 5], tb = 1u << (ctx & 31);
+                    if (tw & tb) {
+                        ff_row_load(FF_ROWW, D.rstate + (size_t)ctx * FF_CONTEXT_SIZE);
+                    } else {
+                        uint32_t *rw = FF_ROWW;
+                        D.touched[ctx >> 5] = tw | tb;
+                        rw[0] = rw[1] = rw[2] = rw[3] = rw[4] = rw[5] = rw[6] = rw[7] = 0x80808080u;
+                    }
+                } else {
+                    ff_row_load(FF_ROWW, D.rstate + (size_t)ctx * FF_CONTEXT_SIZE);
+                }
+                cur_ctx = ctx;
+            }
+            state = 2;
+            slot = 0;
+        }
+        /* one binary decision: get_rac + refill, rangecoder.h:123-152 */
+#if defined(__CUDA_ARCH__)
+        s = (int)ff_lds8(row_sa + (uint32_t)slot);
+        r1 = (range * s) >> 8;
+        range -= r1;
+        bit = low >= range;
+        ff_sts8(row_sa + (uint32_t)slot, ff_lds8(tab_sa + (uint32_t)s + (bit ? 0u : 256u)));
+#else
+        s = FF_ROWB(slot);
+        r1 = (range * s) >> 8;
+        range -= r1;
+        bit = low >= range;
+        FF_ROWB(slot) = FF_TAB(s + (bit ? 0 : 256));
+#endif
+        low -= bit ? range : 0;
+        range = bit ? r1 : range;
+        if (range < 0x100) {
+            const int in = pos < end;
+            range <<= 8;
+            low = (low << 8) + (in ? (int)nbyte : 0);
+            pos += (uint32_t)in;
+            overread += !in;
+            nbyte = buf[pos];                        /* the arena is padded past `end` */
+        }
+        /* get_symbol_inline (ffv1dec.c:42-64) as a walk over the state slots:
+         * 0 zero flag | 1..10 unary exponent | 22..31 mantissa | 11..21 sign */
+        done = 0;
+        diff = 0;
+        if (slot == 0) {
+            if (bit)
+                done = 1;
+            else {
+                slot = 1;
+                e = 0;
+            }
+        } else if (slot < 11) {
+            if (bit) {
+                if (++e > 31) {                      /* get_symbol returns AVERROR_INVALIDDATA */
+                    diff = FFRAC_SYMBOL_ERROR;
+                    done = 1;
+                }
+                slot = 1 + ff_min(e, 9);
+            } else {
+                a = 1;
+                mi = e - 1;
+                slot = e ? 22 + ff_min(mi, 9) : 11;
+            }
+        } else if (slot >= 22) {
+            a += a + (uint32_t)bit;
+            mi--;
+            slot = mi < 0 ? 11 + ff_min(e, 10) : 22 + ff_min(mi, 9);
+        } else {
+            diff = bit ? -(int)a : (int)a;
+            done = 1;
+        }
+        if (done) {
+            int v;
+            diff = sign ? -diff : diff;
+            v = (int)(((uint32_t)ff_median3(L, L + T - LT, T) + (uint32_t)diff) & mask);
+            v = (int)(int16_t)v;
+            *(pix_t *)(ol + (size_t)x * step) = (pix_t)v;     /* decode_plane's store, ffv1dec.c:142-161 */
+            if (ll)
+                *(pix_t *)(ll + (size_t)x * step) = (pix_t)v;
+            LL = L;
+            L = v;
+            LT = T;
+            T = RT;
+            x++;
+            state = 1;
+        }
+    }
+#undef FF_QTL
+    if (!live)
+        return;
+    if (cur_ctx >= 0 && !D.touched)                  /* lazily created states die with the launch */
+        ff_row_store(FF_ROWW, D.rstate + (size_t)cur_ctx * FF_CONTEXT_SIZE);
+    {
+        FFRacDec c;
+        c.buf = buf; c.low = low; c.range = range; c.pos = pos; c.end = end; c.overread = overread;
+        /* end-of-slice check, ffv1dec.c:351-359 */
+        if (P.version > 2) {
+            uint8_t term = 129;
+            ffrac_get(&c, D.tab, &term);
+        }
+        res->end_pos = c.pos;
+        res->overread = c.overread;
+    }
+    res->error = err;
+}
+
+/* which specialisation of ff_decode_slice_range_planar serves the stream: 0 none (generic
+ * path), 1 one byte per sample, 2 LSB-packed little-endian u16 */
+FFGPU_HD int ff_decode_planar_mode(const FFDevParams *P)
+{
+    if (P->ac == FF_AC_GOLOMB || P->colorspace != 0 || P->use32)
+        return 0;
+    if (P->sbits <= 8)
+        return 1;
+    return (P->packed_lsb || P->sbits == 16) ? 2 : 0;
+}
+
 FFGPU_HD void ff_decode_slice(const FFDevParams &P, const FFDecSlice &d, const uint8_t *pkt,
                               const FFDecCtx &D, FFDecResult *res, uint32_t *row)
 {
-    if (P.ac == FF_AC_GOLOMB)
+    if (P.ac == FF_AC_GOLOMB) {
         ff_decode_slice_golomb(P, d, pkt, D, res);
-    else
+    } else if (ff_decode_planar_mode(&P)) {
+        /* planar YCbCr / gray (+alpha), 8-bit or LSB-packed 16-bit containers */
+        if (P.sbits <= 8) {
+            if (D.any_five) ff_decode_slice_range_planar<1, true>(P, d, pkt, D, res, row, 1);
+            else            ff_decode_slice_range_planar<1, false>(P, d, pkt, D, res, row, 1);
+        } else {
+            if (D.any_five) ff_decode_slice_range_planar<2, true>(P, d, pkt, D, res, row, 1);
+            else            ff_decode_slice_range_planar<2, false>(P, d, pkt, D, res, row, 1);
+        }
+    } else {
         ff_decode_slice_range(P, d, pkt, D, res, row);
+    }
 }
 
 #endif /* FFGPU_FFV1_SLICE_CUH */

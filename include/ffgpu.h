@@ -21,7 +21,8 @@
 extern "C" {
 #endif
 
-#define FFGPU_ABI_VERSION 1
+#define FFGPU_ABI_VERSION 2
+#define FFGPU_MAX_DEVICES 16
 
 /* error codes: numerically identical to libavutil/error.h so the libavcodec glue
  *  can return them unchanged */
@@ -65,10 +66,21 @@ typedef struct ffgpu_enc_options {
     int max_batch;                /* frames coded per launch group when every frame is a key frame  */
                                   /* (gop_size <= 1); 0 = default                                   */
     int pipeline_depth;           /* launch groups in flight for send/receive; 0 = default          */
+    /* More than one GPU: with ndevices > 1 the handle spreads the stream over
+     * devices[0..ndevices-1] -- picture i goes to GPU i mod N when every frame is a key frame
+     * (gop_size <= 1), whole GOPs round-robin otherwise (adaptive states carry inside a GOP,
+     * ffv1enc.c:1071) -- and receive_packet hands the packets back in presentation order, the
+     * way the reference's frame threads do (pthread_frame.c; AV_CODEC_CAP_DELAY
+     * ffv1enc.c:1332).  ndevices <= 1: the single GPU `device`. */
+    int ndevices;
+    int devices[FFGPU_MAX_DEVICES];
 } ffgpu_enc_options;
 
-/* one picture in HOST memory: AVFrame.data/linesize plus the per-frame fields the
- * slice header carries (ffv1enc.c:944-949) */
+/* one picture: AVFrame.data/linesize plus the per-frame fields the slice header carries
+ * (ffv1enc.c:944-949).  data[] may point to pageable or pinned HOST memory, or -- frames
+ * that already live on the GPU, AV_PIX_FMT_CUDA -- to CUDA DEVICE memory; the
+ * copy kind is taken from the pointer (unified addressing).  The planes must stay valid and
+ * unchanged until the picture's packet has been received (the glue keeps an av_frame_ref). */
 typedef struct ffgpu_picture {
     const uint8_t *data[4];
     int linesize[4];
@@ -115,6 +127,11 @@ int ffgpu_ffv1_encode_frame(ffgpu_encoder *enc, const ffgpu_picture *pic,
 int ffgpu_ffv1_encode_send_frame(ffgpu_encoder *enc, const ffgpu_picture *pic);
 int ffgpu_ffv1_encode_receive_packet(ffgpu_encoder *enc, uint8_t *pkt, size_t pkt_cap,
                                      size_t *pkt_size, int *key_frame, int64_t *pts);
+/* receive_packet without taking the packet: 0 and its exact size when the next packet is
+ * ready (so that the caller can allocate the AVPacket, ff_alloc_packet2, only then and only
+ * that large), else FFGPU_EAGAIN / FFGPU_EOF / an error exactly as receive_packet would.
+ * FFGPU_EOF is reported once: it ends the flush like receive_packet's. */
+int ffgpu_ffv1_encode_packet_ready(ffgpu_encoder *enc, size_t *pkt_size);
 
 /* Pictures already resident in device memory ("frames stay on the GPU").
  * d_frames holds nframes pictures back to back in the layout ffgpu_ffv1_frame_layout()
@@ -141,6 +158,11 @@ typedef struct ffgpu_dec_options {
     int device;
     int max_batch;                /* packets decoded per launch group (intra-only streams) */
     int pipeline_depth;
+    /* More than one GPU: packet i is decoded on GPU i mod N and receive_frame returns the
+     * pictures in packet order.  Only streams whose every frame is a key frame (version 3,
+     * intra flag in the extradata) can be spread; any other stream runs on devices[0]. */
+    int ndevices;
+    int devices[FFGPU_MAX_DEVICES];
 } ffgpu_dec_options;
 
 typedef struct ffgpu_picture_out {
@@ -222,6 +244,13 @@ int ffgpu_ffv1_encoder_profile(ffgpu_encoder *enc, int enable);
 int ffgpu_ffv1_encoder_kernel_ms(ffgpu_encoder *enc, float *ms, int n);
 int ffgpu_ffv1_decoder_profile(ffgpu_decoder *dec, int enable);
 int ffgpu_ffv1_decoder_kernel_ms(ffgpu_decoder *dec, float *ms, int n);
+
+/* Serial cost of the last ffgpu_ffv1_encode_device() batch as stage A counted it: the number
+ * of binary range-coder decisions of all slices (put_rac calls of encode_line,
+ * ffv1enc_template.c:58-77 / ffv1enc.c:185-231) and of the heaviest slice.  The decoder
+ * takes exactly the same decisions for the same stream.  Waits for the batch.  Zero for
+ * Golomb-Rice streams (no binary decisions). */
+int ffgpu_ffv1_encoder_decisions(ffgpu_encoder *enc, uint64_t *total, uint32_t *heaviest_slice);
 
 /* last error text of the calling thread ("" if none) */
 const char *ffgpu_last_error(void);

@@ -238,6 +238,18 @@ extern "C" int ffv1emul_decode(void *h, const uint8_t *pkt_in, int size, uint8_t
         D.qt_all = d->qt.data(); D.tab = &d->s.cur_tab; D.rstate = rs; D.vstate = vs;
         D.lines = d->lines.data(); D.line_stride = line_stride; D.frame = frame;
         D.gate_wait = FF_NEW_WAIT;
+        D.any_five = 0;
+        for (int q = 0; q < d->s.qt_count; q++)
+            D.any_five |= d->qt[(size_t)q * FF_QT_STRIDE + FF_MAX_CTX_INPUTS * 256];
+        /* lazily created states: exactly when the product uses them (every frame a key frame,
+         * no initial-state tables) */
+        std::vector<uint32_t> touched((size_t)(P.total_ctx + 31) / 32, 0);
+        bool lazy = d->s.version > 2 && d->s.intra && work[i].key_frame && ff_decode_planar_mode(&P);
+        for (int q = 0; q < d->s.qt_count; q++)
+            if (d->s.initial[q]) lazy = false;
+        D.touched = lazy ? touched.data() : nullptr;
+        if (lazy)                                   /* rows must come from the touched logic, not from the reset above */
+            memset(rs, 0x55, (size_t)P.total_ctx * FF_CONTEXT_SIZE);
         alignas(16) uint32_t row[FF_ROW_WORDS];
         ff_decode_slice(P, work[i], pkt.data(), D, &res[i], row);
         if (P.ac != FF_AC_GOLOMB && P.version > 2) {

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     bound = {s[0] for s in F().codec.SYMBOLS}
     assert declared == bound, declared ^ bound
-    assert lib.ffgpu_abi_version() == 1
+    assert lib.ffgpu_abi_version() == 2
 
 
 FORMATS = ["yuv420p", "yuv444p", "yuv411p", "gray", "gray9le", "ya8", "yuva422p", "yuv420p9le",
