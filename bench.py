@@ -35,14 +35,31 @@ WORKLOADS = {
     # BASELINE.json configs[1]: the configuration the metric is quoted on
     "C2": dict(desc="4K 3840x2160 yuv420p10le, -slices 1023 (33x31, reference max), range coder "
                     "(forced by >8 bit), context 0, -g 1, slice CRC",
-               w=3840, h=2160, fmt="yuv420p10le", opts=dict(slices=1023, gop_size=1)),
-    "C3": dict(desc="4K bgr0 RCT, -coder range_tab -context 1, 2x2 slices, -g 1",
-               w=3840, h=2160, fmt="bgr0", opts=dict(coder=2, context=1, gop_size=1)),
+               w=3840, h=2160, fmt="yuv420p10le", opts=dict(slices=1023, gop_size=1), batch=192),
+    # the other BASELINE configs: few, large slices -- the path's parallelism is slices x pictures
+    # in flight, so these run with many pictures per launch group
     "C1": dict(desc="1080p yuv420p 8-bit, default 2x2 slices, Golomb-Rice, -g 1",
-               w=1920, h=1080, fmt="yuv420p", opts=dict(gop_size=1)),
+               w=1920, h=1080, fmt="yuv420p", opts=dict(gop_size=1), batch=768),
+    "C3": dict(desc="4K bgr0 RCT, -coder range_tab -context 1, default 2x2 slices, -g 1",
+               w=3840, h=2160, fmt="bgr0", opts=dict(coder=2, context=1, gop_size=1), batch=96),
+    "C4": dict(desc="4K yuv444p16le, default 2x2 slices, range coder, -g 1: DECODE ONLY of a "
+                    "reference-compatible stream",
+               w=3840, h=2160, fmt="yuv444p16le", opts=dict(gop_size=1), batch=96, decode_only=True),
+    "C5": dict(desc="8K 7680x4320 yuv420p10le, default 3x3 slices, range coder, -g 1",
+               w=7680, h=4320, fmt="yuv420p10le", opts=dict(gop_size=1), batch=48),
     "small": dict(desc="640x360 yuv420p10le 60 slices (debug)", w=640, h=360, fmt="yuv420p10le",
-                  opts=dict(slices=60, gop_size=1)),
+                  opts=dict(slices=60, gop_size=1), batch=16),
 }
+
+# the lavfi sources BASELINE.json names, as filter graphs of the reference's own
+# ffmpeg (oracle/_ref/ffmpeg, built by oracle/build_ffmpeg.sh); tests/synth.py stands in, and
+# says so in `config.source`, where that binary is missing
+LAVFI = {
+    "testsrc2": "testsrc2=s={w}x{h}:r=25",
+    "mandelbrot": "mandelbrot=s={w}x{h}:r=25",
+    "noise": "testsrc2=s={w}x{h}:r=25,noise=alls=100:allf=t+u:all_seed=1234",
+}
+FFMPEG = os.path.join(ROOT, "oracle", "_ref", "ffmpeg")
 
 
 def md5(b):
@@ -118,10 +135,50 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def make_frames(wl, count, first_index=0, stride=1):
+def lavfi_frames(wl, source, count, first):
+    """`count` consecutive frames of a lavfi source, starting at frame `first`, converted to
+    the workload's pixel format by the reference's ffmpeg: list of lists of 2-D uint8 planes"""
+    import cpucodec as cc
+    w, h, fmt = wl["w"], wl["h"], wl["fmt"]
+    graph = LAVFI[source].format(w=w, h=h) + ",trim=start_frame=%d:end_frame=%d" % (first, first + count)
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = os.path.join(ROOT, "ffmpeg_ffv2_b200") + ":" + env.get("LD_LIBRARY_PATH", "")
+    r = subprocess.run([FFMPEG, "-hide_banner", "-loglevel", "error", "-nostdin", "-f", "lavfi", "-i", graph,
+                        "-frames:v", str(count), "-pix_fmt", fmt, "-f", "rawvideo", "-"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=900)
+    if r.returncode != 0:
+        raise RuntimeError(r.stderr.decode(errors="replace")[-500:])
+    geo = cc.plane_geometry(fmt, w, h)
+    per = sum(bw * rows for bw, rows in geo)
+    raw = np.frombuffer(r.stdout, np.uint8)
+    if raw.size != per * count:
+        raise RuntimeError("lavfi source gave %d bytes, expected %d" % (raw.size, per * count))
+    out = []
+    for i in range(count):
+        planes, off = [], i * per
+        for bw, rows in geo:
+            planes.append(np.ascontiguousarray(raw[off:off + bw * rows].reshape(rows, bw)))
+            off += bw * rows
+        out.append(planes)
+    return out
+
+
+def make_frames(wl, count, part=0, source="testsrc2"):
+    """(pictures, description of where they came from).  Rank r of N takes the frames
+    r*count .. r*count+count-1 of the source (its own part of the stream)."""
     import synth
-    return [synth.testsrc2_like(wl["fmt"], wl["w"], wl["h"], first_index + i * stride)
-            for i in range(count)]
+    first = part * count
+    if os.path.exists(FFMPEG) and source in LAVFI and not make_frames.force_synth:
+        try:
+            fr = lavfi_frames(wl, source, count, first)
+            digest = hashlib.md5(b"".join(p.tobytes() for p in fr[0])).hexdigest()
+            return fr, "lavfi %s (reference ffmpeg), frames %d..%d, md5(frame %d)=%s" % (
+                LAVFI[source].format(w=wl["w"], h=wl["h"]), first, first + count - 1, first, digest)
+        except Exception as e:               # noqa: BLE001
+            print("lavfi source unavailable (%s): falling back to tests/synth.py" % e, file=sys.stderr)
+    gen = {"testsrc2": synth.testsrc2_like, "mandelbrot": synth.mandelbrot, "noise": synth.noise}[source]
+    return [gen(wl["fmt"], wl["w"], wl["h"], first + i) for i in range(count)], \
+        "%s-like (tests/synth.py; oracle/_ref/ffmpeg not available)" % source
 
 
 def enc_samples(fmt, w, h):
@@ -133,6 +190,15 @@ def enc_samples(fmt, w, h):
         n = w * h + (2 * cw * ch if f["chroma"] and f["layout"] == "planar" else 0)
         return n + (w * h if f["alpha"] else 0)
     return (3 + f["alpha"]) * w * h
+
+
+make_frames.force_synth = False
+
+
+def metric_name(name, wl):
+    if name == "C2":
+        return "ffv1_encode_decode_fps_4k10"
+    return "ffv1_%s_fps_%s" % ("decode" if wl.get("decode_only") else "encode_decode", name)
 
 
 def cpu_codec_kind():
@@ -170,7 +236,7 @@ def reference_arm(args, wl, rank, world, real_stdout):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    frames = make_frames(wl, 4)
+    frames, src_desc = make_frames(wl, 4, 0, args.source)
     which, kind = cpu_codec_kind()
     sample = 8
     res = []
@@ -179,22 +245,51 @@ def reference_arm(args, wl, rank, world, real_stdout):
         if step >= args.warmup:
             res.append(r)
     tot_frames = sum(r["frames"] for r in res)
-    tot_t = sum(r["t_enc"] + r["t_dec"] for r in res)
+    dec_only = bool(wl.get("decode_only"))
+    tot_t = sum((0.0 if dec_only else r["t_enc"]) + r["t_dec"] for r in res)
     fps = tot_frames / tot_t
     out = {
-        "impl": "reference", "metric": "ffv1_encode_decode_fps_4k10", "value": fps, "unit": "frames/s",
+        "impl": "reference", "metric": metric_name(args.workload, wl), "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_t / max(len(res), 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": args.workload + ": " + wl["desc"], "frames_per_step": sample},
+        "config": {"workload": args.workload + ": " + wl["desc"], "frames_per_step": sample,
+                   "source": src_desc},
         "encode_fps": tot_frames / sum(r["t_enc"] for r in res),
         "decode_fps": tot_frames / sum(r["t_dec"] for r in res),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
-                         "sample": "%d pictures encoded+decoded per step, %d steps, %d slice threads" % (
-                             sample, len(res), threads)},
+                         "sample": "%d pictures %s per step, %d steps, %d slice threads "
+                                   "(the reference's own ffv1enc.c/ffv1dec.c, oracle/_ref)" % (
+                             sample, "decoded" if dec_only else "encoded+decoded", len(res), threads)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), file=real_stdout, flush=True)
+
+
+def bind_to_gpu_numa(gpu_index):
+    """run this process (and its first-touch allocations: pinned buffers, staging) on the host
+    cores next to the GPU.  With all ranks on the default CPU set, eight ranks' pinned buffers
+    land on one socket and every DMA of the far GPUs crosses the socket interconnect."""
+    try:
+        bdf = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=pci.bus_id",
+                              "--format=csv,noheader"], stdout=subprocess.PIPE, text=True,
+                             timeout=20).stdout.strip().lower()
+        if bdf.count(":") == 2 and len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]                      # 00000000:1b:00.0 -> 0000:1b:00.0
+        base = "/sys/bus/pci/devices/" + bdf
+        node = open(base + "/numa_node").read().strip()
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        bind_to_gpu_numa.all_cpus = allowed
+        use = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, use)
+        return {"gpu": gpu_index, "pci": bdf, "numa_node": int(node), "cpus": len(use),
+                "bound": bool(cpus & allowed)}
+    except Exception as e:                     # noqa: BLE001
+        return {"gpu": gpu_index, "bound": False, "why": repr(e)[:100]}
 
 
 def main():
@@ -208,9 +303,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--source", default="testsrc2", choices=sorted(LAVFI),
+                    help="lavfi source of the pictures (BASELINE.json: testsrc2, mandelbrot, noise)")
     ap.add_argument("--batch", type=int, default=0, help="pictures per step and GPU (0 = default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-memory e2e leg")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to the GPU's NUMA node")
     ap.add_argument("--e2e-groups", type=int, default=4, help="launch groups a step's pictures are split into")
     ap.add_argument("--e2e-depth", type=int, default=6, help="launch groups in flight (e2e leg)")
     ap.add_argument("--e2e-host", choices=("c", "python"), default="c",
@@ -218,8 +317,11 @@ def main():
     ap.add_argument("--e2e-repeat", type=int, default=6,
                     help="the e2e leg streams the step's pictures this many times back to back, so "
                          "pipeline fill and drain are amortised like in a long transcode")
+    ap.add_argument("--synth", action="store_true",
+                    help="pictures from tests/synth.py even where the reference ffmpeg is available")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
+    make_frames.force_synth = args.synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -229,6 +331,7 @@ def main():
         reference_arm(args, wl, rank, world, real_stdout)
         return 0
 
+    numa = bind_to_gpu_numa(local) if not args.no_numa else {"bound": False, "why": "--no-numa"}
     import torch
     import torch.distributed as dist
     import ffmpeg_ffv2_b200 as F
@@ -261,11 +364,12 @@ def main():
 
     w, h, fmt, opts = wl["w"], wl["h"], wl["fmt"], wl["opts"]
     frame_bytes, planes = F.frame_layout(fmt, w, h)
-    B = args.batch or (192 if args.workload == "C2" else 16)
-    distinct = min(8, B)
+    B = args.batch or wl["batch"]
+    distinct = min(8 if frame_bytes < (64 << 20) else 4, B)
+    dec_only = bool(wl.get("decode_only"))
 
     # ---- synthetic input: `distinct` pictures (this rank's share of the stream), cycled ----
-    srcs = make_frames(wl, distinct, first_index=rank, stride=world)
+    srcs, src_desc = make_frames(wl, distinct, rank, args.source)
     # pinned host copies of the distinct pictures only (picture i of a step is srcs[i % distinct]):
     # keeps the pinned footprint small when 8 ranks share one host
     h_frames = torch.empty((distinct, frame_bytes), dtype=torch.uint8).pin_memory()
@@ -303,7 +407,12 @@ def main():
     cpu_enc.close()
     dec.decode_device(pkts, d_out.data_ptr(), stream)
     torch.cuda.synchronize()
-    if not torch.equal(d_out, d_frames):
+    def same_pictures(a, b):
+        if fmt == "bgr0":                     # the X byte of bgr0 is not coded (ffv1enc.c: transparency 0)
+            return torch.equal(a.view(torch.int32) & 0x00FFFFFF, b.view(torch.int32) & 0x00FFFFFF)
+        return torch.equal(a, b)
+
+    if not same_pictures(d_out, d_frames):
         raise SystemExit("PARITY FAILURE: decoded pictures differ from the input")
     pkt_bytes = sum(len(p) for p in pkts)
     raw_bytes = sum(rb * rows for (_o, _p, rows, rb) in planes)
@@ -324,7 +433,8 @@ def main():
             launches0 = enc.launches + dec.launches
             wall0 = time.perf_counter()
         ev[0].record()
-        enc.encode_device(d_frames.data_ptr(), B, stream)
+        if not dec_only:
+            enc.encode_device(d_frames.data_ptr(), B, stream)
         ev[1].record()
         dec.decode_device(pkts, d_out.data_ptr(), stream)
         ev[2].record()
@@ -332,7 +442,7 @@ def main():
         if step >= args.warmup:
             t_enc_ms += ev[0].elapsed_time(ev[1])
             t_dec_ms += ev[1].elapsed_time(ev[2])
-            for k, v in list(enc.kernel_ms().items()) + list(dec.kernel_ms().items()):
+            for k, v in ([] if dec_only else list(enc.kernel_ms().items())) + list(dec.kernel_ms().items()):
                 kern[k] = kern.get(k, 0.0) + v
     barrier()
     wall = time.perf_counter() - wall0
@@ -344,7 +454,7 @@ def main():
     dev_time = max_over_ranks(max((t_enc_ms + t_dec_ms) / 1e3, 0.0))
     total_frames = B * K * world
     value = total_frames / dev_time
-    enc_fps = B * K * world / max_over_ranks(t_enc_ms / 1e3)
+    enc_fps = None if dec_only else B * K * world / max_over_ranks(t_enc_ms / 1e3)
     dec_fps = B * K * world / max_over_ranks(t_dec_ms / 1e3)
     for k in kern:
         kern[k] /= K
@@ -389,7 +499,7 @@ def main():
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not dec_only:
         # smaller launch groups, more of them in flight: H2D, kernels and D2H overlap
         vb = max(B // args.e2e_groups, 1)
         enc.close()
@@ -413,12 +523,12 @@ def main():
                         ("message", C.c_char * 256), ("produced", C.c_int), ("enc_finished", C.c_int),
                         ("failed", C.c_int), ("t0", C.c_double)]
 
-        def e2e_step_c():
-            NE = B * args.e2e_repeat
+        def e2e_step_c(src=None, dst=None, repeat=None):
+            NE = B * (repeat or args.e2e_repeat)
             run = E2ERun()
             run.enc, run.dec = enc.h, dec.h
             run.nframes, run.nsrc, run.ndst = NE, B, B
-            run.src, run.dst = c_src, c_dst
+            run.src, run.dst = src or c_src, dst or c_dst
             run.timeout_s = 120.0
             pk = (C.POINTER(C.c_uint8) * NE)()
             sz = (C.c_size_t * NE)()
@@ -550,8 +660,13 @@ def main():
             if callable(ends_pk):
                 ends_pk = ends_pk()
             assert done == B * args.e2e_repeat and npk == done
+        def same_host(a, b):
+            if fmt == "bgr0":
+                return np.array_equal(a.view(np.uint32) & 0x00FFFFFF, b.view(np.uint32) & 0x00FFFFFF)
+            return np.array_equal(a, b)
+
         if ends_pk[:B] != pkts or ends_pk[-B:] != pkts or not all(
-                np.array_equal(ho[i], hf[i % distinct]) for i in range(B)):
+                same_host(ho[i], hf[i % distinct]) for i in range(B)):
             raise SystemExit("PARITY FAILURE: e2e path differs from the device path / the input")
         R = args.e2e_repeat
         e2e = {"value": B * R * K * world / e2e_t, "unit": "frames/s",
@@ -564,6 +679,41 @@ def main():
                "host_loop": "tools/e2e_driver.c (2 threads)" if use_c else "python (2 threads)",
                "frames_per_launch_group": vb, "launch_groups_in_flight": args.e2e_depth,
                "gpu_launches": int(enc.launches + dec.launches - e2e_launch0)}
+
+        # ---- the same through ordinary (pageable) memory, what AVFrames are: the library
+        # stages the pictures through its own pinned buffers with a pool of copy threads ----
+        if use_c and not args.no_pageable:
+            pg_src = [[np.array(a, copy=True) for a in host_planes[i]] for i in range(distinct)]
+            pg_out = np.zeros((B, frame_bytes), np.uint8)
+            p_src = (F.codec.Picture * B)()
+            p_dst = (F.codec.PictureOut * B)()
+            for i in range(B):
+                for k, a in enumerate(pg_src[i % distinct]):
+                    p_src[i].data[k] = a.ctypes.data
+                    p_src[i].linesize[k] = a.strides[0]
+                p_src[i].sar_num, p_src[i].sar_den = 0, 1
+                for k, (off, pitch, rows, rb) in enumerate(planes):
+                    p_dst[i].data[k] = pg_out[i, off:].ctypes.data
+                    p_dst[i].linesize[k] = pitch
+            R2 = max(args.e2e_repeat // 2, 1)
+            t_pg = 0.0
+            for step in range(2):
+                barrier()
+                t0 = time.perf_counter()
+                ends, done, npk = e2e_step_c(p_src, p_dst, R2)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                barrier()
+                if step:
+                    t_pg = max_over_ranks(dt)
+                ends = ends()
+                assert done == B * R2
+            if ends[:B] != pkts or not all(same_host(pg_out[i], hf[i % distinct]) for i in range(B)):
+                raise SystemExit("PARITY FAILURE: pageable e2e path differs from the device path / the input")
+            e2e["pageable"] = {"value": B * R2 * world / t_pg, "unit": "frames/s",
+                               "buffers": "malloc'd (numpy) pictures in and out, staged by the library "
+                                          "(FFGPU_COPY_THREADS=%s)" % os.environ.get("FFGPU_COPY_THREADS", "4")}
+            del pg_src, pg_out
 
     clocks = sampler.stop()            # samples of both timed regions (device-resident + e2e)
 
@@ -603,27 +753,57 @@ def main():
         d1.record()
         torch.cuda.synchronize()
         pcie["duplex_GBps_each_way"] = 2 * nb / d0.elapsed_time(d1) / 1e6
+        # the same duplex copies on ALL ranks at once: what the host fabric (PCIe roots, host
+        # DRAM, the socket interconnect) gives the whole job -- the ceiling of e2e at N > 1
+        barrier()
+        d0.record()
+        s1.wait_event(d0)
+        s2.wait_event(d0)
+        with torch.cuda.stream(s1):
+            for _ in range(3):
+                dp.copy_(hp, non_blocking=True)
+        with torch.cuda.stream(s2):
+            for _ in range(3):
+                hq.copy_(dq, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(s1)
+        torch.cuda.current_stream().wait_stream(s2)
+        d1.record()
+        torch.cuda.synchronize()
+        mine = 3 * nb / d0.elapsed_time(d1) / 1e6
+        pcie["all_ranks_duplex_GBps_each_way_this_rank"] = mine
+        pcie["all_ranks_duplex_GBps_each_way_aggregate"] = sum_over_ranks(mine)
+        if e2e:
+            # bytes the e2e leg moved each way per second, against that ceiling
+            e2e_GBps = e2e["h2d_bytes_per_step"] * world / (e2e["ms_per_step"] / 1e3) / 1e9
+            e2e["host_link_GBps_each_way"] = e2e_GBps
+            e2e["fraction_of_all_ranks_duplex_probe"] = e2e_GBps / pcie["all_ranks_duplex_GBps_each_way_aggregate"]
         del hp, dp, hq, dq
-    except Exception:
+    except Exception as ex:                # noqa: BLE001
+        print("pcie probe failed: %r" % (ex,), file=sys.stderr)
+        if world > 1:
+            raise
         pcie = None
 
     # ---- CPU baseline beside it (rank 0, N == 1): the reference's slice-threaded CPU codec ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        if getattr(bind_to_gpu_numa, "all_cpus", None):      # the CPU baseline gets every host core
+            os.sched_setaffinity(0, bind_to_gpu_numa.all_cpus)
         threads = os.cpu_count() or 1
         r = run_cpu(wl, srcs, threads, 16.0, 400)
-        cpu = {"value": r["fps"], "unit": "frames/s", "cores": threads, "kind": r["kind"],
-               "encode_fps": r["enc_fps"], "decode_fps": r["dec_fps"],
-               "sample": "%d pictures encoded+decoded once (%.1f s), %d slice threads" % (
-                   r["frames"], r["t_enc"] + r["t_dec"], threads)}
+        cpu = {"value": r["dec_fps"] if dec_only else r["fps"], "unit": "frames/s", "cores": threads,
+               "kind": r["kind"], "encode_fps": r["enc_fps"], "decode_fps": r["dec_fps"],
+               "sample": "%d pictures encoded+decoded once (%.1f s), %d slice threads%s" % (
+                   r["frames"], r["t_enc"] + r["t_dec"], threads,
+                   "; value = decode only" if dec_only else "")}
 
     out = {
-        "metric": "ffv1_encode_decode_fps_4k10", "value": value, "unit": "frames/s",
+        "metric": metric_name(args.workload, wl), "value": value, "unit": "frames/s",
         "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": 1e3 * dev_time / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": args.workload + ": " + wl["desc"], "frames_per_step_per_gpu": B,
-                   "distinct_pictures": distinct, "source": "testsrc2-like (tests/synth.py)",
+                   "distinct_pictures": distinct, "source": src_desc,
                    "l2": "inputs larger than L2 (%.0f MB per step)" % (B * frame_bytes / 1e6),
                    "partition": "pictures round-robin over ranks, no collective"},
         "encode_fps": enc_fps, "decode_fps": dec_fps,
@@ -632,7 +812,7 @@ def main():
         "kernel_ms_per_step": kern, "wall_ms_per_step": 1e3 * wall / K,
         "decisions": decisions,
         "roofline": roofline, "gpu_launches": int(gpu_launches), "clocks": clocks,
-        "e2e": e2e, "cpu_baseline": cpu, "pcie": pcie,
+        "e2e": e2e, "cpu_baseline": cpu, "pcie": pcie, "numa": numa,
     }
     if rank == 0:
         print(json.dumps(out), file=real_stdout, flush=True)

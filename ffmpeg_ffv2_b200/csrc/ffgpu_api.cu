@@ -598,7 +598,7 @@ extern "C" int ffgpu_ffv1_encode_init(ffgpu_encoder **penc, const ffgpu_enc_opti
         /* enough pictures per group to keep ~64k slice coders (2k warps) resident */
         int b = opt->max_batch > 0 ? opt->max_batch : (65536 + e->P.nslices - 1) / e->P.nslices;
         size_t cap = ((size_t)16 << 30) / (per_frame ? per_frame : 1);
-        if (b > 256) b = 256;
+        if (b > 1024) b = 1024;                   /* one block scans a group's packet sizes */
         if (opt->max_batch <= 0 && (size_t)b > cap) b = (int)cap;
         if (b < 1) b = 1;
         e->max_batch = b;
@@ -755,6 +755,7 @@ static void enc_fill_dev(const ffgpu_encoder *e, const EncJob *j, const uint8_t 
     E->order = j->d_order;
     E->sort_tmp = j->d_sort_tmp;
     E->sort_tmp_bytes = j->sort_tmp_bytes;
+    E->lane_stride = coder_lane_stride((long)j->n * e->P.nslices);
 }
 
 /* enqueue the kernel chain + result download of a filled group */
@@ -1381,7 +1382,7 @@ static int dec_setup_stream(ffgpu_decoder *d)
                                  (size_t)d->max_slices * d->P.nsets * min_ctx * FF_CONTEXT_SIZE;
         int b = d->opt.max_batch > 0 ? d->opt.max_batch : (65536 + d->max_slices - 1) / d->max_slices;
         size_t cap = ((size_t)16 << 30) / (per_frame ? per_frame : 1);
-        if (b > 256) b = 256;
+        if (b > 1024) b = 1024;
         if (d->opt.max_batch <= 0 && (size_t)b > cap) b = (int)cap;
         if (b < 1) b = 1;
         d->max_batch = b;

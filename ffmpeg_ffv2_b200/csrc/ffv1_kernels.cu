@@ -246,7 +246,14 @@ k_code_range(const FFDevParams P, const FFEncDev E, int nframes)
     for (int i = threadIdx.x; i < FF_STAB_ROWS * FF_STAB_STRIDE; i += CODE_THREADS)
         ff_s_stab[i] = (uint8_t)ff_slot_of(i / FF_STAB_STRIDE, i % FF_STAB_STRIDE);
     __syncthreads();
-    const int tid = blockIdx.x * CODE_THREADS + threadIdx.x;
+    ff_fill_tab16(threadIdx.x, CODE_THREADS);
+    __syncthreads();
+    int tid = blockIdx.x * CODE_THREADS + threadIdx.x;
+    if (E.lane_stride > 1) {                                 /* few slices: spread them over the warps */
+        if (tid % E.lane_stride)
+            return;
+        tid /= E.lane_stride;
+    }
     if (tid >= nframes * P.nslices)
         return;
     const int gid = E.order ? (int)E.order[tid] : tid;      /* heaviest slices first */
@@ -267,7 +274,12 @@ k_code_range(const FFDevParams P, const FFEncDev E, int nframes)
 __global__ void __launch_bounds__(CODE_THREADS)
 k_code_golomb(const FFDevParams P, const FFEncDev E, int nframes)
 {
-    const int tid = blockIdx.x * CODE_THREADS + threadIdx.x;
+    int tid = blockIdx.x * CODE_THREADS + threadIdx.x;
+    if (E.lane_stride > 1) {
+        if (tid % E.lane_stride)
+            return;
+        tid /= E.lane_stride;
+    }
     if (tid >= nframes * P.nslices)
         return;
     const int gid = E.order ? (int)E.order[tid] : tid;
@@ -410,8 +422,8 @@ extern "C" int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nfr
     mark(E->events, FFK_SORT + 1, st);
     /* stage B */
     {
-        const int total = nframes * P->nslices;
-        const int blocks = (total + CODE_THREADS - 1) / CODE_THREADS;
+        const long total = (long)nframes * P->nslices * (E->lane_stride > 1 ? E->lane_stride : 1);
+        const int blocks = (int)((total + CODE_THREADS - 1) / CODE_THREADS);
         if (P->ac == FF_AC_GOLOMB)
             k_code_golomb<<<blocks, CODE_THREADS, 0, st>>>(*P, *E, nframes);
         else
@@ -509,6 +521,8 @@ k_decode(const FFDevParams P, const FFDecDev D, int nframes)
     __shared__ uint32_t s_crc[256];
     for (int i = threadIdx.x; i < 256; i += CODE_THREADS)
         s_crc[i] = ff_crc_table_entry(i);
+    __syncthreads();
+    ff_fill_tab16(threadIdx.x, CODE_THREADS);
     __syncthreads();
     /* the planar path keeps every lane of a warp inside the decode loop (lanes without a
      * slice idle there), so nothing returns before the call */

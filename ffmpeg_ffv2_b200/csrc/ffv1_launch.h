@@ -42,6 +42,7 @@ typedef struct FFEncDev {
     uint32_t *order;                /* [nframes*nslices] slice ids, heaviest first      */
     void *sort_tmp;
     size_t sort_tmp_bytes;
+    int lane_stride;                /* slice coders: 1 = every lane codes a slice ... 32 = one per warp */
     void **events;                  /* optional cudaEvent_t[FFK_ENC_KERNELS + 1]: recorded    */
                                     /* before the first and after every kernel (profiling)  */
 } FFEncDev;

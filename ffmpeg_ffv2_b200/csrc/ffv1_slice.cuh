@@ -249,6 +249,15 @@ extern __shared__ int16_t ff_s_qt[];             /* decoder: qt_count quant tabl
 #define FF_TOK_AHEAD  6
 static __shared__ FFU128 ff_s_tok[FF_TOK_CHUNKS * FF_CODE_THREADS];
 #endif
+#if defined(__CUDACC__)
+/* both successors of an adaptive state in one 16-bit entry: one_state | zero_state << 8 */
+static __shared__ uint16_t ff_s_tab16[256];
+__device__ __forceinline__ void ff_fill_tab16(int tid, int nthreads)
+{
+    for (int i = tid; i < 256; i += nthreads)
+        ff_s_tab16[i] = (uint16_t)(ff_s_tab.one[i] | (ff_s_tab.zero[i] << 8));
+}
+#endif
 #if defined(__CUDA_ARCH__)
 #define FF_TAB(i)   (((const uint8_t *)&ff_s_tab)[i])
 #define FF_ROWB(i)  (((uint8_t *)ff_s_rows)[threadIdx.x * (FF_ROW_WORDS * 4) + (i)])
@@ -332,6 +341,26 @@ __device__ __forceinline__ uint32_t ff_opaque(uint32_t v)
 {
     return __shfl_sync(__activemask(), v, (int)(threadIdx.x & 31));
 }
+__device__ __forceinline__ uint32_t ff_lds16u(uint32_t sa)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(sa));
+    return v;
+}
+/* range decoder refill (rangecoder.h:123-139), out of line: in the loop it would be turned
+ * into a dozen predicated instructions that every decision issues and whose scoreboard wait
+ * on the prefetched byte every decision pays.  in: low, pos, overread, nbyte; out likewise */
+static __device__ __noinline__ uint4 ff_dec_refill(int low, uint32_t pos, int overread, uint32_t nbyte,
+                                            const uint8_t *buf, uint32_t end)
+{
+    const int in = pos < end;
+    uint4 r;
+    r.x = (uint32_t)((low << 8) + (in ? (int)nbyte : 0));
+    r.y = pos + (uint32_t)in;
+    r.z = (uint32_t)(overread + !in);
+    r.w = buf[r.y];                              /* the arena is padded past `end` */
+    return r;
+}
 __device__ __forceinline__ int ff_lds16s(uint32_t sa)
 {
     int v;
@@ -365,11 +394,15 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
     int cur_ctx = -1;
     int e = 0, step = 0, nsteps = 0;
     uint64_t seq = 0;                                /* bit k = value of decision k of the residual */
+    /* the adaptive state of the coming decision, and the current row's slot 0 (the zero
+     * flag), in registers: see ff_decode_slice_range_planar */
+    uint32_t sreg = 128, s0 = 128;
+    int slot = 0;
     (void)tab_; (void)row_;
 
 #if defined(__CUDA_ARCH__)
     uint32_t row_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_rows[threadIdx.x * FF_ROW_WORDS]);
-    uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_tab);
+    uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(ff_s_tab16);
     uint32_t stab_sa = (uint32_t)__cvta_generic_to_shared(ff_s_stab);
     /* a shuffle from the own lane is opaque to ptxas: otherwise it rematerialises the
      * shared-window base (S2R CgaCtaId + shifts, a dozen instructions) in front of every
@@ -377,13 +410,23 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
     row_sa = ff_opaque(row_sa);
     tab_sa = ff_opaque(tab_sa);
     stab_sa = ff_opaque(stab_sa);
-    uint32_t srow = stab_sa, slot = 0;
+    uint32_t srow = stab_sa;
+#define FF_ST_LD(sl) ff_lds8(row_sa + (uint32_t)(sl))
+#define FF_ST_ST(sl, v) ff_sts8(row_sa + (uint32_t)(sl), (v))
+#define FF_TAB16(st) ff_lds16u(tab_sa + 2u * (st))
+#define FF_SLOT_AT(st) ((int)ff_lds8(srow + (uint32_t)(st)))
     const uint32_t nchunks = (n + 3) >> 2;
     for (uint32_t ch = 0; ch < FF_TOK_AHEAD; ch++) {
         if (ch < nchunks)
             ff_cp_async16(&ff_s_tok[ch * FF_CODE_THREADS + threadIdx.x], tokens + 4 * ch);
         ff_cp_async_commit();
     }
+#endif
+#if !defined(__CUDA_ARCH__)
+#define FF_ST_LD(sl) ((uint32_t)FF_ROWB(sl))
+#define FF_ST_ST(sl, v) (FF_ROWB(sl) = (uint8_t)(v))
+#define FF_TAB16(st) ((uint32_t)FF_TAB(st) | ((uint32_t)FF_TAB(256 + (st)) << 8))
+#define FF_SLOT_AT(st) ff_slot_of(e, (st))
 #endif
     ff_enc_resume(&c, pre, pre_bytes, out, sl.bs_cap);
     for (;;) {
@@ -411,9 +454,12 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
             ctx = (int)(tok & FF_TOKEN_CTX_MASK);
             diff = (int32_t)tok >> FF_TOKEN_CTX_BITS;
             if (ctx != cur_ctx) {
-                if (cur_ctx >= 0)
+                if (cur_ctx >= 0) {
+                    FF_ST_ST(0, s0);
                     ff_row_store(FF_ROWW, state + (size_t)cur_ctx * FF_CONTEXT_SIZE);
+                }
                 ff_row_load(FF_ROWW, state + (size_t)ctx * FF_CONTEXT_SIZE);
+                s0 = FF_ST_LD(0);
                 cur_ctx = ctx;
             }
             a = (uint32_t)(diff < 0 ? -diff : diff);
@@ -439,38 +485,42 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
             step = 0;
 #if defined(__CUDA_ARCH__)
             srow = stab_sa + (uint32_t)e * FF_STAB_STRIDE;
-            slot = 0;
 #endif
+            slot = 0;
+            sreg = s0;
         }
         bit = (int)(seq & 1);
         seq >>= 1;
-#if defined(__CUDA_ARCH__)
         {
-            const uint32_t sa = row_sa + slot;
-            s = (int)ff_lds8(sa);
+            const uint32_t t16 = FF_TAB16(sreg);     /* both successor states, fetched early */
+            const uint32_t ns = bit ? (t16 & 0xFFu) : (t16 >> 8);
+            s = (int)sreg;
             r1 = (c.range * s) >> 8;                 /* put_rac, rangecoder.h:104-121 */
             rb = c.range - r1;
-            ff_sts8(sa, ff_lds8(tab_sa + (uint32_t)s + (bit ? 0u : 256u)));
+            if (slot == 0)
+                s0 = ns;
+            else
+                FF_ST_ST(slot, ns);
             step++;
-            slot = ff_lds8(srow + (uint32_t)step);   /* slot of the next decision */
+            if (step < nsteps) {                     /* slot and state of the next decision */
+                const int nslot = FF_SLOT_AT(step);
+                sreg = nslot == slot ? ns : FF_ST_LD(nslot);
+                slot = nslot;
+            }
         }
-#else
-        {
-            const int slot = ff_slot_of(e, step);
-            s = FF_ROWB(slot);
-            r1 = (c.range * s) >> 8;
-            rb = c.range - r1;
-            FF_ROWB(slot) = FF_TAB(s + (bit ? 0 : 256));
-            step++;
-        }
-#endif
         c.low += bit ? rb : 0;
         c.range = bit ? r1 : rb;
         if (c.range < 0x100)
             ffrac_enc_shift1(&c);
     }
-    if (cur_ctx >= 0)
+    if (cur_ctx >= 0) {
+        FF_ST_ST(0, s0);
         ff_row_store(FF_ROWW, state + (size_t)cur_ctx * FF_CONTEXT_SIZE);
+    }
+#undef FF_ST_LD
+#undef FF_ST_ST
+#undef FF_TAB16
+#undef FF_SLOT_AT
     nb = ffrac_enc_finish(&c, tab_, 1);              /* ffv1enc.c:1242 */
     *overflow = c.overflow;
     return nb;
@@ -1455,6 +1505,11 @@ FFGPU_HD void ff_decode_slice_range_planar(const FFDevParams &P, const FFDecSlic
     unsigned state = 1;
     int x = -1, w = 0, err = 0, cur_ctx = -1;
     int five = 0, sign = 0, e = 0, mi = 0, slot = 0;
+    /* the adaptive state of the coming decision, and the current row's slot 0 (the zero
+     * flag, four of five decisions in flat pictures): both live in registers, so the
+     * decision does not start with a shared-memory round trip.  The row's byte 0 in shared
+     * memory is only brought up to date when the row is written back. */
+    uint32_t sreg = 128, s0 = 128;
     uint32_t a = 0;
     int T = 0, LT = 0, L = 0, LL = 0, RT = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0;
     int qo = 0, sbase = 0, step = (int)sizeof(pix_t);
@@ -1470,15 +1525,21 @@ FFGPU_HD void ff_decode_slice_range_planar(const FFDevParams &P, const FFDecSlic
     const int gate_wait = D.gate_wait;
     int waited = 0;
     uint32_t row_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_rows[threadIdx.x * FF_ROW_WORDS]);
-    uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_tab);
+    uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(ff_s_tab16);
     uint32_t qt_sa = (uint32_t)__cvta_generic_to_shared(ff_s_qt);
     row_sa = ff_opaque(row_sa);                      /* see ff_encode_slice_range */
     tab_sa = ff_opaque(tab_sa);
     qt_sa = ff_opaque(qt_sa);
     uint32_t q_sa = qt_sa;                           /* quant table set of the current line */
 #define FF_QTL(i) ff_lds16s(q_sa + 2u * (uint32_t)(i))
+#define FF_ST_LD(sl) ff_lds8(row_sa + (uint32_t)(sl))
+#define FF_ST_ST(sl, v) ff_sts8(row_sa + (uint32_t)(sl), (v))
+#define FF_TAB16(st) ff_lds16u(tab_sa + 2u * (st))
 #else
 #define FF_QTL(i) FF_QT(qo, i)
+#define FF_ST_LD(sl) ((uint32_t)FF_ROWB(sl))
+#define FF_ST_ST(sl, v) (FF_ROWB(sl) = (uint8_t)(v))
+#define FF_TAB16(st) ((uint32_t)FF_TAB(st) | ((uint32_t)FF_TAB(256 + (st)) << 8))
 #endif
 
     /* zero rows: line 0 of plane 0's scratch is the row "above the slice" of every
@@ -1597,8 +1658,10 @@ FFGPU_HD void ff_decode_slice_range_planar(const FFDevParams &P, const FFDecSlic
             sign = ctx < 0;
             ctx = sbase + (sign ? -ctx : ctx);
             if (ctx != cur_ctx) {
-                if (cur_ctx >= 0)
+                if (cur_ctx >= 0) {
+                    FF_ST_ST(0, s0);
                     ff_row_store(FF_ROWW, D.rstate + (size_t)cur_ctx * FF_CONTEXT_SIZE);
+                }
                 if (D.touched) {
                     const uint32_t tw = D.touched[ctx >> 5], tb = 1u << (ctx & 31);
                     if (tw & tb) {
@@ -1611,35 +1674,48 @@ FFGPU_HD void ff_decode_slice_range_planar(const FFDevParams &P, const FFDecSlic
                 } else {
                     ff_row_load(FF_ROWW, D.rstate + (size_t)ctx * FF_CONTEXT_SIZE);
                 }
+                s0 = FF_ST_LD(0);
                 cur_ctx = ctx;
             }
             state = 2;
             slot = 0;
+            sreg = s0;
         }
         /* one binary decision: get_rac + refill, rangecoder.h:123-152 */
-#if defined(__CUDA_ARCH__)
-        s = (int)ff_lds8(row_sa + (uint32_t)slot);
-        r1 = (range * s) >> 8;
-        range -= r1;
-        bit = low >= range;
-        ff_sts8(row_sa + (uint32_t)slot, ff_lds8(tab_sa + (uint32_t)s + (bit ? 0u : 256u)));
-#else
-        s = FF_ROWB(slot);
-        r1 = (range * s) >> 8;
-        range -= r1;
-        bit = low >= range;
-        FF_ROWB(slot) = FF_TAB(s + (bit ? 0 : 256));
-#endif
+        {
+            const uint32_t t16 = FF_TAB16(sreg);     /* both successor states, fetched early */
+            uint32_t ns;
+            s = (int)sreg;
+            r1 = (range * s) >> 8;
+            range -= r1;
+            bit = low >= range;
+            ns = bit ? (t16 & 0xFFu) : (t16 >> 8);
+            if (slot == 0)
+                s0 = ns;
+            else
+                FF_ST_ST(slot, ns);
+            sreg = ns;                               /* if the next decision uses the same slot */
+        }
         low -= bit ? range : 0;
         range = bit ? r1 : range;
         if (range < 0x100) {
+#if defined(__CUDA_ARCH__)
+            const uint4 rf = ff_dec_refill(low, pos, overread, nbyte, buf, end);
+            range <<= 8;
+            low = (int)rf.x;
+            pos = rf.y;
+            overread = (int)rf.z;
+            nbyte = rf.w;
+#else
             const int in = pos < end;
             range <<= 8;
             low = (low << 8) + (in ? (int)nbyte : 0);
             pos += (uint32_t)in;
             overread += !in;
             nbyte = buf[pos];                        /* the arena is padded past `end` */
+#endif
         }
+        const int slot_was = slot;
         /* get_symbol_inline (ffv1dec.c:42-64) as a walk over the state slots:
          * 0 zero flag | 1..10 unary exponent | 22..31 mantissa | 11..21 sign */
         done = 0;
@@ -1671,6 +1747,8 @@ FFGPU_HD void ff_decode_slice_range_planar(const FFDevParams &P, const FFDecSlic
             diff = bit ? -(int)a : (int)a;
             done = 1;
         }
+        if (!done && slot != slot_was)               /* state of the next decision, fetched ahead */
+            sreg = FF_ST_LD(slot);
         if (done) {
             int v;
             diff = sign ? -diff : diff;
@@ -1687,11 +1765,16 @@ FFGPU_HD void ff_decode_slice_range_planar(const FFDevParams &P, const FFDecSlic
             state = 1;
         }
     }
-#undef FF_QTL
     if (!live)
         return;
-    if (cur_ctx >= 0 && !D.touched)                  /* lazily created states die with the launch */
+    if (cur_ctx >= 0 && !D.touched) {                /* lazily created states die with the launch */
+        FF_ST_ST(0, s0);
         ff_row_store(FF_ROWW, D.rstate + (size_t)cur_ctx * FF_CONTEXT_SIZE);
+    }
+#undef FF_QTL
+#undef FF_ST_LD
+#undef FF_ST_ST
+#undef FF_TAB16
     {
         FFRacDec c;
         c.buf = buf; c.low = low; c.range = range; c.pos = pos; c.end = end; c.overread = overread;

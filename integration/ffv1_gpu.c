@@ -18,11 +18,12 @@
 #include "libavutil/opt.h"
 #include "libavutil/pixdesc.h"
 #include "avcodec.h"
+#include "decode.h"
 #include "internal.h"
 
 #include "ffgpu.h"
 
-#define GPU_FIFO 1024
+#define GPU_FIFO 2048          /* >= pictures the launch groups of one handle can hold in flight */
 
 typedef struct FFV1GpuContext {
     AVClass *class;            /* first member: avcodec_open2 applies the AVOptions (utils.c:630-639) */
@@ -32,16 +33,51 @@ typedef struct FFV1GpuContext {
     int context_model;
     /* new: placement */
     int gpu;
+    int gpus;                  /* > 1: spread the stream over GPUs gpu .. gpu+gpus-1 */
     int max_batch;
     int depth;
     ffgpu_encoder *enc;
     ffgpu_decoder *dec;
-    /* decoder: pictures handed to the GPU, waiting to come back in order */
+    /* pictures handed to the GPU that have not come back yet, oldest first.  Encoder: a
+     * reference to every input frame (the library reads the planes asynchronously until the
+     * packet is out, like ffv1enc.c:1194-1196 keeps its av_frame_ref).  Decoder: the output
+     * frames the pictures are downloaded into. */
     AVFrame *fifo[GPU_FIFO];
     int fifo_head, fifo_count;
+    AVPacket *pending;         /* decoder: a packet the library could not take yet */
+    int draining;
 } FFV1GpuContext;
 
+static int fifo_push(FFV1GpuContext *s, AVFrame *f)
+{
+    if (s->fifo_count == GPU_FIFO)
+        return AVERROR(ENOMEM);
+    s->fifo[(s->fifo_head + s->fifo_count++) % GPU_FIFO] = f;
+    return 0;
+}
+
+static AVFrame *fifo_pop(FFV1GpuContext *s)
+{
+    AVFrame *f;
+    if (!s->fifo_count)
+        return NULL;
+    f = s->fifo[s->fifo_head];
+    s->fifo[s->fifo_head] = NULL;
+    s->fifo_head = (s->fifo_head + 1) % GPU_FIFO;
+    s->fifo_count--;
+    return f;
+}
+
+static void set_devices(const FFV1GpuContext *s, int *ndevices, int devices[FFGPU_MAX_DEVICES])
+{
+    int i;
+    *ndevices = s->gpus > 1 ? FFMIN(s->gpus, FFGPU_MAX_DEVICES) : 0;
+    for (i = 0; i < *ndevices; i++)
+        devices[i] = s->gpu + i;
+}
+
 /* exported so that a test harness without libavutil/opt.c can set the private options */
+void ff_ffv1_gpu_set_options(void *priv, int slicecrc, int coder, int context);
 void ff_ffv1_gpu_set_options(void *priv, int slicecrc, int coder, int context)
 {
     FFV1GpuContext *s = priv;
@@ -71,6 +107,7 @@ static av_cold int gpu_encode_init(AVCodecContext *avctx)
     o.device = s->gpu;
     o.max_batch = s->max_batch;
     o.pipeline_depth = s->depth;
+    set_devices(s, &o.ndevices, o.devices);
     if (avctx->flags & (AV_CODEC_FLAG_PASS1 | AV_CODEC_FLAG_PASS2)) {
         avpriv_report_missing_feature(avctx, "2-pass statistics on the GPU path");
         return AVERROR_PATCHWELCOME;
@@ -108,10 +145,13 @@ static int gpu_send_frame(AVCodecContext *avctx, const AVFrame *pict)
 {
     FFV1GpuContext *s = avctx->priv_data;
     ffgpu_picture p = { { 0 } };
+    AVFrame *ref;
     int ret, i;
 
     if (!pict)
         return ffgpu_ffv1_encode_send_frame(s->enc, NULL);
+    if (s->fifo_count == GPU_FIFO)
+        return AVERROR(EAGAIN);
     for (i = 0; i < 4; i++) {
         p.data[i] = pict->data[i];
         p.linesize[i] = pict->linesize[i];
@@ -122,9 +162,15 @@ static int gpu_send_frame(AVCodecContext *avctx, const AVFrame *pict)
     p.sar_den = pict->sample_aspect_ratio.den;
     p.pts = pict->pts;
     ret = ffgpu_ffv1_encode_send_frame(s->enc, &p);   /* FFGPU_EAGAIN == AVERROR(EAGAIN) */
-    if (ret < 0 && ret != AVERROR(EAGAIN))
-        av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
-    return ret;
+    if (ret < 0) {
+        if (ret != AVERROR(EAGAIN))
+            av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
+        return ret;
+    }
+    /* the planes are read asynchronously: hold the frame until its packet is out */
+    if (!(ref = av_frame_clone(pict)))
+        return AVERROR(ENOMEM);
+    return fifo_push(s, ref);
 }
 
 static int gpu_receive_packet(AVCodecContext *avctx, AVPacket *pkt)
@@ -134,15 +180,26 @@ static int gpu_receive_packet(AVCodecContext *avctx, AVPacket *pkt)
     int key = 0, ret;
     int64_t pts = AV_NOPTS_VALUE;
 
-    if ((ret = ff_alloc_packet2(avctx, pkt, ffgpu_ffv1_encoder_max_packet(s->enc), 0)) < 0)
-        return ret;
-    ret = ffgpu_ffv1_encode_receive_packet(s->enc, pkt->data, pkt->size, &size, &key, &pts);
-    if (ret < 0) {                             /* EAGAIN, EOF ("encoded frame too large", ...) */
+    AVFrame *done;
+
+    /* is a packet ready, and how large is it?  Nothing is allocated on EAGAIN / EOF, and the
+     * packet gets its exact size instead of the worst case of ffv1enc.c:1131-1132 */
+    ret = ffgpu_ffv1_encode_packet_ready(s->enc, &size);
+    if (ret < 0) {                             /* EAGAIN, EOF, "encoded frame too large", ... */
         if (ret != AVERROR(EAGAIN) && ret != AVERROR_EOF)
             av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
+        return ret;
+    }
+    if ((ret = ff_alloc_packet2(avctx, pkt, size, 0)) < 0)
+        return ret;
+    ret = ffgpu_ffv1_encode_receive_packet(s->enc, pkt->data, pkt->size, &size, &key, &pts);
+    if (ret < 0) {
+        av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
         av_packet_unref(pkt);
         return ret;
     }
+    done = fifo_pop(s);                        /* packets come back in input order */
+    av_frame_free(&done);
     pkt->size = size;
     pkt->pts = pkt->dts = pts;
     if (key)
@@ -160,6 +217,7 @@ static av_cold int gpu_close(AVCodecContext *avctx)
     s->dec = NULL;
     for (i = 0; i < GPU_FIFO; i++)
         av_frame_free(&s->fifo[i]);
+    av_packet_free(&s->pending);
     return 0;
 }
 
@@ -177,6 +235,9 @@ static av_cold int gpu_decode_init(AVCodecContext *avctx)
     o.device = s->gpu;
     o.max_batch = s->max_batch;
     o.pipeline_depth = s->depth;
+    set_devices(s, &o.ndevices, o.devices);
+    if (!(s->pending = av_packet_alloc()))
+        return AVERROR(ENOMEM);
     if ((ret = ffgpu_ffv1_decode_init(&s->dec, &o)) < 0) {
         av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
         return ret;
@@ -190,9 +251,17 @@ static av_cold int gpu_decode_init(AVCodecContext *avctx)
     return 0;
 }
 
-/* AVCodec.decode: synchronous form (one packet in, one picture out).  The pipelined
- * send_packet/receive_frame entry points of the C ABI map onto AVCodec.receive_frame in the
- * same way the encoder above maps onto encode2; see INTEGRATION.md. */
+static void fill_frame_props(AVFrame *frame, const ffgpu_picture_out *out)
+{
+    frame->pict_type = AV_PICTURE_TYPE_I;
+    frame->key_frame = out->key_frame;
+    frame->interlaced_frame = out->interlaced_frame;
+    frame->top_field_first = out->top_field_first;
+    frame->sample_aspect_ratio = (AVRational){ out->sar_num, out->sar_den };
+}
+
+/* AVCodec.decode: synchronous form (one packet in, one picture out); the pipelined form is
+ * gpu_receive_frame below. */
 static int gpu_decode_frame(AVCodecContext *avctx, void *data, int *got_frame, AVPacket *avpkt)
 {
     FFV1GpuContext *s = avctx->priv_data;
@@ -222,14 +291,114 @@ static int gpu_decode_frame(AVCodecContext *avctx, void *data, int *got_frame, A
         av_frame_unref(frame);
         return ret;
     }
-    frame->pict_type = AV_PICTURE_TYPE_I;
-    frame->key_frame = out.key_frame;
-    frame->interlaced_frame = out.interlaced_frame;
-    frame->top_field_first = out.top_field_first;
-    frame->sample_aspect_ratio = (AVRational){ out.sar_num, out.sar_den };
+    fill_frame_props(frame, &out);
     if (out.damaged_slices)
         av_log(avctx, AV_LOG_ERROR, "%d damaged slice(s) concealed\n", out.damaged_slices);
     return ret;                                /* bytes consumed, like ffv1dec.c:982 */
+}
+
+/* AVCodec.receive_frame (avcodec.h:3654-3662): the pipelined decoder.  It replaces what
+ * frame threading does for the CPU codec (ffv1dec.c:1042-1099, pthread_frame.c): packets are
+ * pulled with ff_decode_get_packet() and queued on the GPU together with the AVFrame they
+ * will be downloaded into; pictures come back in packet order as launch groups finish. */
+static int gpu_receive_frame(AVCodecContext *avctx, AVFrame *frame)
+{
+    FFV1GpuContext *s = avctx->priv_data;
+    ffgpu_picture_out out;
+    const char *name;
+    int ret, i;
+
+    for (;;) {
+        memset(&out, 0, sizeof(out));
+        ret = ffgpu_ffv1_decode_receive_frame(s->dec, &out);
+        if (ret == 0) {
+            AVFrame *f = fifo_pop(s);
+            av_assert0(f);
+            av_frame_move_ref(frame, f);
+            av_frame_free(&f);
+            fill_frame_props(frame, &out);
+            if (out.damaged_slices)
+                av_log(avctx, AV_LOG_ERROR, "%d damaged slice(s) concealed\n", out.damaged_slices);
+            return 0;
+        }
+        if (ret != AVERROR(EAGAIN)) {          /* AVERROR_EOF after the drain, or an error */
+            if (ret != AVERROR_EOF)
+                av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
+            return ret;
+        }
+        /* nothing ready: feed the GPU */
+        if (s->draining)
+            continue;                          /* flushed: the library blocks until pictures come */
+        if (!s->pending->data) {
+            ret = ff_decode_get_packet(avctx, s->pending);
+            if (ret == AVERROR_EOF) {
+                s->draining = 1;
+                if ((ret = ffgpu_ffv1_decode_send_packet(s->dec, NULL, 0, 0, NULL)) < 0)
+                    return ret;
+                continue;
+            }
+            if (ret < 0)
+                return ret;                    /* AVERROR(EAGAIN): the caller sends more packets */
+        }
+        if (!(name = ffgpu_ffv1_decoder_pix_fmt(s->dec))) {
+            if ((ret = ffgpu_ffv1_decoder_probe(s->dec, s->pending->data, s->pending->size)) < 0) {
+                av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
+                av_packet_unref(s->pending);
+                return ret;
+            }
+            name = ffgpu_ffv1_decoder_pix_fmt(s->dec);
+        }
+        avctx->pix_fmt = av_get_pix_fmt(name);
+        {
+            AVFrame *f = av_frame_alloc();
+            ffgpu_picture_out dst = { { 0 } };
+            if (!f)
+                return AVERROR(ENOMEM);
+            if ((ret = ff_get_buffer(avctx, f, AV_GET_BUFFER_FLAG_REF)) < 0) {
+                av_frame_free(&f);
+                return ret;
+            }
+            for (i = 0; i < 4; i++) {
+                dst.data[i] = f->data[i];
+                dst.linesize[i] = f->linesize[i];
+            }
+            ret = ffgpu_ffv1_decode_send_packet(s->dec, s->pending->data, s->pending->size,
+                                                s->pending->pts, &dst);
+            if (ret == AVERROR(EAGAIN)) {      /* every launch group is busy: receive blocks next */
+                av_frame_free(&f);
+                continue;
+            }
+            av_packet_unref(s->pending);
+            if (ret < 0) {
+                av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
+                av_frame_free(&f);
+                return ret;
+            }
+            if ((ret = fifo_push(s, f)) < 0) {
+                av_frame_free(&f);
+                return ret;
+            }
+        }
+    }
+}
+
+static void gpu_flush(AVCodecContext *avctx)
+{
+    FFV1GpuContext *s = avctx->priv_data;
+    ffgpu_picture_out out;
+    AVFrame *f;
+    if (!s->dec)
+        return;
+    /* avcodec_flush_buffers: drop what is in flight */
+    ffgpu_ffv1_decode_send_packet(s->dec, NULL, 0, 0, NULL);
+    do {
+        memset(&out, 0, sizeof(out));
+    } while (ffgpu_ffv1_decode_receive_frame(s->dec, &out) != AVERROR_EOF && s->fifo_count &&
+             (f = fifo_pop(s), av_frame_free(&f), 1));
+    while ((f = fifo_pop(s)))
+        av_frame_free(&f);
+    av_packet_unref(s->pending);
+    s->draining = 0;
 }
 
 #define OFFSET(x) offsetof(FFV1GpuContext, x)
@@ -247,12 +416,14 @@ static const AVOption enc_options[] = {
     { "context", "Context model", OFFSET(context_model), AV_OPT_TYPE_INT, { .i64 = 0 }, 0, 1, VE },
     /* new */
     { "gpu", "CUDA device ordinal", OFFSET(gpu), AV_OPT_TYPE_INT, { .i64 = 0 }, 0, 64, VE },
+    { "gpus", "spread the stream over this many GPUs, starting at gpu", OFFSET(gpus), AV_OPT_TYPE_INT, { .i64 = 1 }, 1, FFGPU_MAX_DEVICES, VE },
     { "gpu_batch", "pictures per launch group (0 = auto)", OFFSET(max_batch), AV_OPT_TYPE_INT, { .i64 = 0 }, 0, 1024, VE },
     { "gpu_depth", "launch groups in flight (0 = auto)", OFFSET(depth), AV_OPT_TYPE_INT, { .i64 = 0 }, 0, 8, VE },
     { NULL }
 };
 static const AVOption dec_options[] = {
     { "gpu", "CUDA device ordinal", OFFSET(gpu), AV_OPT_TYPE_INT, { .i64 = 0 }, 0, 64, VD },
+    { "gpus", "spread an intra-only stream over this many GPUs, starting at gpu", OFFSET(gpus), AV_OPT_TYPE_INT, { .i64 = 1 }, 1, FFGPU_MAX_DEVICES, VD },
     { "gpu_batch", "packets per launch group (0 = auto)", OFFSET(max_batch), AV_OPT_TYPE_INT, { .i64 = 0 }, 0, 1024, VD },
     { "gpu_depth", "launch groups in flight (0 = auto)", OFFSET(depth), AV_OPT_TYPE_INT, { .i64 = 0 }, 0, 8, VD },
     { NULL }
@@ -307,8 +478,10 @@ AVCodec ff_ffv1_gpu_decoder = {
     .priv_data_size = sizeof(FFV1GpuContext),
     .init           = gpu_decode_init,
     .close          = gpu_close,
-    .decode         = gpu_decode_frame,
-    .capabilities   = AV_CODEC_CAP_DR1,
+    .decode         = gpu_decode_frame,        /* synchronous form, used by the vtable harness  */
+    .receive_frame  = gpu_receive_frame,       /* what libavcodec/decode.c:643 calls            */
+    .flush          = gpu_flush,
+    .capabilities   = AV_CODEC_CAP_DR1 | AV_CODEC_CAP_DELAY,
     .caps_internal  = FF_CODEC_CAP_INIT_CLEANUP,
     .priv_class     = &dec_class,
 };

@@ -35,7 +35,7 @@ if [ ! -f ffbuild/config.mak ]; then
         --enable-muxer=nut,avi,matroska,framemd5,framecrc,md5,null,rawvideo \
         --enable-demuxer=nut,avi,matroska,rawvideo \
         --enable-protocol=file,pipe,md5 --enable-indev=lavfi \
-        --enable-filter=testsrc2,testsrc,mandelbrot,scale,format,null,noise,nullsrc,geq,color \
+        --enable-filter=testsrc2,testsrc,mandelbrot,scale,format,null,noise,nullsrc,geq,color,trim,select \
         --disable-ffplay --disable-ffprobe \
         --extra-ldflags="-L$REPO/ffmpeg_ffv2_b200" --extra-libs="-lffgpu -lpthread -ldl -lrt" \
         > configure.log 2>&1 || { tail -20 configure.log; tail -30 ffbuild/config.log; exit 1; }
