@@ -24,17 +24,18 @@ def sources():
            [os.path.join(HERE, "..", "include", "ffgpu.h")]
 
 
-def build(force=False, verbose=False, variant=None, defines=()):
-    """variant/defines: development builds for A/B runs (build/libffgpu_<variant>.so, loaded
-    through the FFGPU_LIB environment variable); the product is the plain build"""
-    global OUT
+def build(force=False, verbose=False, variant=None, defines=(), csrc=None):
+    """variant/defines/csrc: development builds for A/B runs (build/libffgpu_<variant>.so,
+    loaded through the FFGPU_LIB environment variable); the product is the plain build"""
+    global OUT, CSRC
     if variant:
-        saved = OUT
+        saved = OUT, CSRC
         OUT = os.path.join(HERE, "build", "libffgpu_%s.so" % variant)
+        CSRC = csrc or CSRC
         try:
             return _build(True, verbose, "build/" + variant, list(defines))
         finally:
-            OUT = saved
+            OUT, CSRC = saved
     return _build(force, verbose, "build", [])
 
 

@@ -2175,6 +2175,25 @@ extern "C" int ffgpu_ffv1_decode_device(ffgpu_decoder *d, const uint8_t *const *
     CK(cudaEventSynchronize(j->done));
     j->n = 0;
     j->pkt_used = 0;
+    {
+        /* the whole batch goes into one launch: size the packet arena for it (incompressible
+         * pictures pack to about their raw size, the default arena assumes half of it) */
+        size_t need = 256;
+        for (int i = 0; i < nframes; i++)
+            need += align_up(sizes[i], 16) + 64;
+        if (need > 0xFFFF0000u)
+            return fail(FFGPU_ENOSPC, "packets of the batch exceed 4 GiB: use smaller batches");
+        if (need > j->pkt_cap) {
+            cudaFreeHost(j->h_pkt);
+            cudaFree(j->d_pkt);
+            j->h_pkt = j->d_pkt = NULL;
+            j->pkt_cap = align_up(need + need / 8, 4096);
+            if (j->pkt_cap > 0xFFFF0000u)
+                j->pkt_cap = 0xFFFF0000u;
+            CK(cudaHostAlloc(&j->h_pkt, j->pkt_cap, cudaHostAllocDefault));
+            CK(cudaMalloc(&j->d_pkt, j->pkt_cap));
+        }
+    }
     for (int i = 0; i < nframes; i++) {
         r = dec_add_packet(d, j, pkts[i], sizes[i], 0, NULL);
         if (r == FFGPU_EAGAIN)

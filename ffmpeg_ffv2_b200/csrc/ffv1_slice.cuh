@@ -394,15 +394,11 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
     int cur_ctx = -1;
     int e = 0, step = 0, nsteps = 0;
     uint64_t seq = 0;                                /* bit k = value of decision k of the residual */
-    /* the adaptive state of the coming decision, and the current row's slot 0 (the zero
-     * flag), in registers: see ff_decode_slice_range_planar */
-    uint32_t sreg = 128, s0 = 128;
-    int slot = 0;
     (void)tab_; (void)row_;
 
 #if defined(__CUDA_ARCH__)
     uint32_t row_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_rows[threadIdx.x * FF_ROW_WORDS]);
-    uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(ff_s_tab16);
+    uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_tab);
     uint32_t stab_sa = (uint32_t)__cvta_generic_to_shared(ff_s_stab);
     /* a shuffle from the own lane is opaque to ptxas: otherwise it rematerialises the
      * shared-window base (S2R CgaCtaId + shifts, a dozen instructions) in front of every
@@ -410,23 +406,13 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
     row_sa = ff_opaque(row_sa);
     tab_sa = ff_opaque(tab_sa);
     stab_sa = ff_opaque(stab_sa);
-    uint32_t srow = stab_sa;
-#define FF_ST_LD(sl) ff_lds8(row_sa + (uint32_t)(sl))
-#define FF_ST_ST(sl, v) ff_sts8(row_sa + (uint32_t)(sl), (v))
-#define FF_TAB16(st) ff_lds16u(tab_sa + 2u * (st))
-#define FF_SLOT_AT(st) ((int)ff_lds8(srow + (uint32_t)(st)))
+    uint32_t srow = stab_sa, slot = 0;
     const uint32_t nchunks = (n + 3) >> 2;
     for (uint32_t ch = 0; ch < FF_TOK_AHEAD; ch++) {
         if (ch < nchunks)
             ff_cp_async16(&ff_s_tok[ch * FF_CODE_THREADS + threadIdx.x], tokens + 4 * ch);
         ff_cp_async_commit();
     }
-#endif
-#if !defined(__CUDA_ARCH__)
-#define FF_ST_LD(sl) ((uint32_t)FF_ROWB(sl))
-#define FF_ST_ST(sl, v) (FF_ROWB(sl) = (uint8_t)(v))
-#define FF_TAB16(st) ((uint32_t)FF_TAB(st) | ((uint32_t)FF_TAB(256 + (st)) << 8))
-#define FF_SLOT_AT(st) ff_slot_of(e, (st))
 #endif
     ff_enc_resume(&c, pre, pre_bytes, out, sl.bs_cap);
     for (;;) {
@@ -454,12 +440,9 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
             ctx = (int)(tok & FF_TOKEN_CTX_MASK);
             diff = (int32_t)tok >> FF_TOKEN_CTX_BITS;
             if (ctx != cur_ctx) {
-                if (cur_ctx >= 0) {
-                    FF_ST_ST(0, s0);
+                if (cur_ctx >= 0)
                     ff_row_store(FF_ROWW, state + (size_t)cur_ctx * FF_CONTEXT_SIZE);
-                }
                 ff_row_load(FF_ROWW, state + (size_t)ctx * FF_CONTEXT_SIZE);
-                s0 = FF_ST_LD(0);
                 cur_ctx = ctx;
             }
             a = (uint32_t)(diff < 0 ? -diff : diff);
@@ -485,42 +468,38 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
             step = 0;
 #if defined(__CUDA_ARCH__)
             srow = stab_sa + (uint32_t)e * FF_STAB_STRIDE;
-#endif
             slot = 0;
-            sreg = s0;
+#endif
         }
         bit = (int)(seq & 1);
         seq >>= 1;
+#if defined(__CUDA_ARCH__)
         {
-            const uint32_t t16 = FF_TAB16(sreg);     /* both successor states, fetched early */
-            const uint32_t ns = bit ? (t16 & 0xFFu) : (t16 >> 8);
-            s = (int)sreg;
+            const uint32_t sa = row_sa + slot;
+            s = (int)ff_lds8(sa);
             r1 = (c.range * s) >> 8;                 /* put_rac, rangecoder.h:104-121 */
             rb = c.range - r1;
-            if (slot == 0)
-                s0 = ns;
-            else
-                FF_ST_ST(slot, ns);
+            ff_sts8(sa, ff_lds8(tab_sa + (uint32_t)s + (bit ? 0u : 256u)));
             step++;
-            if (step < nsteps) {                     /* slot and state of the next decision */
-                const int nslot = FF_SLOT_AT(step);
-                sreg = nslot == slot ? ns : FF_ST_LD(nslot);
-                slot = nslot;
-            }
+            slot = ff_lds8(srow + (uint32_t)step);   /* slot of the next decision */
         }
+#else
+        {
+            const int slot = ff_slot_of(e, step);
+            s = FF_ROWB(slot);
+            r1 = (c.range * s) >> 8;
+            rb = c.range - r1;
+            FF_ROWB(slot) = FF_TAB(s + (bit ? 0 : 256));
+            step++;
+        }
+#endif
         c.low += bit ? rb : 0;
         c.range = bit ? r1 : rb;
         if (c.range < 0x100)
             ffrac_enc_shift1(&c);
     }
-    if (cur_ctx >= 0) {
-        FF_ST_ST(0, s0);
+    if (cur_ctx >= 0)
         ff_row_store(FF_ROWW, state + (size_t)cur_ctx * FF_CONTEXT_SIZE);
-    }
-#undef FF_ST_LD
-#undef FF_ST_ST
-#undef FF_TAB16
-#undef FF_SLOT_AT
     nb = ffrac_enc_finish(&c, tab_, 1);              /* ffv1enc.c:1242 */
     *overflow = c.overflow;
     return nb;

@@ -190,7 +190,10 @@ static int gpu_receive_packet(AVCodecContext *avctx, AVPacket *pkt)
             av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
         return ret;
     }
-    if ((ret = ff_alloc_packet2(avctx, pkt, size, 0)) < 0)
+    /* a refcounted packet of exactly that size: avcodec_receive_packet hands it on as it is
+     * (libavcodec/encode.c:434-438), there is no encode2 wrapper that would copy it out of
+     * the shared byte_buffer ff_alloc_packet2 may return */
+    if ((ret = av_new_packet(pkt, size)) < 0)
         return ret;
     ret = ffgpu_ffv1_encode_receive_packet(s->enc, pkt->data, pkt->size, &size, &key, &pts);
     if (ret < 0) {
