@@ -397,6 +397,8 @@ struct EncJob {
     uint32_t *d_weight, *d_weight_sorted, *d_order;
     void *d_sort_tmp;
     size_t sort_tmp_bytes;
+    int *d_rct;                 /* version 4: RCT coefficients per (picture, slice) */
+    int32_t *d_rct_stat;
     int pkt_owned;
     /* pinned host */
     uint8_t *h_frame_set, *h_frame_key;
@@ -460,6 +462,7 @@ static int enc_free_job(EncJob *j)
         cudaFree(j->d_pkt);
     cudaFree(j->d_frame_set); cudaFree(j->d_frame_key);
     cudaFree(j->d_weight); cudaFree(j->d_weight_sorted); cudaFree(j->d_order); cudaFree(j->d_sort_tmp);
+    cudaFree(j->d_rct); cudaFree(j->d_rct_stat);
     cudaFreeHost(j->h_frame_set); cudaFreeHost(j->h_frame_key); cudaFreeHost(j->h_pkt_size);
     cudaFreeHost(j->h_pkt_off); cudaFreeHost(j->h_overflow); cudaFreeHost(j->h_pkt);
     cudaFreeHost(j->h_stage);
@@ -542,6 +545,10 @@ static int enc_device_init(ffgpu_encoder *e)
         CK(cudaMalloc(&j->d_order, B * P->nslices * sizeof(uint32_t)));
         j->sort_tmp_bytes = ffk_sort_tmp_bytes((int)(B * P->nslices));
         CK(cudaMalloc(&j->d_sort_tmp, j->sort_tmp_bytes));
+        if (P->version > 3) {
+            CK(cudaMalloc(&j->d_rct, B * P->nslices * 2 * sizeof(int)));
+            CK(cudaMalloc(&j->d_rct_stat, B * P->nslices * 16 * sizeof(int32_t)));
+        }
         CK(cudaMalloc(&j->d_frame_set, B));
         CK(cudaMalloc(&j->d_frame_key, B));
         CK(cudaHostAlloc(&j->h_frame_set, B, cudaHostAllocDefault));
@@ -756,6 +763,8 @@ static void enc_fill_dev(const ffgpu_encoder *e, const EncJob *j, const uint8_t 
     E->sort_tmp = j->d_sort_tmp;
     E->sort_tmp_bytes = j->sort_tmp_bytes;
     E->lane_stride = coder_lane_stride((long)j->n * e->P.nslices);
+    E->rct = j->d_rct;
+    E->rct_stat = j->d_rct_stat;
 }
 
 /* enqueue the kernel chain + result download of a filled group */

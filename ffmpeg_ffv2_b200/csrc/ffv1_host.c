@@ -349,8 +349,19 @@ int ff_stream_from_options(FFStream *s, const ffgpu_enc_options *o)
     if ((unsigned)o->context > 1U)
         return FFGPU_EINVAL;
     s->context_model = o->context;
-    if (s->version == 2 || s->version > 3)
-        return FFGPU_ENOSYS;               /* v2/v4 bitstreams: SURVEY 8f-2, not built yet */
+    if (s->version == 2)
+        return FFGPU_ENOSYS;               /* the abandoned experimental version 2 bitstream */
+    if (s->version > 3) {
+        /* Version 4: every slice header carries the coefficients
+         * choose_rct_params (ffv1enc.c:963-1043) picks -- also for YCbCr input, where that
+         * function reads the planes as if they were RGB, outside the chroma planes and, for
+         * 8-bit input, across row ends: its result then depends on memory the encoder does
+         * not own, so no second implementation can reproduce the packets.  RGB layouts whose
+         * planes it reads in bounds are supported; packed 16-bit RGB dereferences the NULL
+         * plane pointers there. */
+        if (s->colorspace != 1 || pf->layout == FF_LAY_RGB48)
+            return FFGPU_ENOSYS;
+    }
 
     /* transition table, ffv1enc.c:720-728 */
     if (ac == FF_AC_CUSTOM)
@@ -603,8 +614,8 @@ int ff_parse_extradata(FFStream *s, const uint8_t *data, int size)
         if (ff_crc32(0, data, (size_t)size) || size < 4)
             return FFGPU_INVALIDDATA;      /* "CRC mismatch" */
     }
-    if (s->version > 3)
-        return FFGPU_ENOSYS;               /* v4 slice features: SURVEY 8f-2 */
+    if (s->version > 4)
+        return FFGPU_ENOSYS;
     s->cur_tab = s->def_tab;
     if (s->ac == FF_AC_CUSTOM)
         ff_install_custom(&s->cur_tab, s->trans);
@@ -849,8 +860,12 @@ int ff_enc_slice_prefix(const FFStream *s, int i, const FFSliceRect *r, int key_
         ffrac_put_symbol(&c, t, st, picture_structure, 0);
         ffrac_put_symbol(&c, t, st, sar_num, 0);
         ffrac_put_symbol(&c, t, st, sar_den, 0);
+        memcpy(pre->hdr_state, st, sizeof(st));
     }
-    if (s->ac == FF_AC_GOLOMB) {
+    if (s->version > 3) {
+        /* the device continues the header (and closes the coder of Golomb-Rice slices) */
+        pre->nbytes = c.pos;
+    } else if (s->ac == FF_AC_GOLOMB) {
         /* ffv1enc.c:1076-1081: the coder is closed, Rice bits start on the next byte */
         uint32_t n = 0;
         if (s->version > 2 || (!r->x && !r->y))
@@ -1023,7 +1038,8 @@ int ff_dec_parse_packet(FFStream *s, FFDecHostState *hs, const uint8_t *pkt, siz
         FFSliceRect rc;
         int j;
 
-        if (i && hs->device_parse && s->version > 2) {
+        d->rct_by = d->rct_ry = 1;             /* ffv1dec.c:290-291 */
+        if (i && hs->device_parse && s->version == 3) {
             /* the decode kernel checks the CRC, parses the slice header and positions the
              * coder itself (ff_dec_slice_header); until it reports back the rectangle of
              * the regular grid stands in */
@@ -1088,6 +1104,24 @@ int ff_dec_parse_packet(FFStream *s, FFDecHostState *hs, const uint8_t *pkt, siz
             }
             info->sar_num = ffrac_get_symbol(&c, t, st, 0);
             info->sar_den = ffrac_get_symbol(&c, t, st, 0);
+            if (s->version > 3) {
+                /* ffv1dec.c:230-241 */
+                if (ffrac_get(&c, t, st))      /* slice_reset_contexts */
+                    d->key_frame = 1;
+                d->pcm = ffrac_get_symbol(&c, t, st, 0) == 1;
+                if (!d->pcm) {
+                    d->rct_by = ffrac_get_symbol(&c, t, st, 0);
+                    d->rct_ry = ffrac_get_symbol(&c, t, st, 0);
+                    if ((uint64_t)(unsigned)d->rct_by + (uint64_t)(unsigned)d->rct_ry > 4) {
+                        /* "slice_rct_y_coef out of range": decode_slice_header fails */
+                        rc.x = rc.y = rc.w = rc.h = 0;
+                        d->skip = 1;
+                        hs->damaged[i] = 1;
+                        hs->rect[i] = rc;
+                        continue;
+                    }
+                }
+            }
         } else {
             ff_slice_rect(s, i, &rc);
         }

@@ -45,11 +45,56 @@ static inline void mark(void **events, int i, cudaStream_t st)
         cudaEventRecord((cudaEvent_t)events[i], st);
 }
 
+/* ---------------- version 4: per-slice RCT coefficients ---------------- */
+/* choose_rct_params (ffv1enc.c:963-1043) as a reduction: every thread sums the 15 candidate
+ * magnitudes of its pixels, the block reduces them, one atomic per candidate and block. */
+__global__ void __launch_bounds__(SYM_THREADS)
+k_rct_stat(const FFDevParams P, const FFDevSlice *__restrict__ slices,
+           const uint8_t *__restrict__ frames, int32_t *__restrict__ stat)
+{
+    typedef cub::BlockReduce<int32_t, SYM_THREADS> Reduce;
+    __shared__ typename Reduce::TempStorage tmp;
+    const FFDevSlice sl = slices[blockIdx.x];
+    const uint8_t *frame = frames + (size_t)blockIdx.y * P.frame_bytes;
+    const int w1 = sl.w - 1, h1 = sl.h - 1;          /* pixels with x >= 1 and y >= 1 */
+    int32_t acc[FF_RCT_CANDIDATES];
+    for (int i = 0; i < FF_RCT_CANDIDATES; i++)
+        acc[i] = 0;
+    if (w1 > 0 && h1 > 0) {
+        const uint32_t n = (uint32_t)w1 * h1;
+        for (uint32_t i = blockIdx.z * SYM_THREADS + threadIdx.x; i < n; i += gridDim.z * SYM_THREADS) {
+            int32_t v[FF_RCT_CANDIDATES];
+            const int y = (int)(i / (uint32_t)w1), x = (int)(i - (uint32_t)y * w1);
+            ff_rct_pixel_stat(P, frame, sl.x, sl.y, x + 1, y + 1, v);
+            for (int k = 0; k < FF_RCT_CANDIDATES; k++)
+                acc[k] = (int32_t)((uint32_t)acc[k] + (uint32_t)v[k]);
+        }
+    }
+    int32_t *out = stat + ((size_t)blockIdx.y * P.nslices + blockIdx.x) * 16;
+    for (int k = 0; k < FF_RCT_CANDIDATES; k++) {
+        const int32_t sum = Reduce(tmp).Sum(acc[k]);
+        __syncthreads();
+        if (threadIdx.x == 0 && sum)
+            atomicAdd(&out[k], sum);
+    }
+}
+
+__global__ void k_rct_pick(const int32_t *__restrict__ stat, int *__restrict__ rct, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    int by, ry;
+    ff_rct_pick(stat + (size_t)i * 16, &by, &ry);
+    rct[2 * i] = by;
+    rct[2 * i + 1] = ry;
+}
+
 /* ---------------- stage A ---------------- */
 __global__ void __launch_bounds__(SYM_THREADS)
 k_symbolize(const FFDevParams P, const FFDevSlice *__restrict__ slices,
             const uint8_t *__restrict__ frames, const int16_t *__restrict__ qt,
-            uint32_t *__restrict__ tokens, uint32_t *__restrict__ weight)
+            uint32_t *__restrict__ tokens, uint32_t *__restrict__ weight, const int *__restrict__ rct)
 {
     typedef cub::BlockReduce<uint32_t, SYM_THREADS> Reduce;
     __shared__ typename Reduce::TempStorage tmp;
@@ -57,8 +102,10 @@ k_symbolize(const FFDevParams P, const FFDevSlice *__restrict__ slices,
     const uint8_t *frame = frames + (size_t)blockIdx.y * P.frame_bytes;
     uint32_t *tok = tokens + (size_t)blockIdx.y * P.frame_tokens + sl.tok_off;
     uint32_t wsum = 0;
+    const int *rc = rct ? rct + 2 * ((size_t)blockIdx.y * P.nslices + blockIdx.x) : (const int *)0;
+    const int by = rc ? rc[0] : 1, ry = rc ? rc[1] : 1;
     for (uint32_t i = blockIdx.z * SYM_THREADS + threadIdx.x; i < sl.ntok; i += gridDim.z * SYM_THREADS) {
-        const uint32_t t = ff_symbolize_index(P, sl, frame, qt, i);
+        const uint32_t t = ff_symbolize_index(P, sl, frame, qt, i, by, ry);
         tok[i] = t;
         wsum += ff_token_weight(t);
     }
@@ -265,7 +312,8 @@ k_code_range(const FFDevParams P, const FFEncDev E, int nframes)
         sl, E.tokens + (size_t)f * P.frame_tokens + sl.tok_off,
         E.state + st_slot * P.total_ctx * FF_CONTEXT_SIZE, &ff_s_tab,
         E.prefix[(size_t)E.frame_prefix_set[f] * P.nslices + s], E.prefix_bytes,
-        E.bs + (size_t)f * P.frame_bs + sl.bs_off, &ovf, 0);
+        E.bs + (size_t)f * P.frame_bs + sl.bs_off, &ovf, 0, E.rct ? E.rct + 2 * (size_t)gid : (const int *)0,
+        E.rct ? (uint32_t)((16384 + (int64_t)P.width * P.height * 12) / P.nslices) : 0u);
     E.slice_bytes[gid] = n;
     if (ovf)
         atomicOr(E.overflow, 1u);
@@ -291,7 +339,8 @@ k_code_golomb(const FFDevParams P, const FFEncDev E, int nframes)
         P, sl, E.tokens + (size_t)f * P.frame_tokens + sl.tok_off,
         (uint2 *)E.state + st_slot * P.total_ctx,
         E.prefix[(size_t)E.frame_prefix_set[f] * P.nslices + s], E.prefix_bytes,
-        E.bs + (size_t)f * P.frame_bs + sl.bs_off, &ovf);
+        E.bs + (size_t)f * P.frame_bs + sl.bs_off, &ovf, E.tab,
+        E.rct ? E.rct + 2 * (size_t)gid : (const int *)0);
     E.slice_bytes[gid] = n;
     if (ovf)
         atomicOr(E.overflow, 1u);
@@ -392,7 +441,15 @@ extern "C" int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nfr
             }
 #undef SYM_LAUNCH
         } else {
-            k_symbolize<<<grid, SYM_THREADS, 0, st>>>(*P, E->slices, E->frames, E->qt, E->tokens, E->weight);
+            if (E->rct) {
+                /* version 4: the RCT coefficients of every slice first */
+                const int n = nframes * P->nslices;
+                cudaMemsetAsync(E->rct_stat, 0, sizeof(int32_t) * 16 * (size_t)n, st);
+                k_rct_stat<<<grid, SYM_THREADS, 0, st>>>(*P, E->slices, E->frames, E->rct_stat);
+                k_rct_pick<<<(n + 255) / 256, 256, 0, st>>>(E->rct_stat, E->rct, n);
+                launches += 2;
+            }
+            k_symbolize<<<grid, SYM_THREADS, 0, st>>>(*P, E->slices, E->frames, E->qt, E->tokens, E->weight, E->rct);
         }
         mark(E->events, FFK_SYMBOLIZE + 1, st);
         launches++;
@@ -583,6 +640,10 @@ k_decode(const FFDevParams P, const FFDecDev D, int nframes)
         if (live)
             ff_decode_slice(P, w, D.pkt, C, &r, 0);
     } else {
+        if (live && w.pcm) {                         /* version 4 PCM slice: the plain way */
+            ff_decode_slice_pcm(P, w, D.pkt, C, &r);
+            live = false;
+        }
         __syncwarp();
         ff_decode_slice_range_planar<SMODE ? SMODE : 1, FIVE>(P, w, D.pkt, C, &r, 0, live);
     }
@@ -609,7 +670,7 @@ extern "C" int ffk_decode_group(const FFDevParams *P, const FFDecDev *D, int nfr
     if (D->touched) {
         /* states are created on first touch inside k_decode: clear the touched bits only */
         cudaMemsetAsync(D->touched, 0, (size_t)total * D->touched_words * sizeof(uint32_t), st);
-    } else if (!D->initial &&
+    } else if (!D->initial && P->version < 4 &&
         ((size_t)D->max_slices * P->total_ctx * (P->ac == FF_AC_GOLOMB ? 8 : FF_CONTEXT_SIZE)) % 16 == 0) {
         const int golomb = P->ac == FF_AC_GOLOMB;
         const size_t vec = (size_t)D->max_slices * P->total_ctx * (golomb ? 8 : FF_CONTEXT_SIZE) / 16;

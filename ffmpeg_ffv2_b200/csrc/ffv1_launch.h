@@ -43,6 +43,9 @@ typedef struct FFEncDev {
     void *sort_tmp;
     size_t sort_tmp_bytes;
     int lane_stride;                /* slice coders: 1 = every lane codes a slice ... 32 = one per warp */
+    /* version 4: slice_rct_by/ry_coef per (frame, slice), chosen on the device */
+    int *rct;                       /* [nframes][nslices][2] or NULL (version <= 3)      */
+    int32_t *rct_stat;              /* [nframes][nslices][16] scratch of the reduction   */
     void **events;                  /* optional cudaEvent_t[FFK_ENC_KERNELS + 1]: recorded    */
                                     /* before the first and after every kernel (profiling)  */
 } FFEncDev;

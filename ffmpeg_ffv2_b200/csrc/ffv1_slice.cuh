@@ -68,7 +68,8 @@ FFGPU_HD int ff_rd16(const uint8_t *p)
 /* coded sample of plane k at absolute position (X,Y) of that plane's grid, already wrapped
  * to the coder's sample type (int16 unless use32).  encode_plane ffv1enc.c:291-305,
  * encode_rgb_frame ffv1enc_template.c:150-186. */
-FFGPU_HD int ff_coded_sample(const FFDevParams &P, const uint8_t *frame, int k, int X, int Y)
+FFGPU_HD int ff_coded_sample(const FFDevParams &P, const uint8_t *frame, int k, int X, int Y,
+                             int rct_by = 1, int rct_ry = 1)
 {
     if (P.colorspace == 0) {
         const FFDevPlane cp = P.cp[k];
@@ -110,7 +111,7 @@ FFGPU_HD int ff_coded_sample(const FFDevParams &P, const uint8_t *frame, int k, 
         } else {
             b -= g;
             r -= g;
-            g += (b + r) >> 2;                  /* slice_rct_by_coef = slice_rct_ry_coef = 1 */
+            g += (b * rct_by + r * rct_ry) >> 2;   /* slice_rct_by/ry_coef: 1, 1 before version 4 */
             v = k == 0 ? g : (k == 1 ? b : r) + (1 << P.sbits);
         }
         return P.use32 ? v : (int)(int16_t)v;
@@ -128,9 +129,9 @@ FFGPU_HD int ff_coded_sample(const FFDevParams &P, const uint8_t *frame, int k, 
  * Neighbours never cross the slice border.  Returns the token. */
 FFGPU_HD uint32_t ff_symbolize_sample(const FFDevParams &P, const uint8_t *frame,
                                       const int16_t *qt, int k, int X0, int Y0, int w,
-                                      int x, int y, int ctx_base)
+                                      int x, int y, int ctx_base, int rct_by = 1, int rct_ry = 1)
 {
-#define S_(xx, yy) ((yy) < 0 ? 0 : ff_coded_sample(P, frame, k, X0 + (xx), Y0 + (yy)))
+#define S_(xx, yy) ((yy) < 0 ? 0 : ff_coded_sample(P, frame, k, X0 + (xx), Y0 + (yy), rct_by, rct_ry))
     const int cur = S_(x, y);
     const int T   = S_(x, y - 1);
     const int L   = x ? S_(x - 1, y) : T;
@@ -153,10 +154,78 @@ FFGPU_HD uint32_t ff_symbolize_sample(const FFDevParams &P, const uint8_t *frame
     return ((uint32_t)diff << FF_TOKEN_CTX_BITS) | (uint32_t)(ctx_base + ctx);
 }
 
+/* choose_rct_params, ffv1enc.c:963-1043 (version 4): for every pixel with x >= 1 and y >= 1 of
+ * the slice the second difference (horizontal, then vertical) of the three components, and
+ * for each of 15 candidate coefficient pairs the magnitude the luma-like component would
+ * have.  The reference walks the slice with a line buffer; the differences only involve the
+ * pixel and its left, upper and upper-left neighbours, so every pixel is independent here.
+ * NOTE the component naming is the reference's: for the planar layouts it calls plane 0
+ * "b", plane 1 "g" and plane 2 "r" (:1000-1002) whatever the planes hold.
+ * Returns the 15 magnitudes of pixel (x, y) of the slice at (X0, Y0). */
+#define FF_RCT_CANDIDATES 15
+FFGPU_HD void ff_rct_candidates(int i, int *ry, int *by)
+{
+    /* rct_y_coeff[15][2] of ffv1enc.c:966-984, {ry, by} */
+    const int t[FF_RCT_CANDIDATES][2] = { {0, 0}, {1, 1}, {2, 2}, {0, 2}, {2, 0}, {4, 0}, {0, 4}, {0, 3},
+                                          {3, 0}, {3, 1}, {1, 3}, {1, 2}, {2, 1}, {0, 1}, {1, 0} };
+    *ry = t[i][0];
+    *by = t[i][1];
+}
+
+FFGPU_HD void ff_rct_load_bgr(const FFDevParams &P, const uint8_t *frame, int X, int Y, int *b, int *g, int *r)
+{
+    if (P.layout == FF_LAY_BGR32) {
+        const uint8_t *p = frame + P.plane_off[0] + (size_t)Y * P.pitch[0] + (size_t)X * 4;
+        *b = p[0]; *g = p[1]; *r = p[2];
+    } else {
+        *b = ff_rd16(frame + P.plane_off[0] + (size_t)Y * P.pitch[0] + (size_t)X * 2);
+        *g = ff_rd16(frame + P.plane_off[1] + (size_t)Y * P.pitch[1] + (size_t)X * 2);
+        *r = ff_rd16(frame + P.plane_off[2] + (size_t)Y * P.pitch[2] + (size_t)X * 2);
+    }
+}
+
+FFGPU_HD void ff_rct_pixel_stat(const FFDevParams &P, const uint8_t *frame, int X0, int Y0, int x, int y,
+                                int32_t stat[FF_RCT_CANDIDATES])
+{
+    int b[4], g[4], r[4];                  /* (x,y) (x-1,y) (x,y-1) (x-1,y-1) */
+    int bg, bb, br;
+    /* the left neighbour of x == 1 is pixel 0 of the line: lastr/lastg/lastb only restart
+     * from 0 for x == 0 itself (:990), which contributes nothing */
+    ff_rct_load_bgr(P, frame, X0 + x, Y0 + y, &b[0], &g[0], &r[0]);
+    ff_rct_load_bgr(P, frame, X0 + x - 1, Y0 + y, &b[1], &g[1], &r[1]);
+    ff_rct_load_bgr(P, frame, X0 + x, Y0 + y - 1, &b[2], &g[2], &r[2]);
+    ff_rct_load_bgr(P, frame, X0 + x - 1, Y0 + y - 1, &b[3], &g[3], &r[3]);
+    /* the previous line's differences went through the int16_t line buffer (:987, :1023-1025):
+     * they wrap for 16-bit samples */
+    bg = (g[0] - g[1]) - (int)(int16_t)(g[2] - g[3]);
+    bb = (b[0] - b[1]) - (int)(int16_t)(b[2] - b[3]);
+    br = (r[0] - r[1]) - (int)(int16_t)(r[2] - r[3]);
+    br -= bg;
+    bb -= bg;
+    for (int i = 0; i < FF_RCT_CANDIDATES; i++) {
+        int cy, cb, v;
+        ff_rct_candidates(i, &cy, &cb);
+        v = bg + ((br * cy + bb * cb) >> 2);
+        stat[i] = v < 0 ? -v : v;
+    }
+}
+
+/* the winner: the first candidate with the smallest sum (the sums are `int` in the
+ * reference and wrap the same way here) */
+FFGPU_HD void ff_rct_pick(const int32_t stat[FF_RCT_CANDIDATES], int *by, int *ry)
+{
+    int best = 0;
+    for (int i = 1; i < FF_RCT_CANDIDATES; i++)
+        if (stat[i] < stat[best])
+            best = i;
+    ff_rct_candidates(best, ry, by);
+}
+
 /* token index -> (plane, x, y) and the token itself; tokens are laid out in CODING order:
  * YCbCr plane after plane, RGB line-interleaved G,B,R[,A] (ffv1enc_template.c:188-198) */
 FFGPU_HD uint32_t ff_symbolize_index(const FFDevParams &P, const FFDevSlice &sl,
-                                     const uint8_t *frame, const int16_t *qt_all, uint32_t idx)
+                                     const uint8_t *frame, const int16_t *qt_all, uint32_t idx,
+                                     int rct_by = 1, int rct_ry = 1)
 {
     int k, x, y, w;
     if (P.colorspace == 0) {
@@ -181,7 +250,7 @@ FFGPU_HD uint32_t ff_symbolize_index(const FFDevParams &P, const FFDevSlice &sl,
         const FFDevPlane cp = P.cp[k];
         const int16_t *qt = qt_all + (size_t)P.set_qidx[cp.set] * FF_QT_STRIDE;
         return ff_symbolize_sample(P, frame, qt, k, sl.x >> cp.hs, sl.y >> cp.vs, w, x, y,
-                                   P.set_base[cp.set]);
+                                   P.set_base[cp.set], rct_by, rct_ry);
     }
 }
 
@@ -201,6 +270,25 @@ FFGPU_HD void ff_enc_resume(FFRacEnc *c, const FFRacPrefix &pre, const uint8_t *
     c->range = pre.range;
     c->pending = pre.pending;
     c->run = pre.run;
+}
+
+/* The part of a version 4 slice header that depends on the picture (ffv1enc.c:951-959):
+ * slice_coding_mode == 1 flag, the coding mode (always 0: PCM slices are the reference's
+ * answer to an overflowing packet buffer, which this encoder reports as an error instead)
+ * and the two RCT coefficients, coded with the header's adaptive states the host handed
+ * over.  Golomb-Rice slices then close the coder (ffv1enc.c:1076-1081); returns where the
+ * Rice bits start in that case. */
+FFGPU_HD uint32_t ff_enc_v4_header_tail(FFRacEnc *c, const FFRacTables *t, const FFRacPrefix &pre,
+                                        int rct_by, int rct_ry, int golomb)
+{
+    uint8_t st[FF_CONTEXT_SIZE];
+    for (int i = 0; i < FF_CONTEXT_SIZE; i++)
+        st[i] = pre.hdr_state[i];
+    ffrac_put(c, t, st, 0);
+    ffrac_put_symbol(c, t, st, 0, 0);
+    ffrac_put_symbol(c, t, st, rct_by, 0);
+    ffrac_put_symbol(c, t, st, rct_ry, 0);
+    return golomb ? ffrac_enc_finish(c, t, 1) : 0;
 }
 
 /* ---- per-thread cache of the current context's 32 adaptive state bytes ----
@@ -386,15 +474,26 @@ __device__ __forceinline__ void ff_sts8(uint32_t sa, uint32_t v)
 FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *tokens,
                                         uint8_t *state, const FFRacTables *tab_,
                                         const FFRacPrefix &pre, const uint8_t *pre_bytes,
-                                        uint8_t *out, uint32_t *overflow, uint32_t *row_)
+                                        uint8_t *out, uint32_t *overflow, uint32_t *row_,
+                                        const int *rct = 0,     /* version 4: {by, ry} of the slice */
+                                        uint32_t v4_room = 0)   /* version 4: the reference's slice buffer */
 {
     FFRacEnc c;
     const uint32_t n = sl.ntok;
+    /* Version 4 gives every slice (16384 + 12 * width * height) / slice_count bytes
+     * (ffv1enc.c:1180-1181, :1221-1224) and encode_line gives up when fewer than 35 * w are
+     * left at the start of a line (ffv1enc_template.c:33-37); the reference then rewrites the
+     * slice as raw "PCM" bits (:1107-1117).  The byte count only grows, so the guard fires
+     * iff it fires at the start of the LAST line: remember the count there.  This encoder
+     * does not write PCM slices; it reports "encoded frame too large" where the reference
+     * would have written one, instead of silently producing a different packet. */
+    const uint32_t guard_tok = v4_room ? n - (uint32_t)sl.seg_w[sl.nseg - 1] : 0xFFFFFFFFu;
+    uint32_t guard_pos = 0;
     uint32_t i = 0, nb;
     int cur_ctx = -1;
     int e = 0, step = 0, nsteps = 0;
     uint64_t seq = 0;                                /* bit k = value of decision k of the residual */
-    (void)tab_; (void)row_;
+    (void)row_;
 
 #if defined(__CUDA_ARCH__)
     uint32_t row_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_rows[threadIdx.x * FF_ROW_WORDS]);
@@ -415,6 +514,8 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
     }
 #endif
     ff_enc_resume(&c, pre, pre_bytes, out, sl.bs_cap);
+    if (rct)
+        ff_enc_v4_header_tail(&c, tab_, pre, rct[0], rct[1], 0);
     for (;;) {
         int bit, s, r1, rb;
         if (step == nsteps) {                        /* fetch the next residual */
@@ -422,6 +523,8 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
             int ctx, diff;
             if (i == n)
                 break;
+            if (i == guard_tok)
+                guard_pos = c.pos;
 #if defined(__CUDA_ARCH__)
             if ((i & 3) == 0) {                      /* entering chunk i/4: issue chunk i/4 + AHEAD */
                 const uint32_t ch = (i >> 2) + FF_TOK_AHEAD;
@@ -502,6 +605,8 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
         ff_row_store(FF_ROWW, state + (size_t)cur_ctx * FF_CONTEXT_SIZE);
     nb = ffrac_enc_finish(&c, tab_, 1);              /* ffv1enc.c:1242 */
     *overflow = c.overflow;
+    if (v4_room && (int64_t)v4_room - (int64_t)guard_pos < (int64_t)sl.seg_w[sl.nseg - 1] * 35)
+        *overflow = 1;
     return nb;
 }
 
@@ -635,15 +740,23 @@ FFGPU_HD void ff_vlc_put(FFBitW *b, uint2 *sp, int v, int bits)
 FFGPU_HD uint32_t ff_encode_slice_golomb(const FFDevParams &P, const FFDevSlice &sl,
                                          const uint32_t *tokens, uint2 *vstate,
                                          const FFRacPrefix &pre, const uint8_t *pre_bytes,
-                                         uint8_t *out, uint32_t *overflow)
+                                         uint8_t *out, uint32_t *overflow,
+                                         const FFRacTables *tab = 0, const int *rct = 0)
 {
     FFBitW bw;
-    uint32_t i, t = 0;
+    uint32_t i, t = 0, start = pre.golomb_start;
     int seg;
-    for (i = 0; i < pre.nbytes && i < sl.bs_cap; i++)
-        out[i] = pre_bytes[pre.byte_off + i];
+    if (rct) {
+        /* version 4: the header is finished and its coder closed here (see FFRacPrefix) */
+        FFRacEnc c;
+        ff_enc_resume(&c, pre, pre_bytes, out, sl.bs_cap);
+        start = ff_enc_v4_header_tail(&c, tab, pre, rct[0], rct[1], 1);
+    } else {
+        for (i = 0; i < pre.nbytes && i < sl.bs_cap; i++)
+            out[i] = pre_bytes[pre.byte_off + i];
+    }
     bw.buf = out;
-    bw.pos = pre.golomb_start;
+    bw.pos = start;
     bw.cap = sl.bs_cap;
     bw.acc = 0;
     bw.nacc = 0;
@@ -938,18 +1051,20 @@ FFGPU_HD void ff_store_line_ycc(const FFDevParams &P, uint8_t *frame, int k, int
 /* decode_rgb_frame's inverse RCT + store, ffv1dec_template.c:160-190 */
 FFGPU_HD void ff_store_line_rgb(const FFDevParams &P, uint8_t *frame, int X0, int Y, int w,
                                 const int32_t *lg, const int32_t *lb, const int32_t *lr,
-                                const int32_t *la)
+                                const int32_t *la, int rct_by = 1, int rct_ry = 1, int pcm = 0)
 {
     const int offset = 1 << P.sbits;
     int x;
     for (x = 0; x < w; x++) {
         int g = lg[x], b = lb[x], r = lr[x];
         const int a = la ? la[x] : 0;
-        b -= offset;
-        r -= offset;
-        g -= (b + r) >> 2;
-        b += g;
-        r += g;
+        if (!pcm) {                                  /* ffv1dec_template.c:169-176 */
+            b -= offset;
+            r -= offset;
+            g -= (b * rct_by + r * rct_ry) >> 2;
+            b += g;
+            r += g;
+        }
         if (P.layout == FF_LAY_BGR32) {
             uint8_t *p = frame + P.plane_off[0] + (size_t)Y * P.pitch[0] + (size_t)(X0 + x) * 4;
             const uint32_t v = (uint32_t)b + ((uint32_t)g << 8) + ((uint32_t)r << 16) + ((uint32_t)a << 24);
@@ -1183,7 +1298,8 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
                         ff_store_line_rgb(P, D.frame, d.x, d.y + it.y, d.w,
                                           D.lines + o, D.lines + 2 * D.line_stride + o,
                                           D.lines + 4 * D.line_stride + o,
-                                          P.ncoded > 3 ? D.lines + 6 * D.line_stride + o : (const int32_t *)0);
+                                          P.ncoded > 3 ? D.lines + 6 * D.line_stride + o : (const int32_t *)0,
+                                          d.rct_by, d.rct_ry, 0);
                     }
                     if (!ff_line_next(P, d, &it))
                         break;
@@ -1399,7 +1515,8 @@ FFGPU_HD void ff_decode_slice_golomb(const FFDevParams &P, const FFDecSlice &d, 
                 ff_store_line_rgb(P, D.frame, d.x, d.y + y, d.w,
                                   D.lines + o, D.lines + 2 * D.line_stride + o,
                                   D.lines + 4 * D.line_stride + o,
-                                  P.ncoded > 3 ? D.lines + 6 * D.line_stride + o : (const int32_t *)0);
+                                  P.ncoded > 3 ? D.lines + 6 * D.line_stride + o : (const int32_t *)0,
+                                  d.rct_by, d.rct_ry, 0);
             }
         }
     }
@@ -1768,6 +1885,59 @@ FFGPU_HD void ff_decode_slice_range_planar(const FFDevParams &P, const FFDecSlic
     res->error = err;
 }
 
+/* A version 4 slice with slice_coding_mode == 1 ("PCM", decode_line ffv1dec_template.c:37-47):
+ * every sample is `bits` raw decisions, each with a fresh state of 128; no prediction, no
+ * contexts, no colour transform.  The reference encoder falls back to it when a slice
+ * outgrows its buffer (ffv1enc.c:1107-1117); such slices are rare and run the plain way. */
+FFGPU_HD void ff_decode_slice_pcm(const FFDevParams &P, const FFDecSlice &d, const uint8_t *pkt,
+                                  const FFDecCtx &D, FFDecResult *res)
+{
+    FFRacDec c;
+    FFLineIt it;
+    /* decode_rgb_frame: bits + (slice_coding_mode != 1) -> the raw depth; decode_plane: bits */
+    const int bits = P.colorspace ? P.sbits : P.cbits;
+    int err = 0;
+    c.buf = pkt + d.pkt_off;
+    c.low = d.low;
+    c.range = d.range;
+    c.pos = d.pos;
+    c.end = d.size;
+    c.overread = d.overread;
+    if (ff_line_first(P, d, &it)) {
+        do {
+            const int w = P.colorspace ? d.w : it.w;
+            int32_t *line = D.lines + (size_t)it.k * 2 * D.line_stride;
+            if (c.overread > 2) {                    /* is_input_end */
+                err = 1;
+                break;
+            }
+            for (int x = 0; x < w; x++) {
+                int v = 0;
+                for (int i = 0; i < bits; i++) {
+                    uint8_t st = 128;
+                    v += v + ffrac_get(&c, D.tab, &st);
+                }
+                line[x] = ff_wrap_sample(P, v);
+            }
+            if (P.colorspace == 0) {
+                const FFDevPlane cp = P.cp[it.k];
+                ff_store_line_ycc(P, D.frame, it.k, d.x >> cp.hs, (d.y >> cp.vs) + it.y, w, line);
+            } else if (it.k == P.ncoded - 1) {
+                ff_store_line_rgb(P, D.frame, d.x, d.y + it.y, d.w, D.lines, D.lines + 2 * D.line_stride,
+                                  D.lines + 4 * D.line_stride,
+                                  P.ncoded > 3 ? D.lines + 6 * D.line_stride : (const int32_t *)0, 1, 1, 1);
+            }
+        } while (ff_line_next(P, d, &it));
+    }
+    if (P.version > 2) {                             /* end-of-slice check, ffv1dec.c:351-359 */
+        uint8_t term = 129;
+        ffrac_get(&c, D.tab, &term);
+    }
+    res->end_pos = c.pos;
+    res->overread = c.overread;
+    res->error = err;
+}
+
 /* which specialisation of ff_decode_slice_range_planar serves the stream: 0 none (generic
  * path), 1 one byte per sample, 2 LSB-packed little-endian u16 */
 FFGPU_HD int ff_decode_planar_mode(const FFDevParams *P)
@@ -1782,7 +1952,9 @@ FFGPU_HD int ff_decode_planar_mode(const FFDevParams *P)
 FFGPU_HD void ff_decode_slice(const FFDevParams &P, const FFDecSlice &d, const uint8_t *pkt,
                               const FFDecCtx &D, FFDecResult *res, uint32_t *row)
 {
-    if (P.ac == FF_AC_GOLOMB) {
+    if (d.pcm) {
+        ff_decode_slice_pcm(P, d, pkt, D, res);
+    } else if (P.ac == FF_AC_GOLOMB) {
         ff_decode_slice_golomb(P, d, pkt, D, res);
     } else if (ff_decode_planar_mode(&P)) {
         /* planar YCbCr / gray (+alpha), 8-bit or LSB-packed 16-bit containers */

@@ -132,6 +132,11 @@ typedef struct FFRacPrefix {
     uint32_t byte_off;      /* offset of those bytes in the prefix byte arena         */
     uint32_t golomb_start;  /* Golomb: ac_byte_count, where the bit writer starts     */
     uint32_t pad;
+    /* version 4: the slice header goes on with per-slice values only the device knows
+     * (slice_rct_by/ry_coef from choose_rct_params, ffv1enc.c:951-959), so the host stops in
+     * front of them and hands over the header's adaptive states as well; the device also
+     * closes the coder of Golomb-Rice slices (ffv1enc.c:1076-1081) then */
+    uint8_t hdr_state[FF_CONTEXT_SIZE];
 } FFRacPrefix;
 
 /* decoder: per (frame, slice) work item produced by the host packet parser */
@@ -148,6 +153,10 @@ typedef struct FFDecSlice {
     uint32_t golomb_start;  /* Golomb: bit reader starts here (ac_byte_count)        */
     int parse;              /* 1: the device checks the CRC and parses the slice     */
                             /* header itself (slices 1..n-1 of v3 packets)           */
+    /* version 4 slice header, ffv1dec.c:230-241 (slice_reset_contexts is folded into
+     * key_frame: both mean "reset the adaptive states first", ffv1dec.c:304) */
+    int pcm;                /* slice_coding_mode == 1: raw bits, no prediction, no RCT */
+    int rct_by, rct_ry;     /* slice_rct_by_coef / slice_rct_ry_coef (1, 1 before v4) */
 } FFDecSlice;
 
 #define FF_RES_NOT_DECODED 1  /* absent or skipped work item                             */

@@ -101,10 +101,25 @@ extern "C" int ffv1emul_encode(void *h, const uint8_t *const planes[4], const in
     std::vector<FFRacPrefix> pre(P.nslices);
     e->prebytes.assign((size_t)P.nslices * 2048, 0);
     std::vector<uint32_t> bytes(P.nslices);
+    /* version 4: choose_rct_params per slice, one "thread" per pixel */
+    std::vector<int> rct((size_t)P.nslices * 2, 1);
+    if (P.version > 3)
+        for (int i = 0; i < P.nslices; i++) {
+            int32_t stat[FF_RCT_CANDIDATES] = { 0 };
+            for (int y = 1; y < e->sl[i].h; y++)
+                for (int x = 1; x < e->sl[i].w; x++) {
+                    int32_t v[FF_RCT_CANDIDATES];
+                    ff_rct_pixel_stat(P, e->frame.data(), e->sl[i].x, e->sl[i].y, x, y, v);
+                    for (int k = 0; k < FF_RCT_CANDIDATES; k++)
+                        stat[k] = (int32_t)((uint32_t)stat[k] + (uint32_t)v[k]);
+                }
+            ff_rct_pick(stat, &rct[2 * i], &rct[2 * i + 1]);
+        }
     /* stage A: one "thread" per token */
     for (int i = 0; i < P.nslices; i++)
         for (uint32_t t = 0; t < e->sl[i].ntok; t++)
-            e->tokens[e->sl[i].tok_off + t] = ff_symbolize_index(P, e->sl[i], e->frame.data(), e->qt.data(), t);
+            e->tokens[e->sl[i].tok_off + t] = ff_symbolize_index(P, e->sl[i], e->frame.data(), e->qt.data(), t,
+                                                                 rct[2 * i], rct[2 * i + 1]);
     /* state reset on key frames: ff_ffv1_clear_slice_state */
     if (keyf) {
         memset(e->rstate.data(), 128, e->rstate.size());
@@ -121,11 +136,14 @@ extern "C" int ffv1emul_encode(void *h, const uint8_t *const planes[4], const in
         if (P.ac == FF_AC_GOLOMB)
             bytes[i] = ff_encode_slice_golomb(P, e->sl[i], &e->tokens[e->sl[i].tok_off],
                                               &e->vstate[(size_t)i * P.total_ctx], pre[i], e->prebytes.data(),
-                                              &e->bs[e->sl[i].bs_off], &ovf);
+                                              &e->bs[e->sl[i].bs_off], &ovf, &e->s.cur_tab,
+                                              P.version > 3 ? &rct[2 * i] : nullptr);
         else
             bytes[i] = ff_encode_slice_range(e->sl[i], &e->tokens[e->sl[i].tok_off],
                                              &e->rstate[(size_t)i * P.total_ctx * FF_CONTEXT_SIZE], &e->s.cur_tab,
-                                             pre[i], e->prebytes.data(), &e->bs[e->sl[i].bs_off], &ovf, row);
+                                             pre[i], e->prebytes.data(), &e->bs[e->sl[i].bs_off], &ovf, row,
+                                             P.version > 3 ? &rct[2 * i] : nullptr,
+                                             P.version > 3 ? (uint32_t)((16384 + (int64_t)P.width * P.height * 12) / P.nslices) : 0u);
         if (ovf) return FFGPU_INVALIDDATA;
     }
     /* pack */

@@ -541,3 +541,52 @@ def test_stream_spread_over_several_gpus(ndev, kw, nframes):
         for a, b in zip(dec.decode(pkt), frames[i]):
             assert np.array_equal(a, b)
     assert enc.launches > 0 and dec.launches > 0
+
+
+@pytest.mark.parametrize("fmt", ["bgr0", "bgra", "gbrp10le", "gbrap12le", "gbrp16le"])
+def test_version4_rgb_matches_the_reference(fmt):
+    """FFV1 version 4 on the GPU: k_rct_stat / k_rct_pick choose the per-slice RCT
+    coefficients like choose_rct_params (ffv1enc.c:963-1043), the slice coders finish the
+    longer slice header on the device; packets == the compiled reference, pictures restored"""
+    if not cc.available("ref"):
+        pytest.skip("oracle/_ref not built")
+    F = gpu()
+    w, h = 160, 96
+    for kw in (dict(slices=4, coder=2), dict(slices=9, coder=-2, context=1), dict(coder=0),
+               dict(slices=12, coder=1, gop_size=1)):
+        kw = dict(kw, level=4, strict=-2)
+        ref = cc.Encoder("ref", w, h, fmt, **kw)
+        enc = F.FFV1Encoder(w, h, fmt, **kw)
+        assert enc.info == ref.info and enc.extradata == ref.extradata
+        dref = cc.Decoder("ref", w, h, ref.extradata)
+        dec = F.FFV1Decoder(w, h, ref.extradata)
+        for i, kind in enumerate(("smooth", "testsrc2", "extremes", "smooth", "testsrc2")):
+            planes = synth.GENERATORS[kind](fmt, w, h, i)
+            pkt = ref.encode(planes)
+            assert enc.encode(planes) == pkt, (fmt, kw, kind)
+            want = dref.decode(pkt)
+            got = dec.decode(pkt, fmt_hint=dref.pix_fmt)
+            for a, b in zip(want, got):
+                assert np.array_equal(a, b), (fmt, kw, kind)
+        enc.close()
+        dec.close()
+
+
+@pytest.mark.parametrize("fmt", ["yuv420p", "yuv444p10le", "gray", "yuva420p", "yuv420p16le"])
+def test_version4_ycbcr_streams_decode(fmt):
+    """version 4 YCbCr streams of the reference encoder decode to the reference's pictures"""
+    if not cc.available("ref"):
+        pytest.skip("oracle/_ref not built")
+    F = gpu()
+    w, h = 160, 96
+    for kw in (dict(slices=4, coder=2), dict(coder=0), dict(slices=12, coder=1, gop_size=1)):
+        ref = cc.Encoder("ref", w, h, fmt, level=4, strict=-2, **kw)
+        dref = cc.Decoder("ref", w, h, ref.extradata)
+        dec = F.FFV1Decoder(w, h, ref.extradata)
+        for i, kind in enumerate(("smooth", "noise", "testsrc2", "smooth")):
+            pkt = ref.encode(synth.GENERATORS[kind](fmt, w, h, i))
+            want = dref.decode(pkt)
+            got = dec.decode(pkt, fmt_hint=dref.pix_fmt)
+            for a, b in zip(want, got):
+                assert np.array_equal(a, b), (fmt, kw, kind)
+        dec.close()
