@@ -308,6 +308,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="pictures per step and GPU (0 = default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--route", type=int, default=0,
+                    help="e2e leg through ONE routing handle over this many GPUs of this process "
+                         "(ffgpu_enc_options.ndevices), instead of one rank per GPU")
     ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-memory e2e leg")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to the GPU's NUMA node")
     ap.add_argument("--e2e-groups", type=int, default=4, help="launch groups a step's pictures are split into")
@@ -504,8 +507,13 @@ def main():
         vb = max(B // args.e2e_groups, 1)
         enc.close()
         dec.close()
-        enc = F.FFV1Encoder(w, h, fmt, device=local, max_batch=vb, pipeline_depth=args.e2e_depth, **opts)
-        dec = F.FFV1Decoder(w, h, enc.extradata, device=local, max_batch=vb, pipeline_depth=args.e2e_depth)
+        # --route N: ONE process, the product's own round-robin over N GPUs (ndevices in the
+        # options of the C ABI) instead of one torchrun rank per GPU
+        routed = tuple(range(args.route)) if args.route > 1 and world == 1 else ()
+        enc = F.FFV1Encoder(w, h, fmt, device=local, max_batch=vb, pipeline_depth=args.e2e_depth,
+                            devices=routed, **opts)
+        dec = F.FFV1Decoder(w, h, enc.extradata, device=local, max_batch=vb, pipeline_depth=args.e2e_depth,
+                            devices=routed)
 
         # The host loop is C (tools/e2e_driver.c): an encoder thread and a decoder thread on the
         # public C ABI, like the codec threads of a transcoder.  Packets go to the decoder as
@@ -678,6 +686,7 @@ def main():
                       "ffgpu_ffv1_decode_send_packet/receive_frame, pinned host buffers",
                "host_loop": "tools/e2e_driver.c (2 threads)" if use_c else "python (2 threads)",
                "frames_per_launch_group": vb, "launch_groups_in_flight": args.e2e_depth,
+               "routed_devices": len(routed) or 1,
                "gpu_launches": int(enc.launches + dec.launches - e2e_launch0)}
 
         # ---- the same through ordinary (pageable) memory, what AVFrames are: the library

@@ -101,6 +101,8 @@ SYMBOLS = [
     ("ffgpu_ffv1_decoder_profile", C.c_int, [C.c_void_p, C.c_int]),
     ("ffgpu_ffv1_decoder_kernel_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
     ("ffgpu_ffv1_encoder_decisions", C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
+    ("ffgpu_cuda_push_context", C.c_int, [C.c_void_p]),
+    ("ffgpu_cuda_pop_context", C.c_int, []),
     ("ffgpu_last_error", C.c_char_p, []),
     ("ffgpu_abi_version", C.c_int, []),
 ]

@@ -44,6 +44,49 @@ static int fail(int code, const char *fmt, ...)
 }
 
 extern "C" const char *ffgpu_last_error(void) { return g_err; }
+
+/* Frames that live on the GPU (AV_PIX_FMT_CUDA) come from libavutil's CUDA hw device context,
+ * which owns a driver-API CUcontext of its own (hwcontext_cuda.c creates one with
+ * cuCtxCreate).  Device pointers are only valid inside the context that allocated them, and
+ * the CUDA runtime this library is written against adopts whichever context is current on
+ * the calling thread: the glue therefore makes the hw device's context current around every
+ * call into the library (the way nvenc.c:1329-1340 brackets its work), and all memory and
+ * streams of the handle then live in that context too. */
+typedef int (*cu_ctx_push_fn)(void *);
+typedef int (*cu_ctx_pop_fn)(void **);
+
+static void *driver_entry(const char *name)
+{
+    void *fn = NULL;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &st) != cudaSuccess ||
+        st != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return NULL;
+    }
+    return fn;
+}
+
+extern "C" int ffgpu_cuda_push_context(void *cu_context)
+{
+    static cu_ctx_push_fn push;
+    if (!push)
+        push = (cu_ctx_push_fn)driver_entry("cuCtxPushCurrent");
+    if (!push)
+        return fail(FFGPU_EXTERNAL, "CUDA driver entry point cuCtxPushCurrent not available");
+    return push(cu_context) ? fail(FFGPU_EXTERNAL, "cuCtxPushCurrent failed") : 0;
+}
+
+extern "C" int ffgpu_cuda_pop_context(void)
+{
+    static cu_ctx_pop_fn pop;
+    void *old = NULL;
+    if (!pop)
+        pop = (cu_ctx_pop_fn)driver_entry("cuCtxPopCurrent");
+    if (!pop)
+        return fail(FFGPU_EXTERNAL, "CUDA driver entry point cuCtxPopCurrent not available");
+    return pop(&old) ? fail(FFGPU_EXTERNAL, "cuCtxPopCurrent failed") : 0;
+}
 extern "C" int ffgpu_abi_version(void) { return FFGPU_ABI_VERSION; }
 
 #define CK(call)                                                                            \

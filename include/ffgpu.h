@@ -252,6 +252,14 @@ int ffgpu_ffv1_decoder_kernel_ms(ffgpu_decoder *dec, float *ms, int n);
  * Golomb-Rice streams (no binary decisions). */
 int ffgpu_ffv1_encoder_decisions(ffgpu_encoder *enc, uint64_t *total, uint32_t *heaviest_slice);
 
+/* AV_PIX_FMT_CUDA frames belong to the CUcontext of libavutil's CUDA hw device
+ * (AVCUDADeviceContext.cuda_ctx, libavutil/hwcontext_cuda.h).  The glue brackets EVERY call
+ * into this library -- init included, so that the handle's memory lives there -- with
+ * push(cuda_ctx) ... pop(), as libavcodec/nvenc.c:1329-1340 does for NVENC.  Host-memory
+ * callers never need these. */
+int ffgpu_cuda_push_context(void *cu_context);
+int ffgpu_cuda_pop_context(void);
+
 /* last error text of the calling thread ("" if none) */
 const char *ffgpu_last_error(void);
 

@@ -23,6 +23,21 @@
 
 #include "ffgpu.h"
 
+/* Pictures that already live on the GPU: the encoder also takes AV_PIX_FMT_CUDA
+ * frames of an AVHWFramesContext whose sw_format is one of its formats (hwupload_cuda,
+ * scale_cuda, a CUDA decoder in front of it), the pattern of libavcodec/nvenc.c:525-545,
+ * :1654-1680.  The planes are device pointers; the library copies device to device.  Needs a
+ * build with the CUDA hw context (CONFIG_CUDA). */
+#if CONFIG_CUDA
+#include "libavutil/hwcontext.h"
+#include "libavutil/hwcontext_cuda.h"
+#define CUDA_PUSH(s) do { if ((s)->cu_ctx) ffgpu_cuda_push_context((s)->cu_ctx); } while (0)
+#define CUDA_POP(s)  do { if ((s)->cu_ctx) ffgpu_cuda_pop_context(); } while (0)
+#else
+#define CUDA_PUSH(s) do { } while (0)
+#define CUDA_POP(s)  do { } while (0)
+#endif
+
 #define GPU_FIFO 2048          /* >= pictures the launch groups of one handle can hold in flight */
 
 typedef struct FFV1GpuContext {
@@ -45,7 +60,8 @@ typedef struct FFV1GpuContext {
     AVFrame *fifo[GPU_FIFO];
     int fifo_head, fifo_count;
     AVPacket *pending;         /* decoder: a packet the library could not take yet */
-    int draining;
+    int draining, eof;
+    void *cu_ctx;              /* AV_PIX_FMT_CUDA input: the hw device's CUcontext, else NULL */
 } FFV1GpuContext;
 
 static int fifo_push(FFV1GpuContext *s, AVFrame *f)
@@ -96,6 +112,20 @@ static av_cold int gpu_encode_init(AVCodecContext *avctx)
     o.width  = avctx->width;
     o.height = avctx->height;
     o.pix_fmt = av_get_pix_fmt_name(avctx->pix_fmt);
+#if CONFIG_CUDA
+    if (avctx->pix_fmt == AV_PIX_FMT_CUDA) {
+        AVHWFramesContext *frames;
+        AVCUDADeviceContext *cuda;
+        if (!avctx->hw_frames_ctx) {
+            av_log(avctx, AV_LOG_ERROR, "AV_PIX_FMT_CUDA input needs hw_frames_ctx\n");
+            return AVERROR(EINVAL);
+        }
+        frames = (AVHWFramesContext *)avctx->hw_frames_ctx->data;
+        cuda   = frames->device_ctx->hwctx;
+        s->cu_ctx = cuda->cuda_ctx;
+        o.pix_fmt = av_get_pix_fmt_name(frames->sw_format);
+    }
+#endif
     o.slices = avctx->slices;
     o.level  = avctx->level;
     o.gop_size = avctx->gop_size;
@@ -112,7 +142,10 @@ static av_cold int gpu_encode_init(AVCodecContext *avctx)
         avpriv_report_missing_feature(avctx, "2-pass statistics on the GPU path");
         return AVERROR_PATCHWELCOME;
     }
-    if ((ret = ffgpu_ffv1_encode_init(&s->enc, &o)) < 0) {
+    CUDA_PUSH(s);
+    ret = ffgpu_ffv1_encode_init(&s->enc, &o);
+    CUDA_POP(s);
+    if (ret < 0) {
         av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
         return ret;                            /* same AVERROR values as encode_init */
     }
@@ -148,8 +181,12 @@ static int gpu_send_frame(AVCodecContext *avctx, const AVFrame *pict)
     AVFrame *ref;
     int ret, i;
 
-    if (!pict)
-        return ffgpu_ffv1_encode_send_frame(s->enc, NULL);
+    if (!pict) {
+        CUDA_PUSH(s);
+        ret = ffgpu_ffv1_encode_send_frame(s->enc, NULL);
+        CUDA_POP(s);
+        return ret;
+    }
     if (s->fifo_count == GPU_FIFO)
         return AVERROR(EAGAIN);
     for (i = 0; i < 4; i++) {
@@ -161,7 +198,9 @@ static int gpu_send_frame(AVCodecContext *avctx, const AVFrame *pict)
     p.sar_num = pict->sample_aspect_ratio.num;
     p.sar_den = pict->sample_aspect_ratio.den;
     p.pts = pict->pts;
+    CUDA_PUSH(s);
     ret = ffgpu_ffv1_encode_send_frame(s->enc, &p);   /* FFGPU_EAGAIN == AVERROR(EAGAIN) */
+    CUDA_POP(s);
     if (ret < 0) {
         if (ret != AVERROR(EAGAIN))
             av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
@@ -184,7 +223,9 @@ static int gpu_receive_packet(AVCodecContext *avctx, AVPacket *pkt)
 
     /* is a packet ready, and how large is it?  Nothing is allocated on EAGAIN / EOF, and the
      * packet gets its exact size instead of the worst case of ffv1enc.c:1131-1132 */
+    CUDA_PUSH(s);
     ret = ffgpu_ffv1_encode_packet_ready(s->enc, &size);
+    CUDA_POP(s);
     if (ret < 0) {                             /* EAGAIN, EOF, "encoded frame too large", ... */
         if (ret != AVERROR(EAGAIN) && ret != AVERROR_EOF)
             av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
@@ -195,7 +236,9 @@ static int gpu_receive_packet(AVCodecContext *avctx, AVPacket *pkt)
      * the shared byte_buffer ff_alloc_packet2 may return */
     if ((ret = av_new_packet(pkt, size)) < 0)
         return ret;
+    CUDA_PUSH(s);
     ret = ffgpu_ffv1_encode_receive_packet(s->enc, pkt->data, pkt->size, &size, &key, &pts);
+    CUDA_POP(s);
     if (ret < 0) {
         av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
         av_packet_unref(pkt);
@@ -214,8 +257,10 @@ static av_cold int gpu_close(AVCodecContext *avctx)
 {
     FFV1GpuContext *s = avctx->priv_data;
     int i;
+    CUDA_PUSH(s);
     ffgpu_ffv1_encode_close(s->enc);
     ffgpu_ffv1_decode_close(s->dec);
+    CUDA_POP(s);
     s->enc = NULL;
     s->dec = NULL;
     for (i = 0; i < GPU_FIFO; i++)
@@ -311,6 +356,8 @@ static int gpu_receive_frame(AVCodecContext *avctx, AVFrame *frame)
     const char *name;
     int ret, i;
 
+    if (s->eof)                                /* drained: libavcodec may still ask again */
+        return AVERROR_EOF;
     for (;;) {
         memset(&out, 0, sizeof(out));
         ret = ffgpu_ffv1_decode_receive_frame(s->dec, &out);
@@ -327,6 +374,8 @@ static int gpu_receive_frame(AVCodecContext *avctx, AVFrame *frame)
         if (ret != AVERROR(EAGAIN)) {          /* AVERROR_EOF after the drain, or an error */
             if (ret != AVERROR_EOF)
                 av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
+            else
+                s->eof = 1;
             return ret;
         }
         /* nothing ready: feed the GPU */
@@ -361,6 +410,11 @@ static int gpu_receive_frame(AVCodecContext *avctx, AVFrame *frame)
                 av_frame_free(&f);
                 return ret;
             }
+            /* ff_get_buffer took pts and the other properties from the packet
+             * (ff_decode_frame_props); what decode_simple_receive_frame adds for .decode
+             * codecs (decode.c:452-470) is done here for this receive_frame codec */
+            f->pkt_dts = s->pending->dts;
+            f->best_effort_timestamp = f->pts != AV_NOPTS_VALUE ? f->pts : f->pkt_dts;
             for (i = 0; i < 4; i++) {
                 dst.data[i] = f->data[i];
                 dst.linesize[i] = f->linesize[i];
@@ -401,7 +455,7 @@ static void gpu_flush(AVCodecContext *avctx)
     while ((f = fifo_pop(s)))
         av_frame_free(&f);
     av_packet_unref(s->pending);
-    s->draining = 0;
+    s->draining = s->eof = 0;
 }
 
 #define OFFSET(x) offsetof(FFV1GpuContext, x)
@@ -468,6 +522,9 @@ AVCodec ff_ffv1_gpu_encoder = {
         AV_PIX_FMT_RGB48,     AV_PIX_FMT_GBRAP16,   AV_PIX_FMT_RGBA64,    AV_PIX_FMT_GRAY9,
         AV_PIX_FMT_YUV420P14, AV_PIX_FMT_YUV422P14, AV_PIX_FMT_YUV444P14,
         AV_PIX_FMT_YUV440P10, AV_PIX_FMT_YUV440P12,
+#if CONFIG_CUDA
+        AV_PIX_FMT_CUDA,                                /* new: frames resident on the GPU */
+#endif
         AV_PIX_FMT_NONE
     },
     .priv_class     = &enc_class,

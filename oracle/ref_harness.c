@@ -304,6 +304,7 @@ int ff_thread_ref_frame(ThreadFrame *dst, ThreadFrame *src)
 }
 
 #ifdef HARNESS_GPU
+static AVCodecContext *g_glue_avctx;       /* av_new_packet has no context argument */
 int ff_get_buffer(AVCodecContext *avctx, AVFrame *frame, int flags)
 {
     ThreadFrame tf = { frame, { avctx, avctx }, NULL };
@@ -316,6 +317,42 @@ void av_packet_unref(AVPacket *pkt)
 void avpriv_report_missing_feature(void *avc, const char *msg, ...)
 {
     av_log(avc, AV_LOG_WARNING, "%s is not implemented\n", msg);
+}
+/* what the glue's send_frame / receive_packet / receive_frame callbacks use of libavcodec
+ * and libavutil, in the harness's shallow-ownership model (frames never own their planes) */
+AVFrame *av_frame_clone(const AVFrame *src)
+{
+    AVFrame *f = av_frame_alloc();
+    if (f)
+        *f = *src;
+    return f;
+}
+void av_frame_move_ref(AVFrame *dst, AVFrame *src)
+{
+    *dst = *src;
+    av_frame_unref(src);
+}
+int av_new_packet(AVPacket *pkt, int size)
+{
+    return ff_alloc_packet2(g_glue_avctx, pkt, size, 0);
+}
+AVPacket *av_packet_alloc(void)
+{
+    return calloc(1, sizeof(AVPacket));
+}
+void av_packet_free(AVPacket **pkt)
+{
+    if (pkt && *pkt) {
+        free(*pkt);
+        *pkt = NULL;
+    }
+}
+/* the synchronous .decode callback is what this harness drives; receive_frame's packet
+ * source is never reached */
+int ff_decode_get_packet(AVCodecContext *avctx, AVPacket *pkt)
+{
+    (void)avctx; (void)pkt;
+    return AVERROR(EAGAIN);
 }
 #endif
 void ff_thread_finish_setup(AVCodecContext *avctx) { (void)avctx; }
@@ -595,6 +632,7 @@ int ffv1ref_encode(void *hh, const uint8_t *const planes[4], const int linesize[
     memset(&pkt, 0, sizeof(pkt));
     g_last_log[0] = 0;
 #ifdef HARNESS_GPU
+    g_glue_avctx = a;
     /* send_frame / receive_packet: one picture, flush, one packet (the EOF re-arms the handle) */
     if ((ret = ff_ffv1_encoder.send_frame(a, h->in)) < 0)
         return ret;

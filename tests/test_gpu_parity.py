@@ -590,3 +590,81 @@ def test_version4_ycbcr_streams_decode(fmt):
             for a, b in zip(want, got):
                 assert np.array_equal(a, b), (fmt, kw, kind)
         dec.close()
+
+
+def test_pictures_resident_on_the_gpu_through_send_receive():
+    """SURVEY 8f-1 at the C ABI: ffgpu_picture.data[] / ffgpu_picture_out.data[] may be CUDA
+    device pointers (what AV_PIX_FMT_CUDA frames carry); the copy kind is taken from the
+    pointer.  Also the context bracket the glue puts around every call for such frames."""
+    import ctypes as C
+    import torch
+    F = gpu()
+    w, h, fmt = 352, 288, "yuv420p10le"
+    kw = dict(slices=30, gop_size=1)
+    frames = [synth.testsrc2_like(fmt, w, h, i) for i in range(9)]
+    ref = cc.Encoder("oracle", w, h, fmt, **kw)
+    want = [ref.encode(f) for f in frames]
+    # the bracket: the primary context the runtime (torch) uses, pushed and popped again
+    torch.zeros(1, device="cuda")
+    cu = C.CDLL("libcuda.so.1")
+    ctx = C.c_void_p()
+    assert cu.cuCtxGetCurrent(C.byref(ctx)) == 0 and ctx.value
+    lib = F.lib()
+    assert lib.ffgpu_cuda_push_context(ctx) == 0
+    try:
+        # device-resident planes with a pitch of their own
+        dev = []
+        for planes in frames:
+            dev.append([torch.from_numpy(np.pad(p, ((0, 0), (0, 64)))).cuda() for p in planes])
+        enc = F.FFV1Encoder(w, h, fmt, max_batch=4, pipeline_depth=2, **kw)
+        got, i = [], 0
+        while True:
+            if i < len(dev):
+                pic = F.codec.Picture()
+                for k, t in enumerate(dev[i]):
+                    pic.data[k] = t.data_ptr()
+                    pic.linesize[k] = t.stride(0)
+                pic.sar_num, pic.sar_den, pic.pts = 0, 1, i
+                r = lib.ffgpu_ffv1_encode_send_frame(enc.h, C.byref(pic))
+                assert r in (0, F.EAGAIN)
+                if r == 0:
+                    i += 1
+                    continue
+            elif i == len(dev):
+                enc.send_frame(None)
+                i += 1
+            r = enc.receive_packet()
+            if r == F.EOF:
+                break
+            if r is not None:
+                got.append(r[0])
+        assert got == want
+        # decode into device-resident destination planes
+        dec = F.FFV1Decoder(w, h, enc.extradata, max_batch=4, pipeline_depth=2)
+        outs = [[torch.zeros_like(t) for t in dev[0]] for _ in want]
+        sent = done = 0
+        flushed = False
+        while True:
+            if sent < len(want):
+                po = F.codec.PictureOut()
+                for k, t in enumerate(outs[sent]):
+                    po.data[k] = t.data_ptr()
+                    po.linesize[k] = t.stride(0)
+                if dec.send_packet(want[sent], pts=sent, dst=(po, outs[sent])):
+                    sent += 1
+                    continue
+            elif not flushed:
+                dec.send_packet(None)
+                flushed = True
+            r = dec.receive_frame()
+            if r == F.EOF:
+                break
+            if r is not None:
+                done += 1
+        torch.cuda.synchronize()
+        assert done == len(want)
+        for o, src in zip(outs, frames):
+            for t, p in zip(o, src):
+                assert np.array_equal(t.cpu().numpy()[:, :p.shape[1]], p)
+    finally:
+        assert lib.ffgpu_cuda_pop_context() == 0
