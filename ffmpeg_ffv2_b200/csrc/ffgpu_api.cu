@@ -194,6 +194,21 @@ static int coder_lane_stride(long items)
     return s;
 }
 
+/* heavy / light schedule (FFSched): FFGPU_HEAVY_STRIDE (0 switches the classes off) and
+ * FFGPU_HEAVY_FACTOR (percent of the mean weight) are tuning hooks */
+static int heavy_stride_opt(void)
+{
+    const char *env = getenv("FFGPU_HEAVY_STRIDE");
+    const int v = env ? atoi(env) : 4;
+    return v == 2 || v == 4 || v == 8 || v == 16 || v == 32 ? v : (v == 0 ? 0 : 4);
+}
+static float heavy_factor_opt(void)
+{
+    const char *env = getenv("FFGPU_HEAVY_FACTOR");
+    const int v = env ? atoi(env) : 350;
+    return v > 0 ? v / 100.0f : 3.5f;
+}
+
 /* quant tables in the layout the kernels index: [table][5*256 + flag] */
 static void flatten_qt(const FFStream *s, int16_t *q)
 {
@@ -440,6 +455,7 @@ struct EncJob {
     uint32_t *d_weight, *d_weight_sorted, *d_order;
     void *d_sort_tmp;
     size_t sort_tmp_bytes;
+    FFSched *d_sched;
     int *d_rct;                 /* version 4: RCT coefficients per (picture, slice) */
     int32_t *d_rct_stat;
     int pkt_owned;
@@ -505,7 +521,7 @@ static int enc_free_job(EncJob *j)
         cudaFree(j->d_pkt);
     cudaFree(j->d_frame_set); cudaFree(j->d_frame_key);
     cudaFree(j->d_weight); cudaFree(j->d_weight_sorted); cudaFree(j->d_order); cudaFree(j->d_sort_tmp);
-    cudaFree(j->d_rct); cudaFree(j->d_rct_stat);
+    cudaFree(j->d_rct); cudaFree(j->d_rct_stat); cudaFree(j->d_sched);
     cudaFreeHost(j->h_frame_set); cudaFreeHost(j->h_frame_key); cudaFreeHost(j->h_pkt_size);
     cudaFreeHost(j->h_pkt_off); cudaFreeHost(j->h_overflow); cudaFreeHost(j->h_pkt);
     cudaFreeHost(j->h_stage);
@@ -588,6 +604,8 @@ static int enc_device_init(ffgpu_encoder *e)
         CK(cudaMalloc(&j->d_order, B * P->nslices * sizeof(uint32_t)));
         j->sort_tmp_bytes = ffk_sort_tmp_bytes((int)(B * P->nslices));
         CK(cudaMalloc(&j->d_sort_tmp, j->sort_tmp_bytes));
+        CK(cudaMalloc(&j->d_sched, sizeof(FFSched)));
+        CK(cudaMemset(j->d_sched, 0, sizeof(FFSched)));
         if (P->version > 3) {
             CK(cudaMalloc(&j->d_rct, B * P->nslices * 2 * sizeof(int)));
             CK(cudaMalloc(&j->d_rct_stat, B * P->nslices * 16 * sizeof(int32_t)));
@@ -808,6 +826,13 @@ static void enc_fill_dev(const ffgpu_encoder *e, const EncJob *j, const uint8_t 
     E->lane_stride = coder_lane_stride((long)j->n * e->P.nslices);
     E->rct = j->d_rct;
     E->rct_stat = j->d_rct_stat;
+    {
+        const char *env = getenv("FFGPU_STAGE_A");
+        E->legacy_stage_a = env && !strcmp(env, "legacy");
+    }
+    E->heavy_stride = heavy_stride_opt();
+    E->heavy_factor = heavy_factor_opt();
+    E->sched = E->heavy_stride ? j->d_sched : NULL;
 }
 
 /* enqueue the kernel chain + result download of a filled group */
@@ -1344,6 +1369,7 @@ struct DecJob {
     int32_t *d_wide_lines;      /* picture-wide scratch pool for slices wider than their grid cell */
     uint32_t *d_wide_used;
     uint32_t *d_touched;        /* lazily created states: one bit per (work item, context) */
+    FFSched *d_sched;
     uint8_t *d_frames;
     uint8_t *h_stage;           /* pinned staging for destinations in pageable memory (lazily) */
     FFDecResult *d_result, *h_result;
@@ -1390,7 +1416,7 @@ static void dec_free_job(DecJob *j)
 {
     cudaFreeHost(j->h_pkt); cudaFree(j->d_pkt); cudaFreeHost(j->h_work); cudaFree(j->d_work);
     cudaFreeHost(j->h_nslices); cudaFree(j->d_nslices); cudaFree(j->d_state); cudaFree(j->d_lines);
-    cudaFree(j->d_wide_lines); cudaFree(j->d_wide_used); cudaFree(j->d_touched);
+    cudaFree(j->d_wide_lines); cudaFree(j->d_wide_used); cudaFree(j->d_touched); cudaFree(j->d_sched);
     cudaFree(j->d_frames); cudaFree(j->d_result); cudaFreeHost(j->h_result); cudaFreeHost(j->h_stage);
     cudaFree(j->d_weight); cudaFree(j->d_weight_sorted); cudaFree(j->d_order); cudaFree(j->d_sort_tmp);
     free(j->meta);
@@ -1567,6 +1593,8 @@ static int dec_device_init(ffgpu_decoder *d)
         CK(cudaMalloc(&j->d_nslices, B * sizeof(int)));
         if (d->intra)
             CK(cudaMalloc(&j->d_state, B * state_frame));
+        CK(cudaMalloc(&j->d_sched, sizeof(FFSched)));
+        CK(cudaMemset(j->d_sched, 0, sizeof(FFSched)));
         if (d->lazy_states)
             CK(cudaMalloc(&j->d_touched, B * d->max_slices * (size_t)((P->total_ctx + 31) / 32) * sizeof(uint32_t)));
         CK(cudaMalloc(&j->d_lines, B * d->max_slices * P->ncoded * 2 * d->line_stride * sizeof(int32_t)));
@@ -1717,6 +1745,9 @@ static void dec_fill_dev(const ffgpu_decoder *d, const DecJob *j, uint8_t *frame
     D->any_five = d->any_five;
     D->generic = d->generic;
     D->lane_stride = 1;                            /* set per launch from the number of work items */
+    D->heavy_stride = heavy_stride_opt();
+    D->heavy_factor = heavy_factor_opt();
+    D->sched = D->heavy_stride ? j->d_sched : NULL;
     D->hdr.micro_version = d->s.micro_version;
     D->hdr.qt_count = d->s.qt_count;
     D->hdr.ctx_cap = d->max_ctx;

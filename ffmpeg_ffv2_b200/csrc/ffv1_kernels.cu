@@ -267,6 +267,223 @@ k_symbolize_planar(const FFDevParams P, const FFDevSlice *__restrict__ slices,
         atomicAdd(&weight[(size_t)blockIdx.y * P.nslices + blockIdx.x], wsum);
 }
 
+
+/* ---------------- stage A, bulk-copy form (sm_90+ async proxy, SASS: UBLKCP) ----------------
+ * Same result as k_symbolize_planar.  The strip a CTA works on -- up to SB_TX x SB_TY samples
+ * of one plane of a slice plus its halo (two rows above, two columns left, one right) -- is
+ * brought into shared memory by the bulk-copy engine (cp.async.bulk, one 16-byte-aligned row
+ * segment per copy, completion counted on an mbarrier), double buffered: while the threads
+ * turn one strip into tokens the next one is already in flight, and no thread's issue slots
+ * or registers are spent on global loads.  A thread owns a sample column of (a row segment of)
+ * the strip and walks down it, so T / LT / RT / TT are last row's values carried in registers
+ * and only the current sample and its left / right neighbours are read from shared memory.
+ * The border rules of ffv1enc.c:284-289 are the same selects as in k_symbolize_planar. */
+#define SB_TX      256
+#define SB_TY      16
+#define SB_THREADS 256
+
+__device__ __forceinline__ void sb_mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void sb_mbar_expect(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+                 "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sb_bulk_load(void *smem, const void *gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(bytes),
+                   "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void sb_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; spins++) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (spins > (1u << 24))
+            __trap();                                /* a lost copy must not hang the GPU */
+    }
+}
+
+struct SbPlane {
+    const uint8_t *plane;       /* row 0, byte 0 of the memory plane in this picture */
+    int X0, Y0, w, h;           /* slice rectangle in the plane's sample grid        */
+    int ntx, nunits, pitch, ctx_base;
+    uint32_t base;              /* first token of the plane inside the slice         */
+};
+
+template <bool WIDE, bool FIVE>
+__global__ void __launch_bounds__(SB_THREADS)
+k_symbolize_bulk(const FFDevParams P, const FFDevSlice *__restrict__ slices,
+                 const uint8_t *__restrict__ frames, const int16_t *__restrict__ qt,
+                 uint32_t *__restrict__ tokens, uint32_t *__restrict__ weight)
+{
+    constexpr int BPS = WIDE ? 2 : 1;
+    constexpr int ROWB = ((SB_TX + 3) * BPS + 30) & ~15;     /* aligned span of a halo'd row */
+    __shared__ __align__(128) uint8_t tile[2][(SB_TY + 2) * ROWB + 16];
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ int16_t sq[FF_QT_STRIDE];
+    __shared__ SbPlane sp[FF_MAX_PLANES];
+    __shared__ int s_nunits;
+    {
+        const uint32_t *src = (const uint32_t *)(qt + (size_t)P.set_qidx[0] * FF_QT_STRIDE);
+        for (int i = threadIdx.x; i < FF_QT_STRIDE / 2; i += SB_THREADS)
+            ((uint32_t *)sq)[i] = src[i];
+    }
+    if (threadIdx.x == 0) {
+        const FFDevSlice *slp = &slices[blockIdx.x];
+        const uint8_t *frame = frames + (size_t)blockIdx.y * P.frame_bytes;
+        uint32_t base = 0;
+        int n = 0;
+        for (int k = 0; k < FF_MAX_PLANES; k++) {
+            SbPlane q;
+            memset(&q, 0, sizeof(q));
+            if (k < P.ncoded) {
+                const int mem = P.cp[k].mem;
+                q.w = slp->seg_w[k];
+                q.h = slp->seg_lines[k];
+                q.X0 = slp->x >> P.cp[k].hs;
+                q.Y0 = slp->y >> P.cp[k].vs;
+                q.ntx = (q.w + SB_TX - 1) / SB_TX;
+                q.nunits = q.ntx * ((q.h + SB_TY - 1) / SB_TY);
+                q.pitch = P.pitch[mem];
+                q.plane = frame + P.plane_off[mem];
+                q.ctx_base = P.set_base[P.cp[k].set];
+                q.base = base;
+                base += (uint32_t)q.w * q.h;
+                n += q.nunits;
+            }
+            sp[k] = q;
+        }
+        s_nunits = n;
+        sb_mbar_init(&bar[0], 1);
+        sb_mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t *tok = tokens + (size_t)blockIdx.y * P.frame_tokens + slices[blockIdx.x].tok_off;
+    const int cbits = P.cbits;
+    const int nunits = s_nunits;
+    uint32_t wsum = 0, phase0 = 0, phase1 = 0;
+
+    /* unit u -> plane k, tile origin (x0, y0), extent (txe, tye), byte window [b0, b0 + nb) */
+#define SB_UNIT(u, k, x0, y0, txe, tye, b0, nb)                                                   \
+    int k = 0, x0, y0, txe, tye, b0, nb;                                                         \
+    {                                                                                             \
+        int uu = (u);                                                                             \
+        for (int q = 0; q < FF_MAX_PLANES - 1; q++)                                               \
+            if (k == q && uu >= sp[q].nunits) {                                                   \
+                uu -= sp[q].nunits;                                                               \
+                k = q + 1;                                                                        \
+            }                                                                                     \
+        const int ty_ = uu / sp[k].ntx, tx_ = uu - ty_ * sp[k].ntx;                               \
+        x0 = tx_ * SB_TX;                                                                         \
+        y0 = ty_ * SB_TY;                                                                         \
+        txe = min(SB_TX, sp[k].w - x0);                                                           \
+        tye = min(SB_TY, sp[k].h - y0);                                                           \
+        const int c0_ = (sp[k].X0 + x0 - 2) * BPS, c1_ = (sp[k].X0 + x0 + txe + 1) * BPS;         \
+        b0 = max(c0_, 0) & ~15;                                                                   \
+        nb = min((c1_ + 15) & ~15, sp[k].pitch) - b0;                                             \
+    }
+
+    /* warp 0 starts the copies of unit u into buffer b */
+#define SB_ISSUE(u, b)                                                                            \
+    if (threadIdx.x < 32) {                                                                       \
+        SB_UNIT(u, k_, x0_, y0_, txe_, tye_, b0_, nb_)                                            \
+        const int first_ = max(y0_ - 2, 0), nrows_ = y0_ + tye_ - first_;                         \
+        (void)txe_;                                                                               \
+        if (threadIdx.x == 0) {                                                                   \
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                          \
+            sb_mbar_expect(&bar[b], (uint32_t)nrows_ * (uint32_t)nb_);                            \
+        }                                                                                         \
+        __syncwarp();                                                                             \
+        if ((int)threadIdx.x < nrows_) {                                                          \
+            const int r_ = first_ + (int)threadIdx.x;                                             \
+            sb_bulk_load(&tile[b][(r_ - (y0_ - 2)) * ROWB],                                       \
+                         sp[k_].plane + (size_t)(sp[k_].Y0 + r_) * sp[k_].pitch + b0_,            \
+                         (uint32_t)nb_, &bar[b]);                                                 \
+        }                                                                                         \
+    }
+
+    int u = blockIdx.z;
+    if (u < nunits) {
+        SB_ISSUE(u, 0)
+    }
+    for (int it = 0; u < nunits; it++, u += gridDim.z) {
+        const int b = it & 1;
+        __syncthreads();                             /* buffer b^1 is no longer read */
+        if (u + (int)gridDim.z < nunits) {
+            if (b) { SB_ISSUE(u + gridDim.z, 0) } else { SB_ISSUE(u + gridDim.z, 1) }
+        }
+        sb_mbar_wait(&bar[b], b ? phase1 : phase0);
+        if (b) phase1 ^= 1; else phase0 ^= 1;
+        {
+            SB_UNIT(u, k, x0, y0, txe, tye, b0, nb)
+            (void)nb;
+            /* threads: `cols` sample columns x `nseg` row segments */
+            int cols = 32;
+            while (cols < txe)
+                cols <<= 1;
+            const int nseg = SB_THREADS / cols, rps = (tye + nseg - 1) / nseg;
+            const int lx = threadIdx.x & (cols - 1), seg = threadIdx.x / cols;
+            const int x = x0 + lx, ys = y0 + seg * rps, ye = min(ys + rps, y0 + tye);
+            if (lx < txe && ys < ye) {
+                const int w = sp[k].w;
+                const uint8_t *tb = tile[b];
+                /* byte offset of column x (and its neighbours, clamped into the copied window) */
+                const int cx = (sp[k].X0 + x) * BPS - b0;
+                const int cl = max(cx - BPS, 0), cll = max(cx - 2 * BPS, 0), cr = cx + BPS;
+#define SB_LD(row, off) (WIDE ? (int)*(const int16_t *)(tb + ((row) - (y0 - 2)) * ROWB + (off))    \
+                              : (int)tb[((row) - (y0 - 2)) * ROWB + (off)])
+                int Tm = ys >= 1 ? SB_LD(ys - 1, cx) : 0;
+                int Lm = ys >= 1 ? SB_LD(ys - 1, cl) : 0;
+                int Rm = ys >= 1 ? SB_LD(ys - 1, cr) : 0;
+                int TTm = ys >= 2 ? SB_LD(ys - 2, cx) : 0;
+                const bool first = x == 0, last = x == w - 1;
+                uint32_t *trow = tok + sp[k].base + (uint32_t)ys * w + x;
+                const int ctx_base = sp[k].ctx_base;
+                for (int y = ys; y < ye; y++) {
+                    const int cur = SB_LD(y, cx), Lr = SB_LD(y, cl), Rr = SB_LD(y, cr);
+                    const int T = Tm, TT = TTm;
+                    const int L = first ? T : Lr;
+                    const int LT = first ? TT : Lm;
+                    const int RT = last ? T : Rm;
+                    int ctx = sq[(L - LT) & 0xFF] + sq[256 + ((LT - T) & 0xFF)] + sq[512 + ((T - RT) & 0xFF)];
+                    if (FIVE) {
+                        const int LLr = SB_LD(y, cll);
+                        const int LL = x >= 2 ? LLr : (x == 1 ? Lm : 0);
+                        ctx += sq[768 + ((LL - L) & 0xFF)] + sq[1024 + ((TT - T) & 0xFF)];
+                    }
+                    int diff = cur - ff_median3(L, L + T - LT, T);
+                    const int neg = ctx < 0;
+                    ctx = neg ? -ctx : ctx;
+                    diff = ff_fold(neg ? -diff : diff, cbits);
+                    const uint32_t t = ((uint32_t)diff << FF_TOKEN_CTX_BITS) | (uint32_t)(ctx_base + ctx);
+                    *trow = t;
+                    trow += w;
+                    wsum += ff_token_weight(t);
+                    TTm = T;
+                    Tm = cur;
+                    Lm = Lr;
+                    Rm = Rr;
+                }
+#undef SB_LD
+            }
+        }
+    }
+#undef SB_UNIT
+#undef SB_ISSUE
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    if ((threadIdx.x & 31) == 0 && weight && wsum)
+        atomicAdd(&weight[(size_t)blockIdx.y * P.nslices + blockIdx.x], wsum);
+}
+
 /* ---------------- adaptive state reset ---------------- */
 /* fills the state arenas of the frames flagged as key frames with a 64-bit pattern
  * (range coder: 128 in every byte; Golomb: {drift 0, error_sum 4, bias 0, count 1}) */
@@ -284,6 +501,67 @@ __global__ void k_fill_state(uint2 *__restrict__ state, size_t words_per_frame,
         p[i] = v;
 }
 
+/* ---------------- heavy / light schedule of the slice coders ---------------- */
+__global__ void __launch_bounds__(1024)
+k_sched(const uint32_t *__restrict__ sorted, int n, float factor, int heavy_stride, FFSched *out)
+{
+    typedef cub::BlockReduce<unsigned long long, 1024> Reduce;
+    __shared__ typename Reduce::TempStorage tmp;
+    __shared__ unsigned long long s_sum;
+    unsigned long long sum = 0;
+    for (int i = threadIdx.x; i < n; i += 1024)
+        sum += sorted[i];
+    sum = Reduce(tmp).Sum(sum);
+    if (threadIdx.x == 0)
+        s_sum = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        /* first sorted index whose weight is not above factor x mean (the array descends) */
+        const double limit = (double)factor * (double)s_sum / (double)(n > 0 ? n : 1);
+        int lo = 0, hi = n / 4;                      /* at most a quarter of the items */
+        while (lo < hi) {
+            const int mid = (lo + hi) / 2;
+            if ((double)sorted[mid] > limit)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        out->n_heavy = (uint32_t)lo;
+        out->heavy_threads = ((uint32_t)lo * (uint32_t)heavy_stride + 31u) & ~31u;
+    }
+}
+
+/* sorted work item of coder thread `tid`, or -1 */
+__device__ __forceinline__ int ff_sched_item(int tid, int total, int lane_stride, const FFSched *sched,
+                                             int heavy_stride)
+{
+    if (lane_stride > 1) {                           /* few items: spread them over the warps */
+        if (tid % lane_stride)
+            return -1;
+        tid /= lane_stride;
+        return tid < total ? tid : -1;
+    }
+    if (sched) {
+        const uint32_t nh = sched->n_heavy, ht = sched->heavy_threads;
+        if ((uint32_t)tid < ht) {
+            const uint32_t i = (uint32_t)tid / (uint32_t)heavy_stride;
+            return ((uint32_t)tid % (uint32_t)heavy_stride) == 0 && i < nh ? (int)i : -1;
+        }
+        tid = (int)(nh + ((uint32_t)tid - ht));
+    }
+    return tid < total ? tid : -1;
+}
+
+/* threads a coder launch needs in the worst case (a quarter of the items heavy) */
+static long ff_sched_threads(long total, int lane_stride, int sched, int heavy_stride)
+{
+    if (lane_stride > 1)
+        return total * lane_stride;
+    if (sched)
+        return ((total / 4 * heavy_stride + 31) & ~31L) + total;
+    return total;
+}
+
 /* ---------------- stage B ---------------- */
 __global__ void __launch_bounds__(CODE_THREADS)
 k_code_range(const FFDevParams P, const FFEncDev E, int nframes)
@@ -295,13 +573,9 @@ k_code_range(const FFDevParams P, const FFEncDev E, int nframes)
     __syncthreads();
     ff_fill_tab16(threadIdx.x, CODE_THREADS);
     __syncthreads();
-    int tid = blockIdx.x * CODE_THREADS + threadIdx.x;
-    if (E.lane_stride > 1) {                                 /* few slices: spread them over the warps */
-        if (tid % E.lane_stride)
-            return;
-        tid /= E.lane_stride;
-    }
-    if (tid >= nframes * P.nslices)
+    const int tid = ff_sched_item(blockIdx.x * CODE_THREADS + threadIdx.x, nframes * P.nslices,
+                                  E.lane_stride, E.sched, E.heavy_stride);
+    if (tid < 0)
         return;
     const int gid = E.order ? (int)E.order[tid] : tid;      /* heaviest slices first */
     const int f = gid / P.nslices, s = gid - f * P.nslices;
@@ -322,13 +596,9 @@ k_code_range(const FFDevParams P, const FFEncDev E, int nframes)
 __global__ void __launch_bounds__(CODE_THREADS)
 k_code_golomb(const FFDevParams P, const FFEncDev E, int nframes)
 {
-    int tid = blockIdx.x * CODE_THREADS + threadIdx.x;
-    if (E.lane_stride > 1) {
-        if (tid % E.lane_stride)
-            return;
-        tid /= E.lane_stride;
-    }
-    if (tid >= nframes * P.nslices)
+    const int tid = ff_sched_item(blockIdx.x * CODE_THREADS + threadIdx.x, nframes * P.nslices,
+                                  E.lane_stride, E.sched, E.heavy_stride);
+    if (tid < 0)
         return;
     const int gid = E.order ? (int)E.order[tid] : tid;
     const int f = gid / P.nslices, s = gid - f * P.nslices;
@@ -432,6 +702,32 @@ extern "C" int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nfr
             if (zr < 1) zr = 1;
             if (zr > 1024) zr = 1024;
             dim3 g2(P->nslices, nframes, zr);
+            /* the bulk-copy form needs samples that are dense in their memory plane (every
+             * planar layout; not the interleaved gray+alpha one).  FFGPU_STAGE_A=legacy keeps
+             * the register/shuffle kernel for A/B runs. */
+            int dense = 1;
+            for (int k = 0; k < P->ncoded; k++)
+                dense &= P->cp[k].step == (P->sbits > 8 ? 2 : 1) && P->cp[k].off == 0;
+            if (dense && !E->legacy_stage_a) {
+                long tiles = 0;
+                for (int k = 0; k < P->ncoded; k++) {
+                    const int wk = ((sw - 1) >> P->cp[k].hs) + 1, hk = ((sh - 1) >> P->cp[k].vs) + 1;
+                    tiles += (long)((wk + SB_TX - 1) / SB_TX) * ((hk + SB_TY - 1) / SB_TY);
+                }
+                /* a few strips per CTA so that the double buffering has something to overlap */
+                int zb = (int)((tiles + 3) / 4);
+                if (zb < 1) zb = 1;
+                if (zb > 1024) zb = 1024;
+                dim3 g3(P->nslices, nframes, zb);
+#define SB_LAUNCH(W, F) k_symbolize_bulk<W, F><<<g3, SB_THREADS, 0, st>>>(*P, E->slices, E->frames, E->qt, \
+                                                                          E->tokens, E->weight)
+                if (P->sbits > 8) {
+                    if (five) SB_LAUNCH(true, true); else SB_LAUNCH(true, false);
+                } else {
+                    if (five) SB_LAUNCH(false, true); else SB_LAUNCH(false, false);
+                }
+#undef SB_LAUNCH
+            } else {
 #define SYM_LAUNCH(W, F) k_symbolize_planar<W, F><<<g2, SYM_THREADS, 0, st>>>(*P, E->slices, E->frames, E->qt, \
                                                                               E->tokens, E->weight)
             if (P->sbits > 8) {
@@ -440,6 +736,7 @@ extern "C" int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nfr
                 if (five) SYM_LAUNCH(false, true); else SYM_LAUNCH(false, false);
             }
 #undef SYM_LAUNCH
+            }
         } else {
             if (E->rct) {
                 /* version 4: the RCT coefficients of every slice first */
@@ -476,10 +773,14 @@ extern "C" int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nfr
         cub::DeviceRadixSort::SortPairsDescending(E->sort_tmp, tmp, E->weight, E->weight_sorted, E->iota,
                                                   E->order, nframes * P->nslices, 0, 32, st);
     }
+    if (E->sched && E->weight && E->order && E->lane_stride <= 1)
+        k_sched<<<1, 1024, 0, st>>>(E->weight_sorted, nframes * P->nslices, E->heavy_factor, E->heavy_stride,
+                                    E->sched);
     mark(E->events, FFK_SORT + 1, st);
     /* stage B */
     {
-        const long total = (long)nframes * P->nslices * (E->lane_stride > 1 ? E->lane_stride : 1);
+        const long total = ff_sched_threads((long)nframes * P->nslices, E->lane_stride,
+                                            E->sched && E->weight && E->order, E->heavy_stride);
         const int blocks = (int)((total + CODE_THREADS - 1) / CODE_THREADS);
         if (P->ac == FF_AC_GOLOMB)
             k_code_golomb<<<blocks, CODE_THREADS, 0, st>>>(*P, *E, nframes);
@@ -583,13 +884,9 @@ k_decode(const FFDevParams P, const FFDecDev D, int nframes)
     __syncthreads();
     /* the planar path keeps every lane of a warp inside the decode loop (lanes without a
      * slice idle there), so nothing returns before the call */
-    int tid = blockIdx.x * CODE_THREADS + threadIdx.x;
-    bool have = true;
-    if (D.lane_stride > 1) {
-        have = tid % D.lane_stride == 0;
-        tid /= D.lane_stride;
-    }
-    have = have && tid < nframes * D.max_slices;
+    const int tid = ff_sched_item(blockIdx.x * CODE_THREADS + threadIdx.x, nframes * D.max_slices,
+                                  D.lane_stride, D.sched, D.heavy_stride);
+    const bool have = tid >= 0;
     if (SMODE == 0 && !have)
         return;
     const int gid = have ? (D.order ? (int)D.order[tid] : tid) : 0;   /* largest slices first */
@@ -692,10 +989,12 @@ extern "C" int ffk_decode_group(const FFDevParams *P, const FFDecDev *D, int nfr
         cub::DeviceRadixSort::SortPairsDescending(D->sort_tmp, tmp, D->weight, D->weight_sorted, D->iota,
                                                   D->order, total, 0, 32, st);
     }
+    if (D->sched && D->weight && D->order && D->lane_stride <= 1)
+        k_sched<<<1, 1024, 0, st>>>(D->weight_sorted, total, D->heavy_factor, D->heavy_stride, D->sched);
     mark(D->events, FFK_DEC_SORT + 1, st);
     {
-        const int stride = D->lane_stride > 1 ? D->lane_stride : 1;
-        const long threads = (long)total * stride;
+        const long threads = ff_sched_threads(total, D->lane_stride, D->sched && D->weight && D->order,
+                                              D->heavy_stride);
         const unsigned blocks = (unsigned)((threads + CODE_THREADS - 1) / CODE_THREADS);
         const size_t smem = (size_t)D->qt_count * FF_QT_STRIDE * sizeof(int16_t);
         const int planar = D->generic ? 0 : ff_decode_planar_mode(P);

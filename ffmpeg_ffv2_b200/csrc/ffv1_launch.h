@@ -14,6 +14,19 @@ extern "C" {
 
 typedef void *ffk_stream;      /* cudaStream_t */
 
+/* Which slice a coder thread takes.  The slices of a launch are sorted by weight (binary
+ * decisions / bytes), heaviest first.  A launch lasts as long as its heaviest slices, and a
+ * warp whose 32 lanes all carry heavy, unrelated slices is the slowest way to run them (every
+ * iteration executes the divergent paths of 32 coders).  The heaviest slices -- those above
+ * heavy_factor x the mean weight, at most a quarter of all -- therefore run `heavy_stride`
+ * lanes apart (8 per warp for stride 4), the rest one per lane.  k_sched derives n_heavy on
+ * the device from the sorted weights; the grid is sized for the worst case and surplus
+ * threads leave at once. */
+typedef struct FFSched {
+    uint32_t n_heavy;               /* sorted items [0, n_heavy) are the heavy class     */
+    uint32_t heavy_threads;         /* threads reserved for them (a multiple of 32)      */
+} FFSched;
+
 /* encoder work arrays of one launch group (all device pointers) */
 typedef struct FFEncDev {
     const FFDevSlice *slices;       /* [nslices]                                        */
@@ -43,6 +56,10 @@ typedef struct FFEncDev {
     void *sort_tmp;
     size_t sort_tmp_bytes;
     int lane_stride;                /* slice coders: 1 = every lane codes a slice ... 32 = one per warp */
+    int legacy_stage_a;             /* 1: k_symbolize_planar instead of the bulk-copy kernel */
+    FFSched *sched;                 /* heavy / light classes of this launch, or NULL      */
+    int heavy_stride;               /* lanes between two heavy slices (power of two)      */
+    float heavy_factor;
     /* version 4: slice_rct_by/ry_coef per (frame, slice), chosen on the device */
     int *rct;                       /* [nframes][nslices][2] or NULL (version <= 3)      */
     int32_t *rct_stat;              /* [nframes][nslices][16] scratch of the reduction   */
@@ -93,6 +110,9 @@ typedef struct FFDecDev {
     int touched_words;
     int any_five;                   /* some quant table uses 5 context inputs           */
     int lane_stride;                /* 1: every lane decodes a slice; 32: one slice per warp */
+    FFSched *sched;                 /* heavy / light classes of this launch, or NULL     */
+    int heavy_stride;
+    float heavy_factor;
     int generic;                    /* 1: use the generic slice decoder even where the planar one applies */
     uint32_t *weight;               /* [nframes*max_slices] slice byte counts            */
     uint32_t *weight_sorted;
