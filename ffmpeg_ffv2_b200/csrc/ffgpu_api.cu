@@ -828,7 +828,7 @@ static void enc_fill_dev(const ffgpu_encoder *e, const EncJob *j, const uint8_t 
     E->rct_stat = j->d_rct_stat;
     {
         const char *env = getenv("FFGPU_STAGE_A");
-        E->legacy_stage_a = env && !strcmp(env, "legacy");
+        E->legacy_stage_a = env && !strcmp(env, "legacy") ? 1 : env && !strcmp(env, "bulk") ? -1 : 0;
     }
     E->heavy_stride = heavy_stride_opt();
     E->heavy_factor = heavy_factor_opt();

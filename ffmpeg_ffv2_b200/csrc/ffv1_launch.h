@@ -56,7 +56,7 @@ typedef struct FFEncDev {
     void *sort_tmp;
     size_t sort_tmp_bytes;
     int lane_stride;                /* slice coders: 1 = every lane codes a slice ... 32 = one per warp */
-    int legacy_stage_a;             /* 1: k_symbolize_planar instead of the bulk-copy kernel */
+    int legacy_stage_a;             /* 1: always k_symbolize_planar, -1: always the bulk-copy kernel, 0: by slice width */
     FFSched *sched;                 /* heavy / light classes of this launch, or NULL      */
     int heavy_stride;               /* lanes between two heavy slices (power of two)      */
     float heavy_factor;
