@@ -721,7 +721,7 @@ def main():
                 raise SystemExit("PARITY FAILURE: pageable e2e path differs from the device path / the input")
             e2e["pageable"] = {"value": B * R2 * world / t_pg, "unit": "frames/s",
                                "buffers": "malloc'd (numpy) pictures in and out, staged by the library "
-                                          "(FFGPU_COPY_THREADS=%s)" % os.environ.get("FFGPU_COPY_THREADS", "4")}
+                                          "(FFGPU_COPY_THREADS=%s)" % os.environ.get("FFGPU_COPY_THREADS", "8")}
             del pg_src, pg_out
 
     clocks = sampler.stop()            # samples of both timed regions (device-resident + e2e)

@@ -31,6 +31,7 @@ class EncOptions(C.Structure):
         ("strict_std_compliance", C.c_int), ("bits_per_raw_sample", C.c_int),
         ("device", C.c_int), ("max_batch", C.c_int), ("pipeline_depth", C.c_int),
         ("ndevices", C.c_int), ("devices", C.c_int * 16),
+        ("pass1", C.c_int), ("pass2", C.c_int), ("stats_in", C.c_char_p),
     ]
 
 
@@ -77,6 +78,7 @@ SYMBOLS = [
                                                   C.POINTER(C.c_size_t)]),
     ("ffgpu_ffv1_encode_device_fetch", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t,
                                                  C.POINTER(C.c_size_t)]),
+    ("ffgpu_ffv1_encoder_stats_out", C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     ("ffgpu_ffv1_encode_close", C.c_int, [C.c_void_p]),
     ("ffgpu_ffv1_decode_init", C.c_int, [C.POINTER(C.c_void_p), C.POINTER(DecOptions)]),
     ("ffgpu_ffv1_decoder_pix_fmt", C.c_char_p, [C.c_void_p]),
@@ -164,11 +166,13 @@ class FFV1Encoder:
 
     def __init__(self, width, height, pix_fmt, slices=0, level=-99, gop_size=12, coder=0, context=0,
                  slicecrc=-1, strict=0, bits_per_raw_sample=0, device=0, max_batch=0,
-                 pipeline_depth=0, devices=()):
+                 pipeline_depth=0, devices=(), pass1=0, pass2=0, stats_in=None):
         self._fmt = pix_fmt.encode()
+        self._stats = stats_in.encode() if isinstance(stats_in, str) else stats_in
         self.opt = EncOptions(width, height, self._fmt, slices, level, gop_size, coder, context,
                               slicecrc, strict, bits_per_raw_sample, device, max_batch,
-                              pipeline_depth, len(devices), (C.c_int * 16)(*devices))
+                              pipeline_depth, len(devices), (C.c_int * 16)(*devices),
+                              pass1, pass2, self._stats)
         self.h = C.c_void_p()
         r = lib().ffgpu_ffv1_encode_init(C.byref(self.h), C.byref(self.opt))
         if r < 0:
@@ -263,6 +267,14 @@ class FFV1Encoder:
         if n < 0:
             raise FFGpuError("encoder_kernel_ms", n, _err())
         return dict(zip(self.ENC_KERNELS, list(ms)[:n]))
+
+    def stats_out(self):
+        """AVCodecContext.stats_out of a first pass (text)"""
+        buf = C.create_string_buffer(6 << 20)
+        n = lib().ffgpu_ffv1_encoder_stats_out(self.h, buf, len(buf))
+        if n < 0:
+            raise FFGpuError("encoder_stats_out", n, _err())
+        return buf.raw[:n].decode()
 
     def decisions(self):
         """(total binary decisions, decisions of the heaviest slice) of the last device batch"""

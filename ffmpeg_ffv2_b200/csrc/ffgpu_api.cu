@@ -275,7 +275,7 @@ static int copy_picture(const FFDevParams *P, const FFPixFmt *pf, int w, int h, 
  * therefore cross through pinned staging buffers owned by the handle: the host side of the
  * copy is a plain memcpy, split over a few worker threads (one core moves ~10 GB/s, a 4K
  * 10-bit picture is 25 MB), and the PCIe side is one linear asynchronous copy per picture.
- * Pinned, registered or device pointers skip all of this.  FFGPU_COPY_THREADS (default 4,
+ * Pinned, registered or device pointers skip all of this.  FFGPU_COPY_THREADS (default 8,
  * 1 = the calling thread only) sizes the pool. */
 enum { MEM_PAGEABLE = 0, MEM_PINNED, MEM_DEVICE };
 
@@ -345,7 +345,7 @@ static void *pool_worker(void *)
 static void pool_start(void)
 {
     const char *env = getenv("FFGPU_COPY_THREADS");
-    int n = env ? atoi(env) : 4;
+    int n = env ? atoi(env) : 8;
     if (n < 1) n = 1;
     if (n > POOL_MAX_THREADS) n = POOL_MAX_THREADS;
     for (int i = 0; i < n - 1; i++) {              /* the calling thread is one of the n */
@@ -360,11 +360,14 @@ static void pool_start(void)
 static void par_copy(const CopyTask *tasks, int ntasks)
 {
     pthread_once(&g_pool.once, pool_start);
-    if (g_pool.nthreads == 0 || pthread_mutex_trylock(&g_pool.use) != 0) {
+    if (g_pool.nthreads == 0) {
         for (int i = 0; i < ntasks; i++)
             copy_rows(&tasks[i]);
         return;
     }
+    /* one picture at a time through the pool: an encoder and a decoder thread that both
+     * stage pictures queue here, each copy then runs at the pool's full width */
+    pthread_mutex_lock(&g_pool.use);
     pthread_mutex_lock(&g_pool.lock);
     g_pool.nchunks = 0;
     for (int i = 0; i < ntasks; i++) {
@@ -505,6 +508,11 @@ struct ffgpu_encoder {
     uint64_t launches;
     int profile;                        /* record events around every kernel of device batches */
     void *events[FFK_ENC_KERNELS + 1];
+    /* two-pass coding */
+    unsigned long long *d_rc_stat, *d_rc_stat2;   /* first pass: decision counters (device) */
+    uint8_t *d_initial;                           /* second pass: [total_ctx][32]           */
+    uint64_t gob_count;                           /* key frames coded (ffv1enc.c:1206)      */
+    char *stats_in;
     /* more than one GPU: this handle only routes; sub[i] is a complete encoder on devices[i].
      * Picture k belongs to sub[(k / chunk) % nsub]; packets are returned in that order. */
     int nsub, chunk, send_blocked;
@@ -561,6 +569,20 @@ static int enc_device_init(ffgpu_encoder *e)
     CK(cudaMalloc(&e->d_prefix_bytes, (size_t)NPREFIX_SETS * P->nslices * e->prefix_stride));
     if (!e->intra) {
         CK(cudaMalloc(&e->d_state_shared, state_frame));
+    }
+    if (e->opt.pass1 && !golomb) {
+        const size_t n2 = (size_t)e->s.ctx_count[e->s.context_model] * 32 * 2 * sizeof(unsigned long long);
+        CK(cudaMalloc(&e->d_rc_stat, 256 * 2 * sizeof(unsigned long long)));
+        CK(cudaMemset(e->d_rc_stat, 0, 256 * 2 * sizeof(unsigned long long)));
+        CK(cudaMalloc(&e->d_rc_stat2, n2));
+        CK(cudaMemset(e->d_rc_stat2, 0, n2));
+    }
+    if (e->s.initial[e->s.context_model] && !golomb) {
+        /* one row per context of a slice: the table's initial states, repeated per plane set */
+        const size_t per = (size_t)e->s.ctx_count[e->s.context_model] * FF_CONTEXT_SIZE;
+        CK(cudaMalloc(&e->d_initial, per * P->nsets));
+        for (int k = 0; k < P->nsets; k++)
+            CK(cudaMemcpy(e->d_initial + per * k, e->s.initial[e->s.context_model], per, cudaMemcpyHostToDevice));
     }
     {
         const size_t n = (size_t)e->max_batch * P->nslices;
@@ -642,6 +664,10 @@ extern "C" int ffgpu_ffv1_encode_init(ffgpu_encoder **penc, const ffgpu_enc_opti
     e->opt = *opt;
     snprintf(e->pix_fmt, sizeof(e->pix_fmt), "%s", opt->pix_fmt ? opt->pix_fmt : "");
     e->opt.pix_fmt = e->pix_fmt;
+    if (opt->stats_in) {
+        e->stats_in = strdup(opt->stats_in);
+        e->opt.stats_in = e->stats_in;
+    }
     if ((r = ff_stream_from_options(&e->s, &e->opt)) < 0) {
         free(e);
         return fail(r, "encode_init: options rejected (%d)", r);
@@ -826,6 +852,10 @@ static void enc_fill_dev(const ffgpu_encoder *e, const EncJob *j, const uint8_t 
     E->lane_stride = coder_lane_stride((long)j->n * e->P.nslices);
     E->rct = j->d_rct;
     E->rct_stat = j->d_rct_stat;
+    E->rc_stat = e->d_rc_stat;
+    E->rc_stat2 = e->d_rc_stat2;
+    E->stat_ctx_count = e->s.ctx_count[e->s.context_model];
+    E->initial = e->d_initial;
     {
         const char *env = getenv("FFGPU_STAGE_A");
         E->legacy_stage_a = env && !strcmp(env, "legacy") ? 1 : env && !strcmp(env, "bulk") ? -1 : 0;
@@ -1032,6 +1062,7 @@ extern "C" int ffgpu_ffv1_encode_send_frame(ffgpu_encoder *e, const ffgpu_pictur
         return r;
     j->h_frame_set[j->n] = (uint8_t)set;
     j->h_frame_key[j->n] = (uint8_t)key;
+    e->gob_count += key;
     j->pts[j->n] = pic->pts;
     j->key[j->n] = key;
     j->n++;
@@ -1189,6 +1220,7 @@ extern "C" int ffgpu_ffv1_encode_device(ffgpu_encoder *e, const void *d_frames, 
         j->h_frame_set[i] = (uint8_t)set;
         j->h_frame_key[i] = (uint8_t)key;
         j->key[i] = key;
+        e->gob_count += key;
     }
     e->picture_number += nframes;
     j->n = nframes;
@@ -1254,6 +1286,73 @@ extern "C" int ffgpu_ffv1_encode_device_fetch(ffgpu_encoder *e, int frame, uint8
     CK(cudaMemcpy(pkt, d, n, cudaMemcpyDeviceToHost));
     if (pkt_size) *pkt_size = n;
     return 0;
+}
+
+/* the counters of this handle (and of its sub-handles) added into host arrays */
+static int enc_collect_stats(ffgpu_encoder *e, uint64_t *rc, uint64_t *rc2, size_t n2, uint64_t *gob)
+{
+    for (int i = 0; i < e->nsub; i++) {
+        int r = enc_collect_stats(e->sub[i], rc, rc2, n2, gob);
+        if (r < 0)
+            return r;
+    }
+    *gob += e->gob_count;
+    if (e->dev_ready && e->d_rc_stat) {
+        uint64_t *tmp = (uint64_t *)malloc((512 + n2) * sizeof(uint64_t));
+        if (!tmp)
+            return fail(FFGPU_ENOMEM, "out of memory");
+        cudaSetDevice(e->opt.device);
+        if (cudaDeviceSynchronize() != cudaSuccess ||
+            cudaMemcpy(tmp, e->d_rc_stat, 512 * sizeof(uint64_t), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(tmp + 512, e->d_rc_stat2, n2 * sizeof(uint64_t), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            free(tmp);
+            return fail(FFGPU_EXTERNAL, "CUDA: copy of the first-pass counters failed");
+        }
+        for (size_t k = 0; k < 512; k++)
+            rc[k] += tmp[k];
+        for (size_t k = 0; k < n2; k++)
+            rc2[k] += tmp[512 + k];
+        free(tmp);
+    }
+    return 0;
+}
+
+extern "C" int ffgpu_ffv1_encoder_stats_out(ffgpu_encoder *e, char *buf, size_t cap)
+{
+    /* the text of ffv1enc.c:1160-1175: rc_stat, newline, rc_stat2 of every quant table (only
+     * the encoder's own table was ever counted), the number of key frames, newline */
+    if (!e || !buf)
+        return fail(FFGPU_EINVAL, "null argument");
+    if (!e->opt.pass1)
+        return fail(FFGPU_EINVAL, "not a first pass");
+    const FFStream *s = &e->s;
+    const size_t n2 = (size_t)s->ctx_count[s->context_model] * 64;
+    uint64_t *rc = (uint64_t *)calloc(512 + n2, sizeof(uint64_t)), gob = 0;
+    size_t pos = 0;
+    int r;
+    if (!rc)
+        return fail(FFGPU_ENOMEM, "out of memory");
+    if ((r = enc_collect_stats(e, rc, rc + 512, n2, &gob)) < 0) {
+        free(rc);
+        return r;
+    }
+#define OUT_(...) do { int w_ = snprintf(buf + pos, cap - pos, __VA_ARGS__); \
+                       if (w_ < 0 || (size_t)w_ >= cap - pos) { free(rc); return fail(FFGPU_ENOSPC, "stats buffer too small"); } \
+                       pos += (size_t)w_; } while (0)
+    for (int j = 0; j < 256; j++)
+        OUT_("%llu %llu ", (unsigned long long)rc[2 * j], (unsigned long long)rc[2 * j + 1]);
+    /* (the reference prints a newline here without advancing its pointer, ffv1enc.c:1165: the
+     * next number overwrites it, so there is none) */
+    for (int i = 0; i < s->qt_count; i++)
+        for (int j = 0; j < s->ctx_count[i]; j++)
+            for (int m = 0; m < 32; m++) {
+                const uint64_t *v = i == s->context_model ? rc + 512 + ((size_t)j * 32 + m) * 2 : NULL;
+                OUT_("%llu %llu ", (unsigned long long)(v ? v[0] : 0), (unsigned long long)(v ? v[1] : 0));
+            }
+    OUT_("%d\n", (int)gob);
+#undef OUT_
+    free(rc);
+    return (int)pos;
 }
 
 extern "C" int ffgpu_ffv1_encoder_decisions(ffgpu_encoder *e, uint64_t *total, uint32_t *heaviest)
@@ -1332,7 +1431,9 @@ extern "C" int ffgpu_ffv1_encode_close(ffgpu_encoder *e)
         if (e->up_stream) cudaStreamDestroy(e->up_stream);
         cudaFree(e->d_slices); cudaFree(e->d_qt); cudaFree(e->d_tab); cudaFree(e->d_prefix);
         cudaFree(e->d_prefix_bytes); cudaFree(e->d_state_shared); cudaFree(e->d_iota);
+        cudaFree(e->d_rc_stat); cudaFree(e->d_rc_stat2); cudaFree(e->d_initial);
     }
+    free(e->stats_in);
     free(e->h_slices);
     free(e->extradata);
     ff_stream_free(&e->s);

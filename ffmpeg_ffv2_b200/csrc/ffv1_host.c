@@ -13,6 +13,7 @@
 #include "ffv1_host.h"
 
 #include <limits.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -273,6 +274,200 @@ static void wl32(uint8_t *p, uint32_t v)
 /* ------------------------------------------------------------------ */
 /* encoder option resolution                                            */
 /* ------------------------------------------------------------------ */
+/* ------------------------------------------------------------------ */
+/* second pass: tables from the first pass's statistics                  */
+/* ------------------------------------------------------------------ */
+/* Everything here is floating point in the reference and decides bytes of the extradata, so
+ * the expressions are evaluated in the reference's order (ffv1enc.c:139-183, :469-515,
+ * :793-873); the integer parts are restated freely. */
+
+/* find_best_state, ffv1enc.c:139-183: for a true probability i/256 and k further symbols,
+ * which starting state (within +-10 of i) costs the fewest expected bits */
+static void best_start_states(uint8_t (*best)[256], const uint8_t one_state[256])
+{
+    double l2[256];
+    int i, j, k, m;
+    for (i = 1; i < 256; i++)
+        l2[i] = log2(i / 256.0);
+    for (i = 0; i < 256; i++) {
+        double best_len[256];
+        const double p = i / 256.0;
+        for (j = 0; j < 256; j++)
+            best_len[j] = 1 << 30;
+        for (j = FFMAX(i - 10, 1); j < FFMIN(i + 11, 256); j++) {
+            double occ[256] = { 0 };
+            double len = 0;
+            occ[j] = 1.0;
+            if (!one_state[j])
+                continue;
+            for (k = 0; k < 256; k++) {
+                double next[256] = { 0 };
+                for (m = 1; m < 256; m++)
+                    if (occ[m])
+                        len -= occ[m] * (p * l2[m] + (1 - p) * l2[256 - m]);
+                if (len < best_len[k]) {
+                    best_len[k] = len;
+                    best[i][k] = (uint8_t)j;
+                }
+                for (m = 1; m < 256; m++)
+                    if (occ[m]) {
+                        next[one_state[m]] += occ[m] * p;
+                        next[256 - one_state[256 - m]] += occ[m] * (1 - p);
+                    }
+                memcpy(occ, next, sizeof(occ));
+            }
+        }
+    }
+}
+
+/* the reference swaps its 64-bit counters through an int (FFSWAP(int, ...), ffv1enc.c:490) */
+static void swap_through_int(uint64_t *a, uint64_t *b)
+{
+    const int t = (int)*b;
+    *b = *a;
+    *a = (uint64_t)(int64_t)t;
+}
+
+/* sort_stt, ffv1enc.c:469-515: exchange neighbouring states of the transition table while
+ * that shortens the first pass's decisions */
+static void sort_transitions(uint64_t rc[256][2], uint8_t stt[256])
+{
+    int changed, i, i2, j;
+#define COST_(o, n) (rc[o][0] * -log2((256 - (n)) / 256.0) + rc[o][1] * -log2((n) / 256.0))
+#define COST2_(o, n) (COST_(o, n) + COST_(256 - (o), 256 - (n)))
+    do {
+        changed = 0;
+        for (i = 12; i < 244; i++)
+            for (i2 = i + 1; i2 < 245 && i2 < i + 4; i2++) {
+                const double size0 = COST2_(i, i) + COST2_(i2, i2);
+                const double sizeX = COST2_(i, i2) + COST2_(i2, i);
+                if (size0 - sizeX > size0 * (1e-14) && i != 128 && i2 != 128) {
+                    uint8_t t = stt[i];
+                    stt[i] = stt[i2];
+                    stt[i2] = t;
+                    swap_through_int(&rc[i][0], &rc[i2][0]);
+                    swap_through_int(&rc[i][1], &rc[i2][1]);
+                    if (i != 256 - i2) {
+                        t = stt[256 - i];
+                        stt[256 - i] = stt[256 - i2];
+                        stt[256 - i2] = t;
+                        swap_through_int(&rc[256 - i][0], &rc[256 - i2][0]);
+                        swap_through_int(&rc[256 - i][1], &rc[256 - i2][1]);
+                    }
+                    for (j = 1; j < 256; j++) {
+                        if (stt[j] == i)
+                            stt[j] = (uint8_t)i2;
+                        else if (stt[j] == i2)
+                            stt[j] = (uint8_t)i;
+                        if (i != 256 - i2) {
+                            if (stt[256 - j] == 256 - i)
+                                stt[256 - j] = (uint8_t)(256 - i2);
+                            else if (stt[256 - j] == 256 - i2)
+                                stt[256 - j] = (uint8_t)(256 - i);
+                        }
+                    }
+                    changed = 1;
+                }
+            }
+    } while (changed);
+#undef COST_
+#undef COST2_
+}
+
+static int clip_int(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }
+
+/* AVCodecContext.stats_in -> s->trans (sorted) and s->initial[], ffv1enc.c:793-873 */
+static int second_pass_tables(FFStream *s, const char *stats)
+{
+    static uint64_t rc[256][2];                 /* as in the reference the LAST block of the file counts */
+    uint64_t (*rc2[FF_MAX_QUANT_TABLES])[32][2] = { 0 };
+    uint8_t (*best)[256] = NULL;
+    const char *p = stats;
+    char *next;
+    int gob_count = 0, i, j, k, m, ret = FFGPU_INVALIDDATA;
+
+    for (i = 0; i < s->qt_count; i++) {
+        rc2[i] = calloc((size_t)s->ctx_count[i], sizeof(*rc2[i]));
+        if (!rc2[i]) {
+            ret = FFGPU_ENOMEM;
+            goto done;
+        }
+    }
+    for (;;) {
+        for (j = 0; j < 256; j++)
+            for (i = 0; i < 2; i++) {
+                rc[j][i] = (uint64_t)strtol(p, &next, 0);
+                if (next == p)
+                    goto done;                  /* "2Pass file invalid" */
+                p = next;
+            }
+        for (i = 0; i < s->qt_count; i++)
+            for (j = 0; j < s->ctx_count[i]; j++)
+                for (k = 0; k < 32; k++)
+                    for (m = 0; m < 2; m++) {
+                        rc2[i][j][k][m] = (uint64_t)strtol(p, &next, 0);
+                        if (next == p)
+                            goto done;
+                        p = next;
+                    }
+        gob_count = (int)strtol(p, &next, 0);
+        if (next == p || gob_count <= 0)
+            goto done;
+        p = next;
+        while (*p == '\n' || *p == ' ')
+            p++;
+        if (!p[0])
+            break;
+    }
+    if (s->ac == FF_AC_CUSTOM)
+        sort_transitions(rc, s->trans);
+    best = malloc(256 * 256);
+    if (!best) {
+        ret = FFGPU_ENOMEM;
+        goto done;
+    }
+    memset(best, 0, 256 * 256);
+    best_start_states(best, s->trans);
+    for (i = 0; i < s->qt_count; i++) {
+        uint8_t *init = malloc((size_t)s->ctx_count[i] * FF_CONTEXT_SIZE);
+        if (!init) {
+            ret = FFGPU_ENOMEM;
+            goto done;
+        }
+        memset(init, 128, (size_t)s->ctx_count[i] * FF_CONTEXT_SIZE);
+        free(s->initial[i]);
+        s->initial[i] = init;
+        for (k = 0; k < 32; k++) {
+            double a = 0, b = 0;
+            int jp = 0;
+            for (j = 0; j < s->ctx_count[i]; j++) {
+                double pr = 128;
+                if ((rc2[i][j][k][0] + rc2[i][j][k][1] > 200 && j) || a + b > 200) {
+                    if (a + b)
+                        pr = 256.0 * b / (a + b);
+                    init[jp * FF_CONTEXT_SIZE + k] =
+                        best[clip_int((int)round(pr), 1, 255)][clip_int((int)((a + b) / gob_count), 0, 255)];
+                    for (jp++; jp < j; jp++)
+                        init[jp * FF_CONTEXT_SIZE + k] = init[(jp - 1) * FF_CONTEXT_SIZE + k];
+                    a = b = 0;
+                }
+                a += rc2[i][j][k][0];
+                b += rc2[i][j][k][1];
+                if (a + b)
+                    pr = 256.0 * b / (a + b);
+                init[j * FF_CONTEXT_SIZE + k] =
+                    best[clip_int((int)round(pr), 1, 255)][clip_int((int)((a + b) / gob_count), 0, 255)];
+            }
+        }
+    }
+    ret = 0;
+done:
+    for (i = 0; i < FF_MAX_QUANT_TABLES; i++)
+        free(rc2[i]);
+    free(best);
+    return ret;
+}
+
 int ff_stream_from_options(FFStream *s, const ffgpu_enc_options *o)
 {
     const FFPixFmt *pf = ff_find_pixfmt(o->pix_fmt);
@@ -287,7 +482,7 @@ int ff_stream_from_options(FFStream *s, const ffgpu_enc_options *o)
     ff_default_tables(&s->def_tab);
 
     /* version, ffv1enc.c:526-558 */
-    if (o->slices > 1)
+    if (o->slices > 1 || o->pass1 || o->pass2)
         s->version = FFMAX(s->version, 2);
     if (o->slices == 0 && o->level < 0 && o->width * o->height > 720 * 576)
         s->version = FFMAX(s->version, 2);
@@ -373,6 +568,15 @@ int ff_stream_from_options(FFStream *s, const ffgpu_enc_options *o)
         ff_install_custom(&s->cur_tab, s->trans);
 
     build_quant_tables(s);
+    if (o->stats_in && o->stats_in[0]) {
+        int r = second_pass_tables(s, o->stats_in);
+        if (r < 0)
+            return r;
+        if (ac == FF_AC_CUSTOM) {              /* sort_stt may have reordered the table */
+            s->cur_tab = s->def_tab;
+            ff_install_custom(&s->cur_tab, s->trans);
+        }
+    }
     s->plane_sets = s->transparency ? 3 : 2;   /* v<=3: ffv1enc.c:769-772 */
     s->hs = pf->layout == FF_LAY_PLANAR && pf->chroma ? pf->hs : 0;
     s->vs = pf->layout == FF_LAY_PLANAR && pf->chroma ? pf->vs : 0;
@@ -456,11 +660,11 @@ int ff_write_extradata(FFStream *s, int gop_size, uint8_t **data, int *size)
     *size = 0;
     if (s->version < 2)
         return 0;
-    buf = (uint8_t *)malloc(1 << 16);
+    buf = (uint8_t *)malloc(1 << 20);          /* a second pass adds up to 7563 x 32 initial states */
     if (!buf)
         return FFGPU_ENOMEM;
     memset(st, 128, sizeof(st));
-    ffrac_enc_init(&c, buf, (1 << 16) - 8);
+    ffrac_enc_init(&c, buf, (1 << 20) - 8);
 
     ffrac_put_symbol(&c, t, st, s->version, 0);
     if (s->version > 2) {
@@ -483,8 +687,23 @@ int ff_write_extradata(FFStream *s, int gop_size, uint8_t **data, int *size)
     for (i = 0; i < s->qt_count; i++)
         for (j = 0; j < FF_MAX_CTX_INPUTS; j++)
             put_quant_table(&c, t, s->qt[i][j]);
-    for (i = 0; i < s->qt_count; i++)
-        ffrac_put(&c, t, st, 0);           /* initial states all 128 (no 2-pass) */
+    for (i = 0; i < s->qt_count; i++) {
+        /* contains_non_128 / the initial states of a second pass, ffv1enc.c:337-347, :442-455 */
+        int any = 0;
+        size_t q;
+        for (q = 0; s->initial[i] && q < (size_t)s->ctx_count[i] * FF_CONTEXT_SIZE; q++)
+            any |= s->initial[i][q] != 128;
+        ffrac_put(&c, t, st, any);
+        if (any) {
+            uint8_t st2[FF_CONTEXT_SIZE][FF_CONTEXT_SIZE];
+            memset(st2, 128, sizeof(st2));
+            for (j = 0; j < s->ctx_count[i]; j++)
+                for (int k = 0; k < FF_CONTEXT_SIZE; k++) {
+                    const int pred = j ? s->initial[i][(j - 1) * FF_CONTEXT_SIZE + k] : 128;
+                    ffrac_put_symbol(&c, t, st2[k], (int8_t)(s->initial[i][j * FF_CONTEXT_SIZE + k] - pred), 1);
+                }
+        }
+    }
     if (s->version > 2) {
         s->intra = gop_size < 2;
         ffrac_put_symbol(&c, t, st, s->ec, 0);

@@ -562,6 +562,21 @@ static long ff_sched_threads(long total, int lane_stride, int sched, int heavy_s
     return total;
 }
 
+/* second pass: the slices of key frames start from the initial states of the extradata
+ * (ff_ffv1_clear_slice_state with initial_states, ffv1.c:192-197) */
+__global__ void k_fill_state_initial(uint4 *__restrict__ state, size_t vec_per_slice, int nslices,
+                                     const uint8_t *__restrict__ frame_key, int state_per_frame,
+                                     const uint4 *__restrict__ initial)
+{
+    const int f = blockIdx.y;
+    if (!frame_key[f])
+        return;
+    uint4 *p = state + (state_per_frame ? (size_t)f * vec_per_slice * nslices : 0);
+    const size_t n = vec_per_slice * nslices;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = initial[i % vec_per_slice];
+}
+
 /* ---------------- stage B ---------------- */
 __global__ void __launch_bounds__(CODE_THREADS)
 k_code_range(const FFDevParams P, const FFEncDev E, int nframes)
@@ -582,12 +597,17 @@ k_code_range(const FFDevParams P, const FFEncDev E, int nframes)
     const FFDevSlice sl = E.slices[s];
     const size_t st_slot = (size_t)(E.state_per_frame ? f : 0) * P.nslices + s;
     uint32_t ovf = 0;
+    FFPassStats pass;
+    pass.rc_stat = E.rc_stat;
+    pass.rc_stat2 = E.rc_stat2;
+    pass.ctx_count = E.stat_ctx_count;
     const uint32_t n = ff_encode_slice_range(
         sl, E.tokens + (size_t)f * P.frame_tokens + sl.tok_off,
         E.state + st_slot * P.total_ctx * FF_CONTEXT_SIZE, &ff_s_tab,
         E.prefix[(size_t)E.frame_prefix_set[f] * P.nslices + s], E.prefix_bytes,
         E.bs + (size_t)f * P.frame_bs + sl.bs_off, &ovf, 0, E.rct ? E.rct + 2 * (size_t)gid : (const int *)0,
-        E.rct ? (uint32_t)((16384 + (int64_t)P.width * P.height * 12) / P.nslices) : 0u);
+        E.rct ? (uint32_t)((16384 + (int64_t)P.width * P.height * 12) / P.nslices) : 0u,
+        E.rc_stat ? &pass : (const FFPassStats *)0);
     E.slice_bytes[gid] = n;
     if (ovf)
         atomicOr(E.overflow, 1u);
@@ -764,9 +784,14 @@ extern "C" int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nfr
         int bx = (int)((words + 255) / 256);
         if (bx > 2048) bx = 2048;
         dim3 grid(bx, nframes);
-        k_fill_state<<<grid, 256, 0, st>>>((uint2 *)E->state, words, E->frame_key, E->state_per_frame,
-                                           golomb ? FF_VLC_INIT_LO : 0x80808080u,
-                                           golomb ? FF_VLC_INIT_HI : 0x80808080u);
+        if (E->initial && !golomb)
+            k_fill_state_initial<<<grid, 256, 0, st>>>((uint4 *)E->state, (size_t)P->total_ctx * FF_CONTEXT_SIZE / 16,
+                                                       P->nslices, E->frame_key, E->state_per_frame,
+                                                       (const uint4 *)E->initial);
+        else
+            k_fill_state<<<grid, 256, 0, st>>>((uint2 *)E->state, words, E->frame_key, E->state_per_frame,
+                                               golomb ? FF_VLC_INIT_LO : 0x80808080u,
+                                               golomb ? FF_VLC_INIT_HI : 0x80808080u);
         mark(E->events, FFK_FILL_STATE + 1, st);
         launches++;
         if (!launch_ok()) return FFGPU_EXTERNAL;

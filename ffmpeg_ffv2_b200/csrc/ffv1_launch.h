@@ -60,6 +60,11 @@ typedef struct FFEncDev {
     FFSched *sched;                 /* heavy / light classes of this launch, or NULL      */
     int heavy_stride;               /* lanes between two heavy slices (power of two)      */
     float heavy_factor;
+    /* two-pass coding: counters of a first pass (or NULL), initial states of a second pass
+     * as one row per context of the slice, [total_ctx][32] (or NULL: every state starts at 128) */
+    unsigned long long *rc_stat, *rc_stat2;
+    int stat_ctx_count;
+    const uint8_t *initial;
     /* version 4: slice_rct_by/ry_coef per (frame, slice), chosen on the device */
     int *rct;                       /* [nframes][nslices][2] or NULL (version <= 3)      */
     int32_t *rct_stat;              /* [nframes][nslices][16] scratch of the reduction   */

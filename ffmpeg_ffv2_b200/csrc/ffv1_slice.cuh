@@ -471,12 +471,33 @@ __device__ __forceinline__ void ff_sts8(uint32_t sa, uint32_t v)
  *   e+2..2e+1        mantissa, MSB first       state[22 + min(i,9)]
  *   2e+2             sign                      state[11 + min(e,10)]
  * returns the slice's byte count; *overflow != 0 if the arena was too small */
+/* first pass (AV_CODEC_FLAG_PASS1): the counters put_symbol_inline keeps, ffv1enc.c:193-199 */
+typedef struct FFPassStats {
+    unsigned long long *rc_stat;    /* [256][2]: decisions by adaptive state value and bit          */
+    unsigned long long *rc_stat2;   /* [contexts of the table][32][2]: by context, state slot, bit  */
+    int ctx_count;                  /* contexts of the encoder's quant table (sets share counters)  */
+} FFPassStats;
+
+FFGPU_HD void ff_pass_count(const FFPassStats *st, int state, int ctx, int slot, int bit)
+{
+    unsigned long long *a = st->rc_stat + 2 * state + bit;
+    unsigned long long *b = st->rc_stat2 + ((size_t)(ctx % st->ctx_count) * 32 + slot) * 2 + bit;
+#if defined(__CUDA_ARCH__)
+    atomicAdd(a, 1ull);
+    atomicAdd(b, 1ull);
+#else
+    (*a)++;
+    (*b)++;
+#endif
+}
+
 FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *tokens,
                                         uint8_t *state, const FFRacTables *tab_,
                                         const FFRacPrefix &pre, const uint8_t *pre_bytes,
                                         uint8_t *out, uint32_t *overflow, uint32_t *row_,
                                         const int *rct = 0,     /* version 4: {by, ry} of the slice */
-                                        uint32_t v4_room = 0)   /* version 4: the reference's slice buffer */
+                                        uint32_t v4_room = 0,   /* version 4: the reference's slice buffer */
+                                        const FFPassStats *pass = 0)  /* first pass: count the decisions */
 {
     FFRacEnc c;
     const uint32_t n = sl.ntok;
@@ -580,6 +601,8 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
         {
             const uint32_t sa = row_sa + slot;
             s = (int)ff_lds8(sa);
+            if (pass)
+                ff_pass_count(pass, s, cur_ctx, (int)slot, bit);
             r1 = (c.range * s) >> 8;                 /* put_rac, rangecoder.h:104-121 */
             rb = c.range - r1;
             ff_sts8(sa, ff_lds8(tab_sa + (uint32_t)s + (bit ? 0u : 256u)));
@@ -590,6 +613,8 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
         {
             const int slot = ff_slot_of(e, step);
             s = FF_ROWB(slot);
+            if (pass)
+                ff_pass_count(pass, s, cur_ctx, slot, bit);
             r1 = (c.range * s) >> 8;
             rb = c.range - r1;
             FF_ROWB(slot) = FF_TAB(s + (bit ? 0 : 256));

@@ -74,6 +74,14 @@ typedef struct ffgpu_enc_options {
      * ffv1enc.c:1332).  ndevices <= 1: the single GPU `device`. */
     int ndevices;
     int devices[FFGPU_MAX_DEVICES];
+    /* Two-pass coding (AV_CODEC_FLAG_PASS1 / _PASS2 and AVCodecContext.stats_in,
+     * ffv1enc.c:528, :785-873, :1134-1177).  pass1: the range coder's decisions are counted
+     * (rc_stat / rc_stat2) and ffgpu_ffv1_encoder_stats_out() returns the text the reference
+     * leaves in AVCodecContext.stats_out after the flush.  stats_in: that text, possibly of
+     * several first passes concatenated; encode_init derives the sorted state transition
+     * table and the initial states per context from it and writes them to the extradata. */
+    int pass1, pass2;
+    const char *stats_in;
 } ffgpu_enc_options;
 
 /* one picture: AVFrame.data/linesize plus the per-frame fields the slice header carries
@@ -145,6 +153,11 @@ int ffgpu_ffv1_encode_device_result(ffgpu_encoder *enc, int frame, const void **
 /* copy the packets of the last ffgpu_ffv1_encode_device() call to host memory */
 int ffgpu_ffv1_encode_device_fetch(ffgpu_encoder *enc, int frame, uint8_t *pkt, size_t pkt_cap,
                                    size_t *pkt_size);
+
+/* AVCodecContext.stats_out of a first pass (ffv1enc.c:1134-1177): the decision statistics of
+ * every picture coded so far, as text.  Call it after the flush (it waits for the pictures
+ * in flight).  Returns the length, or FFGPU_ENOSPC / FFGPU_EINVAL (not a first pass). */
+int ffgpu_ffv1_encoder_stats_out(ffgpu_encoder *enc, char *buf, size_t cap);
 
 /* AVCodec.close = encode_close, ffv1enc.c:1283 */
 int ffgpu_ffv1_encode_close(ffgpu_encoder *enc);

@@ -38,7 +38,8 @@
 #define CUDA_POP(s)  do { } while (0)
 #endif
 
-#define GPU_FIFO 2048          /* >= pictures the launch groups of one handle can hold in flight */
+#define GPU_FIFO 2048
+#define GPU_STATS_OUT_SIZE (1024 * 1024 * 6)   /* STATS_OUT_SIZE, ffv1enc.c:911 */          /* >= pictures the launch groups of one handle can hold in flight */
 
 typedef struct FFV1GpuContext {
     AVClass *class;            /* first member: avcodec_open2 applies the AVOptions (utils.c:630-639) */
@@ -138,10 +139,12 @@ static av_cold int gpu_encode_init(AVCodecContext *avctx)
     o.max_batch = s->max_batch;
     o.pipeline_depth = s->depth;
     set_devices(s, &o.ndevices, o.devices);
-    if (avctx->flags & (AV_CODEC_FLAG_PASS1 | AV_CODEC_FLAG_PASS2)) {
-        avpriv_report_missing_feature(avctx, "2-pass statistics on the GPU path");
-        return AVERROR_PATCHWELCOME;
-    }
+    /* two-pass coding, ffv1enc.c:528, :785-873, :912-916 */
+    o.pass1 = !!(avctx->flags & AV_CODEC_FLAG_PASS1);
+    o.pass2 = !!(avctx->flags & AV_CODEC_FLAG_PASS2);
+    o.stats_in = avctx->stats_in;
+    if (o.pass1 && !(avctx->stats_out = av_mallocz(GPU_STATS_OUT_SIZE)))
+        return AVERROR(ENOMEM);
     CUDA_PUSH(s);
     ret = ffgpu_ffv1_encode_init(&s->enc, &o);
     CUDA_POP(s);
@@ -229,8 +232,17 @@ static int gpu_receive_packet(AVCodecContext *avctx, AVPacket *pkt)
     if (ret < 0) {                             /* EAGAIN, EOF, "encoded frame too large", ... */
         if (ret != AVERROR(EAGAIN) && ret != AVERROR_EOF)
             av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
+        if (ret == AVERROR_EOF && avctx->stats_out) {
+            /* first pass: the statistics appear with the end of the flush (ffv1enc.c:1134-1177) */
+            CUDA_PUSH(s);
+            if (ffgpu_ffv1_encoder_stats_out(s->enc, avctx->stats_out, GPU_STATS_OUT_SIZE) < 0)
+                av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
+            CUDA_POP(s);
+        }
         return ret;
     }
+    if (avctx->stats_out)
+        avctx->stats_out[0] = 0;               /* ffv1enc.c:1264-1265 */
     /* a refcounted packet of exactly that size: avcodec_receive_packet hands it on as it is
      * (libavcodec/encode.c:434-438), there is no encode2 wrapper that would copy it out of
      * the shared byte_buffer ff_alloc_packet2 may return */

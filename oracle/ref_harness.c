@@ -544,6 +544,21 @@ static void harness_free(Harness *h)
     free(h);
 }
 
+/* two-pass coding: AV_CODEC_FLAG_PASS1 / _PASS2 and AVCodecContext.stats_in for the next open */
+static int g_open_flags;
+static const char *g_open_stats_in;
+void *ffv1ref_encoder_open(const FFV1RefParams *p, int *err);
+void *ffv1ref_encoder_open2(const FFV1RefParams *p, int pass1, int pass2, const char *stats_in, int *err)
+{
+    void *h;
+    g_open_flags = (pass1 ? AV_CODEC_FLAG_PASS1 : 0) | (pass2 ? AV_CODEC_FLAG_PASS2 : 0);
+    g_open_stats_in = stats_in;
+    h = ffv1ref_encoder_open(p, err);
+    g_open_flags = 0;
+    g_open_stats_in = NULL;
+    return h;
+}
+
 void *ffv1ref_encoder_open(const FFV1RefParams *p, int *err)
 {
     Harness *h = harness_new(&ff_ffv1_encoder, p->threads);
@@ -564,6 +579,8 @@ void *ffv1ref_encoder_open(const FFV1RefParams *p, int *err)
     a->gop_size = p->gop_size;
     a->strict_std_compliance = p->strict;
     a->bits_per_raw_sample = p->bits_per_raw_sample;
+    a->flags |= g_open_flags;
+    a->stats_in = (char *)g_open_stats_in;
     /* AVOption defaults of ffv1enc.c:1291-1307, then the caller's values */
 #ifdef HARNESS_GPU
     (void)s;
@@ -585,6 +602,27 @@ void *ffv1ref_encoder_open(const FFV1RefParams *p, int *err)
     *err = 0;
     return h;
 }
+
+#ifndef HARNESS_GPU
+/* the flush call of a first pass (encode2 with a NULL frame, ffv1enc.c:1134-1177) leaves the
+ * statistics in AVCodecContext.stats_out */
+int ffv1ref_encoder_stats_out(void *hh, char *buf, int cap)
+{
+    Harness *h = hh;
+    AVCodecContext *a = h->avctx;
+    AVPacket pkt;
+    int got = 0, n;
+    if (!(a->flags & AV_CODEC_FLAG_PASS1) || !a->stats_out)
+        return AVERROR(EINVAL);
+    memset(&pkt, 0, sizeof(pkt));
+    ff_ffv1_encoder.encode2(a, &pkt, NULL, &got);
+    n = (int)strlen(a->stats_out);
+    if (n >= cap)
+        return AVERROR(ENOSPC);
+    memcpy(buf, a->stats_out, n + 1);
+    return n;
+}
+#endif
 
 int ffv1ref_encoder_extradata(void *hh, const uint8_t **data)
 {

@@ -103,13 +103,23 @@ class CodecError(RuntimeError):
 
 class Encoder:
     def __init__(self, which, width, height, pix_fmt, slices=0, level=-99, gop_size=12, coder=0,
-                 context=0, slicecrc=-1, strict=0, threads=1, bits_per_raw_sample=0):
+                 context=0, slicecrc=-1, strict=0, threads=1, bits_per_raw_sample=0,
+                 pass1=0, pass2=0, stats_in=None):
         self.a = api(which)
         self._fmt = pix_fmt.encode()
         self.p = Params(width, height, self._fmt, slices, level, gop_size, coder, context,
                         slicecrc, strict, threads, bits_per_raw_sample)
         err = C.c_int()
-        self.h = self.a.encoder_open(C.byref(self.p), C.byref(err))
+        if pass1 or pass2 or stats_in:
+            # two-pass coding: only the checkers that have it ("ref", "emul")
+            self._stats = stats_in.encode() if isinstance(stats_in, str) else stats_in
+            fn = getattr(self.a.lib, PATHS[which][1] + "encoder_open2")
+            fn.restype = C.c_void_p
+            fn.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_int)]
+            self.h = fn(C.byref(self.p), pass1, pass2, self._stats, C.byref(err))
+        else:
+            self.h = self.a.encoder_open(C.byref(self.p), C.byref(err))
+        self.which = which
         if not self.h:
             raise CodecError("%s encoder init" % which, err.value)
         self.width, self.height, self.pix_fmt = width, height, pix_fmt
@@ -120,6 +130,16 @@ class Encoder:
         ptr = C.POINTER(C.c_uint8)()
         n = self.a.encoder_extradata(self.h, C.byref(ptr))
         return bytes(bytearray(ptr[:n])) if n > 0 else b""
+
+    def stats_out(self):
+        """AVCodecContext.stats_out after the flush of a first pass"""
+        fn = getattr(self.a.lib, PATHS[self.which][1] + "encoder_stats_out")
+        fn.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        buf = C.create_string_buffer(6 << 20)
+        n = fn(self.h, buf, len(buf))
+        if n < 0:
+            raise CodecError("stats_out", n)
+        return buf.raw[:n].decode()
 
     @property
     def info(self):

@@ -7,6 +7,7 @@
  *
  * API shape = the oracle's (ffv1emul_ prefix) so tests/cpucodec.py can drive it.
  */
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -50,12 +51,27 @@ struct Enc {
     std::vector<uint32_t> tokens, crc;
     uint8_t *extradata = nullptr;
     int extradata_size = 0, gop = 12, pic = 0;
+    /* two-pass coding */
+    int pass1 = 0, gob_count = 0;
+    std::vector<unsigned long long> rc_stat, rc_stat2;
 };
+
+static int g_pass1, g_pass2;
+static const char *g_stats_in;
+extern "C" void *ffv1emul_encoder_open(const Params *p, int *err);
+extern "C" void *ffv1emul_encoder_open2(const Params *p, int pass1, int pass2, const char *stats_in, int *err)
+{
+    g_pass1 = pass1; g_pass2 = pass2; g_stats_in = stats_in;
+    void *h = ffv1emul_encoder_open(p, err);
+    g_pass1 = g_pass2 = 0; g_stats_in = nullptr;
+    return h;
+}
 
 extern "C" void *ffv1emul_encoder_open(const Params *p, int *err)
 {
     ffgpu_enc_options o;
     memset(&o, 0, sizeof(o));
+    o.pass1 = g_pass1; o.pass2 = g_pass2; o.stats_in = g_stats_in;
     o.width = p->width; o.height = p->height; o.pix_fmt = p->pix_fmt; o.slices = p->slices;
     o.level = p->level; o.gop_size = p->gop_size; o.coder = p->coder; o.context = p->context;
     o.slicecrc = p->slicecrc; o.strict_std_compliance = p->strict;
@@ -66,6 +82,9 @@ extern "C" void *ffv1emul_encoder_open(const Params *p, int *err)
         *err = ff_write_extradata(&e->s, o.gop_size, &e->extradata, &e->extradata_size);
     if (*err < 0) { delete e; return nullptr; }
     e->gop = o.gop_size;
+    e->pass1 = o.pass1;
+    e->rc_stat.assign(512, 0);
+    e->rc_stat2.assign((size_t)e->s.ctx_count[e->s.context_model] * 64, 0);
     e->sl.resize(e->s.nh * e->s.nv);
     ff_fill_dev_params(&e->s, 1, &e->P, e->sl.data());
     e->qt = make_qt(e->s);
@@ -121,8 +140,15 @@ extern "C" int ffv1emul_encode(void *h, const uint8_t *const planes[4], const in
             e->tokens[e->sl[i].tok_off + t] = ff_symbolize_index(P, e->sl[i], e->frame.data(), e->qt.data(), t,
                                                                  rct[2 * i], rct[2 * i + 1]);
     /* state reset on key frames: ff_ffv1_clear_slice_state */
+    e->gob_count += keyf;
     if (keyf) {
         memset(e->rstate.data(), 128, e->rstate.size());
+        if (const uint8_t *init = e->s.initial[e->s.context_model]) {   /* second pass */
+            const size_t per = (size_t)e->s.ctx_count[e->s.context_model] * FF_CONTEXT_SIZE;
+            for (int i = 0; i < P.nslices; i++)
+                for (int k = 0; k < P.nsets; k++)
+                    memcpy(&e->rstate[((size_t)i * P.nsets + k) * per], init, per);
+        }
         for (auto &v : e->vstate) { v.x = FF_VLC_INIT_LO; v.y = FF_VLC_INIT_HI; }
     }
     /* stage B: one "thread" per slice */
@@ -130,6 +156,10 @@ extern "C" int ffv1emul_encode(void *h, const uint8_t *const planes[4], const in
         FFSliceRect r = { e->sl[i].x, e->sl[i].y, e->sl[i].w, e->sl[i].h };
         uint32_t ovf = 0;
         alignas(16) uint32_t row[FF_ROW_WORDS];
+        FFPassStats pass;
+        pass.rc_stat = e->rc_stat.data();
+        pass.rc_stat2 = e->rc_stat2.data();
+        pass.ctx_count = e->s.ctx_count[e->s.context_model];
         int rc = ff_enc_slice_prefix(&e->s, i, &r, keyf, 3, 0, 1, &pre[i], &e->prebytes[(size_t)i * 2048], 2048);
         if (rc < 0) return rc;
         pre[i].byte_off = (uint32_t)i * 2048;
@@ -143,7 +173,8 @@ extern "C" int ffv1emul_encode(void *h, const uint8_t *const planes[4], const in
                                              &e->rstate[(size_t)i * P.total_ctx * FF_CONTEXT_SIZE], &e->s.cur_tab,
                                              pre[i], e->prebytes.data(), &e->bs[e->sl[i].bs_off], &ovf, row,
                                              P.version > 3 ? &rct[2 * i] : nullptr,
-                                             P.version > 3 ? (uint32_t)((16384 + (int64_t)P.width * P.height * 12) / P.nslices) : 0u);
+                                             P.version > 3 ? (uint32_t)((16384 + (int64_t)P.width * P.height * 12) / P.nslices) : 0u,
+                                             e->pass1 ? &pass : nullptr);
         if (ovf) return FFGPU_INVALIDDATA;
     }
     /* pack */
@@ -157,6 +188,26 @@ extern "C" int ffv1emul_encode(void *h, const uint8_t *const planes[4], const in
     if (key) *key = keyf;
     e->pic++;
     return (int)off;
+}
+
+extern "C" int ffv1emul_encoder_stats_out(void *h, char *buf, int cap)
+{
+    Enc *e = (Enc *)h;
+    const FFStream &s = e->s;
+    size_t pos = 0;
+    if (!e->pass1) return FFGPU_EINVAL;
+#define OUT_(...) do { int w_ = snprintf(buf + pos, cap - pos, __VA_ARGS__); if (w_ < 0 || (size_t)w_ >= cap - pos) return FFGPU_ENOSPC; pos += w_; } while (0)
+    for (int j = 0; j < 256; j++) OUT_("%llu %llu ", e->rc_stat[2 * j], e->rc_stat[2 * j + 1]);
+    for (int i = 0; i < s.qt_count; i++)
+        for (int j = 0; j < s.ctx_count[i]; j++)
+            for (int m = 0; m < 32; m++) {
+                const bool own = i == s.context_model;
+                OUT_("%llu %llu ", own ? e->rc_stat2[((size_t)j * 32 + m) * 2] : 0ull,
+                     own ? e->rc_stat2[((size_t)j * 32 + m) * 2 + 1] : 0ull);
+            }
+    OUT_("%d\n", e->gob_count);
+#undef OUT_
+    return (int)pos;
 }
 
 extern "C" void ffv1emul_encoder_close(void *h)

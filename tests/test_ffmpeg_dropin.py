@@ -80,3 +80,22 @@ def test_ffmpeg_two_gpus_option(tmp_path):
     cpu = md5_lines(ffmpeg(*common, "-c:v", "ffv1", *opts, "-f", "framemd5", "-"))
     gpu = md5_lines(ffmpeg(*common, "-c:v", "ffv1_gpu", "-gpus", "2", *opts, "-f", "framemd5", "-"))
     assert gpu == cpu
+
+
+def test_ffmpeg_two_pass(tmp_path):
+    """`-pass 1` / `-pass 2` through fftools: the pass log the GPU codec leaves (stats_out,
+    written by ffmpeg.c:1326,1953) and the second pass's packets equal the CPU codec's"""
+    common = ["-f", "lavfi", "-i", SOURCES["testsrc2"].format(w=640, h=360), "-frames:v", "10",
+              "-pix_fmt", "yuv420p"]
+    opts = ["-coder", "range_tab", "-slices", "4", "-g", "1"]
+    logs = {}
+    for codec in ("ffv1", "ffv1_gpu"):
+        log = str(tmp_path / codec)
+        ffmpeg(*common, "-c:v", codec, *opts, "-pass", "1", "-passlogfile", log, "-f", "null", "-")
+        logs[codec] = open(log + "-0.log").read()
+    assert logs["ffv1"] == logs["ffv1_gpu"] and len(logs["ffv1"]) > 1000
+    out = {}
+    for codec in ("ffv1", "ffv1_gpu"):
+        out[codec] = md5_lines(ffmpeg(*common, "-c:v", codec, *opts, "-pass", "2", "-passlogfile",
+                                      str(tmp_path / "ffv1"), "-f", "framemd5", "-"))
+    assert out["ffv1"] == out["ffv1_gpu"] and len(out["ffv1"]) == 10

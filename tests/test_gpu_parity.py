@@ -668,3 +668,42 @@ def test_pictures_resident_on_the_gpu_through_send_receive():
                 assert np.array_equal(t.cpu().numpy()[:, :p.shape[1]], p)
     finally:
         assert lib.ffgpu_cuda_pop_context() == 0
+
+
+@pytest.mark.parametrize("fmt", ["yuv420p", "yuv420p10le", "bgr0"])
+def test_two_pass_matches_the_reference(fmt):
+    """SURVEY 8f-3 on the GPU: decision counters of the slice coders -> stats text == the
+    reference's stats_out; second pass (initial states on the device, sorted transition
+    table) -> extradata and packets == the reference's; decoder with initial states"""
+    if not cc.available("ref"):
+        pytest.skip("oracle/_ref not built")
+    F = gpu()
+    w, h = 160, 96
+    kinds = ("smooth", "noise", "testsrc2", "smooth", "testsrc2", "noise", "smooth")
+    for kw in (dict(slices=4, coder=2), dict(slices=12, coder=-2, context=1, gop_size=1), dict(coder=1, slices=9)):
+        frames = [synth.GENERATORS[k](fmt, w, h, i) for i, k in enumerate(kinds)]
+        r1 = cc.Encoder("ref", w, h, fmt, pass1=1, **kw)
+        g1 = F.FFV1Encoder(w, h, fmt, pass1=1, **kw)
+        for f in frames:
+            assert g1.encode(f) == r1.encode(f)
+        stats = r1.stats_out()
+        assert g1.stats_out() == stats, (fmt, kw)
+        # the pipelined path over two sub-handles adds its counters up
+        g1b = F.FFV1Encoder(w, h, fmt, pass1=1, devices=_device_list(2), max_batch=3, **kw)
+        _pump_encoder(F, g1b, frames)
+        assert g1b.stats_out() == stats or kw.get("gop_size", 12) != 1
+        r2 = cc.Encoder("ref", w, h, fmt, pass2=1, stats_in=stats, **kw)
+        g2 = F.FFV1Encoder(w, h, fmt, pass2=1, stats_in=stats, **kw)
+        assert g2.extradata == r2.extradata, (fmt, kw)
+        dref = cc.Decoder("ref", w, h, r2.extradata)
+        dec = F.FFV1Decoder(w, h, r2.extradata)
+        for f in frames:
+            pkt = r2.encode(f)
+            assert g2.encode(f) == pkt, (fmt, kw)
+            try:
+                want = dref.decode(pkt)
+            except cc.CodecError:
+                break
+            got = dec.decode(pkt, fmt_hint=dref.pix_fmt)
+            for a, b in zip(want, got):
+                assert np.array_equal(a, b), (fmt, kw)
