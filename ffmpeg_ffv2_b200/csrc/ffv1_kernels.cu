@@ -601,13 +601,19 @@ k_code_range(const FFDevParams P, const FFEncDev E, int nframes)
     pass.rc_stat = E.rc_stat;
     pass.rc_stat2 = E.rc_stat2;
     pass.ctx_count = E.stat_ctx_count;
-    const uint32_t n = ff_encode_slice_range(
-        sl, E.tokens + (size_t)f * P.frame_tokens + sl.tok_off,
-        E.state + st_slot * P.total_ctx * FF_CONTEXT_SIZE, &ff_s_tab,
-        E.prefix[(size_t)E.frame_prefix_set[f] * P.nslices + s], E.prefix_bytes,
-        E.bs + (size_t)f * P.frame_bs + sl.bs_off, &ovf, 0, E.rct ? E.rct + 2 * (size_t)gid : (const int *)0,
-        E.rct ? (uint32_t)((16384 + (int64_t)P.width * P.height * 12) / P.nslices) : 0u,
-        E.rc_stat ? &pass : (const FFPassStats *)0);
+    uint32_t n;
+#define CODE_ARGS_  \
+        sl, E.tokens + (size_t)f * P.frame_tokens + sl.tok_off, \
+        E.state + st_slot * P.total_ctx * FF_CONTEXT_SIZE, &ff_s_tab, \
+        E.prefix[(size_t)E.frame_prefix_set[f] * P.nslices + s], E.prefix_bytes, \
+        E.bs + (size_t)f * P.frame_bs + sl.bs_off, &ovf, 0, E.rct ? E.rct + 2 * (size_t)gid : (const int *)0, \
+        E.rct ? (uint32_t)((16384 + (int64_t)P.width * P.height * 12) / P.nslices) : 0u, \
+        E.rc_stat ? &pass : (const FFPassStats *)0
+    if (E.rc_stat)
+        n = ff_encode_slice_range<true>(CODE_ARGS_);
+    else
+        n = ff_encode_slice_range<false>(CODE_ARGS_);
+#undef CODE_ARGS_
     E.slice_bytes[gid] = n;
     if (ovf)
         atomicOr(E.overflow, 1u);

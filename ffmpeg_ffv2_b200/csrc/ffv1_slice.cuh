@@ -491,6 +491,7 @@ FFGPU_HD void ff_pass_count(const FFPassStats *st, int state, int ctx, int slot,
 #endif
 }
 
+template <bool STATS>               /* STATS: a first pass, count every decision */
 FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *tokens,
                                         uint8_t *state, const FFRacTables *tab_,
                                         const FFRacPrefix &pre, const uint8_t *pre_bytes,
@@ -601,7 +602,7 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
         {
             const uint32_t sa = row_sa + slot;
             s = (int)ff_lds8(sa);
-            if (pass)
+            if (STATS)
                 ff_pass_count(pass, s, cur_ctx, (int)slot, bit);
             r1 = (c.range * s) >> 8;                 /* put_rac, rangecoder.h:104-121 */
             rb = c.range - r1;
@@ -613,7 +614,7 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
         {
             const int slot = ff_slot_of(e, step);
             s = FF_ROWB(slot);
-            if (pass)
+            if (STATS)
                 ff_pass_count(pass, s, cur_ctx, slot, bit);
             r1 = (c.range * s) >> 8;
             rb = c.range - r1;

@@ -168,8 +168,15 @@ extern "C" int ffv1emul_encode(void *h, const uint8_t *const planes[4], const in
                                               &e->vstate[(size_t)i * P.total_ctx], pre[i], e->prebytes.data(),
                                               &e->bs[e->sl[i].bs_off], &ovf, &e->s.cur_tab,
                                               P.version > 3 ? &rct[2 * i] : nullptr);
+        else if (e->pass1)
+            bytes[i] = ff_encode_slice_range<true>(e->sl[i], &e->tokens[e->sl[i].tok_off],
+                                             &e->rstate[(size_t)i * P.total_ctx * FF_CONTEXT_SIZE], &e->s.cur_tab,
+                                             pre[i], e->prebytes.data(), &e->bs[e->sl[i].bs_off], &ovf, row,
+                                             P.version > 3 ? &rct[2 * i] : nullptr,
+                                             P.version > 3 ? (uint32_t)((16384 + (int64_t)P.width * P.height * 12) / P.nslices) : 0u,
+                                             e->pass1 ? &pass : nullptr);
         else
-            bytes[i] = ff_encode_slice_range(e->sl[i], &e->tokens[e->sl[i].tok_off],
+            bytes[i] = ff_encode_slice_range<false>(e->sl[i], &e->tokens[e->sl[i].tok_off],
                                              &e->rstate[(size_t)i * P.total_ctx * FF_CONTEXT_SIZE], &e->s.cur_tab,
                                              pre[i], e->prebytes.data(), &e->bs[e->sl[i].bs_off], &ovf, row,
                                              P.version > 3 ? &rct[2 * i] : nullptr,

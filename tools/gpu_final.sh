@@ -3,7 +3,7 @@
 # list and full captures of the top kernels (summarised into profiles/ by profiles/summarize.py)
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -k "full_size or pipelined or dropin or staging" > gpurun_out/pytest_final.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_final.log
+timeout 900 python -m pytest tests -m gpu -q -k "two_pass or full_size or pipelined or dropin or staging or version4 or glue" > gpurun_out/pytest_final.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_final.log
 tail -4 gpurun_out/pytest_final.log
 python bench.py --impl reference > gpurun_out/r02_bench_reference.json 2> gpurun_out/ref.err
 python bench.py > gpurun_out/r02_bench_n1.json 2> gpurun_out/n1.err; tail -2 gpurun_out/n1.err
