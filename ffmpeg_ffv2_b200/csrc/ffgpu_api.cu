@@ -459,6 +459,11 @@ struct EncJob {
     void *d_sort_tmp;
     size_t sort_tmp_bytes;
     FFSched *d_sched;
+    /* stage B in two halves (few-slice streams): decision records */
+    uint16_t *d_rec;
+    unsigned long long rec_cap, *d_rec_off;
+    uint32_t *d_guard_rec;
+    int *d_split_ok;
     int *d_rct;                 /* version 4: RCT coefficients per (picture, slice) */
     int32_t *d_rct_stat;
     int pkt_owned;
@@ -530,6 +535,7 @@ static int enc_free_job(EncJob *j)
     cudaFree(j->d_frame_set); cudaFree(j->d_frame_key);
     cudaFree(j->d_weight); cudaFree(j->d_weight_sorted); cudaFree(j->d_order); cudaFree(j->d_sort_tmp);
     cudaFree(j->d_rct); cudaFree(j->d_rct_stat); cudaFree(j->d_sched);
+    cudaFree(j->d_rec); cudaFree(j->d_rec_off); cudaFree(j->d_guard_rec); cudaFree(j->d_split_ok);
     cudaFreeHost(j->h_frame_set); cudaFreeHost(j->h_frame_key); cudaFreeHost(j->h_pkt_size);
     cudaFreeHost(j->h_pkt_off); cudaFreeHost(j->h_overflow); cudaFreeHost(j->h_pkt);
     cudaFreeHost(j->h_stage);
@@ -628,6 +634,19 @@ static int enc_device_init(ffgpu_encoder *e)
         CK(cudaMalloc(&j->d_sort_tmp, j->sort_tmp_bytes));
         CK(cudaMalloc(&j->d_sched, sizeof(FFSched)));
         CK(cudaMemset(j->d_sched, 0, sizeof(FFSched)));
+        if (!golomb && !e->opt.pass1 && coder_lane_stride((long)B * P->nslices) >= 8 &&
+            !(getenv("FFGPU_SPLIT") && !atoi(getenv("FFGPU_SPLIT")))) {
+            /* a group never has enough slices to fill the GPU's lanes: stage B in two halves.
+             * Room for two decisions per sample on average (4 bytes per sample, like the
+             * tokens); pictures that need more take the one-kernel coder, decided per group on
+             * the device.  FFGPU_SPLIT=0 switches the split form off. */
+            j->rec_cap = (unsigned long long)B * P->frame_tokens * 2;
+            CK(cudaMalloc(&j->d_rec, j->rec_cap * sizeof(uint16_t)));
+            CK(cudaMalloc(&j->d_rec_off, (B * P->nslices + 1) * sizeof(unsigned long long)));
+            CK(cudaMalloc(&j->d_guard_rec, B * P->nslices * sizeof(uint32_t)));
+            CK(cudaMalloc(&j->d_split_ok, sizeof(int)));
+            CK(cudaMemset(j->d_split_ok, 0, sizeof(int)));
+        }
         if (P->version > 3) {
             CK(cudaMalloc(&j->d_rct, B * P->nslices * 2 * sizeof(int)));
             CK(cudaMalloc(&j->d_rct_stat, B * P->nslices * 16 * sizeof(int32_t)));
@@ -852,6 +871,11 @@ static void enc_fill_dev(const ffgpu_encoder *e, const EncJob *j, const uint8_t 
     E->lane_stride = coder_lane_stride((long)j->n * e->P.nslices);
     E->rct = j->d_rct;
     E->rct_stat = j->d_rct_stat;
+    E->rec = j->d_rec;
+    E->rec_cap = j->rec_cap;
+    E->rec_off = j->d_rec_off;
+    E->guard_rec = j->d_guard_rec;
+    E->split_ok = j->d_split_ok;
     E->rc_stat = e->d_rc_stat;
     E->rc_stat2 = e->d_rc_stat2;
     E->stat_ctx_count = e->s.ctx_count[e->s.context_model];
@@ -1048,8 +1072,11 @@ extern "C" int ffgpu_ffv1_encode_send_frame(ffgpu_encoder *e, const ffgpu_pictur
     if (mem_kind(pic->data[0]) == MEM_PAGEABLE) {
         /* an ordinary AVFrame: host memcpy into pinned staging, one linear DMA from there */
         uint8_t *data[4], *st;
-        if (!j->h_stage)
-            CK(cudaHostAlloc(&j->h_stage, (size_t)e->max_batch * e->P.frame_bytes, cudaHostAllocDefault));
+        /* the first pageable picture creates the staging of EVERY launch group, so that no
+         * later group stops the pipeline for a page-locked allocation */
+        for (int g = 0; g < e->depth && !j->h_stage; g++)
+            if (!e->jobs[g].h_stage)
+                CK(cudaHostAlloc(&e->jobs[g].h_stage, (size_t)e->max_batch * e->P.frame_bytes, cudaHostAllocDefault));
         st = j->h_stage + (size_t)j->n * e->P.frame_bytes;
         for (int k = 0; k < 4; k++)
             data[k] = (uint8_t *)pic->data[k];
@@ -1970,6 +1997,10 @@ static int dec_add_packet(ffgpu_decoder *d, DecJob *j, const uint8_t *pkt, size_
         m->dst = *dst;
         m->has_dst = 1;
         m->staged = mem_kind(dst->data[0]) == MEM_PAGEABLE;
+        /* the first pageable destination creates the staging of every launch group */
+        for (int g = 0; g < d->depth && m->staged && !j->h_stage; g++)
+            if (!d->jobs[g].h_stage)
+                CK(cudaHostAlloc(&d->jobs[g].h_stage, (size_t)d->max_batch * d->P.frame_bytes, cudaHostAllocDefault));
     }
     j->h_nslices[j->n] = n;
     j->pkt_used = off + size;

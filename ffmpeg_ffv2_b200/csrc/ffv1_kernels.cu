@@ -588,6 +588,8 @@ k_code_range(const FFDevParams P, const FFEncDev E, int nframes)
     __syncthreads();
     ff_fill_tab16(threadIdx.x, CODE_THREADS);
     __syncthreads();
+    if (E.rec && *E.split_ok)                                /* k_chain_states + k_code_records did it */
+        return;
     const int tid = ff_sched_item(blockIdx.x * CODE_THREADS + threadIdx.x, nframes * P.nslices,
                                   E.lane_stride, E.sched, E.heavy_stride);
     if (tid < 0)
@@ -614,6 +616,104 @@ k_code_range(const FFDevParams P, const FFEncDev E, int nframes)
     else
         n = ff_encode_slice_range<false>(CODE_ARGS_);
 #undef CODE_ARGS_
+    E.slice_bytes[gid] = n;
+    if (ovf)
+        atomicOr(E.overflow, 1u);
+}
+
+
+/* ---------------- stage B in two halves (few-slice launches) ---------------- */
+/* where each slice's decision records start: an exclusive sum of the decision counts stage A
+ * produced; also decides whether the records fit the arena.  The split form only runs for
+ * launches of at most a few thousand slices, a single thread adds them up. */
+__global__ void k_rec_offsets(const FFEncDev E, int n)
+{
+    if (blockIdx.x || threadIdx.x)
+        return;
+    unsigned long long sum = 0;
+    for (int i = 0; i < n; i++) {
+        E.rec_off[i] = sum;
+        sum += E.weight[i];
+    }
+    E.rec_off[n] = sum;
+    *E.split_ok = sum <= E.rec_cap;
+}
+
+/* One warp per slice.  32 tokens per step, in coding order; tokens that share a context are
+ * taken one after the other (the member of rank r in round r), all others at once.  The
+ * state rows live in global memory (the arena of the one-kernel coder, L1-resident for the
+ * contexts in use); __syncwarp() orders the rounds' accesses to a shared row. */
+__global__ void __launch_bounds__(CODE_THREADS)
+k_chain_states(const FFDevParams P, const FFEncDev E, int nframes)
+{
+    __shared__ FFRacTables s_tab;
+    for (int i = threadIdx.x; i < (int)sizeof(FFRacTables) / 4; i += CODE_THREADS)
+        ((uint32_t *)&s_tab)[i] = ((const uint32_t *)E.tab)[i];
+    __syncthreads();
+    if (!*E.split_ok)
+        return;
+    const int gid = blockIdx.x * (CODE_THREADS / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (gid >= nframes * P.nslices)
+        return;
+    const int f = gid / P.nslices, s = gid - f * P.nslices;
+    const FFDevSlice sl = E.slices[s];
+    const uint32_t *tokens = E.tokens + (size_t)f * P.frame_tokens + sl.tok_off;
+    const size_t st_slot = (size_t)(E.state_per_frame ? f : 0) * P.nslices + s;
+    uint8_t *rows = E.state + st_slot * P.total_ctx * FF_CONTEXT_SIZE;
+    uint16_t *rec = E.rec + E.rec_off[gid];
+    const uint32_t n = sl.ntok;
+    const uint32_t guard_tok = E.rct ? n - (uint32_t)sl.seg_w[sl.nseg - 1] : 0xFFFFFFFFu;
+    uint32_t base = 0;
+    for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const bool valid = i < n;
+        const uint32_t tok = valid ? tokens[i] : 0u;
+        uint32_t w = valid ? ff_token_weight(tok) : 0u, incl = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o)
+                incl += v;
+        }
+        const uint32_t off = base + incl - w;
+        base += __shfl_sync(0xffffffffu, incl, 31);
+        if (valid && i == guard_tok)
+            E.guard_rec[gid] = off;
+        /* lanes without a token get a key no context has */
+        const unsigned grp = __match_any_sync(0xffffffffu, valid ? (tok & FF_TOKEN_CTX_MASK) : 0x10000u + lane);
+        const int rank = __popc(grp & ((1u << lane) - 1u));
+        const int rounds = __reduce_max_sync(0xffffffffu, valid ? __popc(grp) : 0);
+        for (int r = 0; r < rounds; r++) {
+            if (valid && rank == r)
+                ff_chain_token(tok, rows, &s_tab, rec + off);
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CODE_THREADS)
+k_code_records(const FFDevParams P, const FFEncDev E, int nframes)
+{
+    for (int i = threadIdx.x; i < (int)sizeof(FFRacTables) / 4; i += CODE_THREADS)
+        ((uint32_t *)&ff_s_tab)[i] = ((const uint32_t *)E.tab)[i];
+    __syncthreads();
+    if (!*E.split_ok)
+        return;
+    const int tid = ff_sched_item(blockIdx.x * CODE_THREADS + threadIdx.x, nframes * P.nslices,
+                                  E.lane_stride, (const FFSched *)0, E.heavy_stride);
+    if (tid < 0)
+        return;
+    const int gid = E.order ? (int)E.order[tid] : tid;
+    const int f = gid / P.nslices, s = gid - f * P.nslices;
+    const FFDevSlice sl = E.slices[s];
+    uint32_t ovf = 0;
+    const uint32_t n = ff_encode_slice_records(
+        sl, E.rec + E.rec_off[gid], (uint32_t)(E.rec_off[gid + 1] - E.rec_off[gid]),
+        E.rct ? E.guard_rec[gid] : 0xFFFFFFFFu, &ff_s_tab,
+        E.prefix[(size_t)E.frame_prefix_set[f] * P.nslices + s], E.prefix_bytes,
+        E.bs + (size_t)f * P.frame_bs + sl.bs_off, &ovf, E.rct ? E.rct + 2 * (size_t)gid : (const int *)0,
+        E.rct ? (uint32_t)((16384 + (int64_t)P.width * P.height * 12) / P.nslices) : 0u);
     E.slice_bytes[gid] = n;
     if (ovf)
         atomicOr(E.overflow, 1u);
@@ -817,10 +917,19 @@ extern "C" int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nfr
         const long total = ff_sched_threads((long)nframes * P->nslices, E->lane_stride,
                                             E->sched && E->weight && E->order, E->heavy_stride);
         const int blocks = (int)((total + CODE_THREADS - 1) / CODE_THREADS);
-        if (P->ac == FF_AC_GOLOMB)
+        if (P->ac == FF_AC_GOLOMB) {
             k_code_golomb<<<blocks, CODE_THREADS, 0, st>>>(*P, *E, nframes);
-        else
+        } else {
+            if (E->rec && E->weight) {
+                /* few, large slices: state chains by warps, then the bare arithmetic coder */
+                const int n = nframes * P->nslices;
+                k_rec_offsets<<<1, 32, 0, st>>>(*E, n);
+                k_chain_states<<<(n + CODE_THREADS / 32 - 1) / (CODE_THREADS / 32), CODE_THREADS, 0, st>>>(*P, *E, nframes);
+                k_code_records<<<blocks, CODE_THREADS, 0, st>>>(*P, *E, nframes);
+                launches += 3;
+            }
             k_code_range<<<blocks, CODE_THREADS, 0, st>>>(*P, *E, nframes);
+        }
         mark(E->events, FFK_CODE + 1, st);
         launches++;
         if (!launch_ok()) return FFGPU_EXTERNAL;

@@ -60,6 +60,14 @@ typedef struct FFEncDev {
     FFSched *sched;                 /* heavy / light classes of this launch, or NULL      */
     int heavy_stride;               /* lanes between two heavy slices (power of two)      */
     float heavy_factor;
+    /* stage B in two halves (few-slice launches, see ff_chain_token): decision records of the
+     * group, where each slice's records start, and whether the records fit (decided on the
+     * device: incompressible pictures take the one-kernel coder instead) */
+    uint16_t *rec;                  /* [rec_cap] or NULL: the split form is not configured */
+    unsigned long long rec_cap;     /* records the arena holds                           */
+    unsigned long long *rec_off;    /* [nframes*nslices + 1]                             */
+    uint32_t *guard_rec;            /* [nframes*nslices] version 4 overflow guard position */
+    int *split_ok;                  /* [1]                                               */
     /* two-pass coding: counters of a first pass (or NULL), initial states of a second pass
      * as one row per context of the slice, [total_ctx][32] (or NULL: every state starts at 128) */
     unsigned long long *rc_stat, *rc_stat2;

@@ -636,6 +636,85 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
     return nb;
 }
 
+
+/* ------------------------------------------------------------------ */
+/* stage B in two halves, for streams with few, large slices            */
+/* ------------------------------------------------------------------ */
+/* In the ENCODER every context and every bit is known once stage A has run.  What is serial
+ * is (1) the sequence of adaptive states of each (context, slot) and (2) the arithmetic
+ * coder's low / range / carry.  (1) only orders decisions that share a context, (2) is a
+ * handful of instructions per decision once the probabilities are known.  A launch with few
+ * slices (BASELINE C3/C5: 4 or 9 per picture) leaves the GPU empty and lasts as long as one
+ * lane needs for a whole slice, so there the two are separated:
+ *   ff_chain_token          (k_chain_states, one WARP per slice) 32 tokens at a time: tokens
+ *                           of different contexts run their state chains in parallel, tokens
+ *                           of one context in coding order; every decision leaves a 16-bit
+ *                           record (state | bit << 8) at its place in coding order
+ *   ff_encode_slice_records (k_code_records, one lane per slice) put_rac + renorm_encoder
+ *                           (rangecoder.h:71-121) over the records
+ * The packets are the same bytes as ff_encode_slice_range writes. */
+FFGPU_HD uint32_t ff_chain_token(uint32_t tok, uint8_t *rows, const FFRacTables *tab, uint16_t *rec)
+{
+    const int ctx = (int)(tok & FF_TOKEN_CTX_MASK);
+    const int diff = (int32_t)tok >> FF_TOKEN_CTX_BITS;
+    const uint32_t a = (uint32_t)(diff < 0 ? -diff : diff);
+    uint8_t *row = rows + (size_t)ctx * FF_CONTEXT_SIZE;
+    if (!a) {
+        const int s = row[0];
+        rec[0] = (uint16_t)(s | 0x100);
+        row[0] = tab->one[s];
+        return 1;
+    } else {
+        const int e = ffrac_ilog2(a), n = 2 * e + 3;
+        for (int step = 0; step < n; step++) {
+            const int slot = ff_slot_of(e, step);
+            int bit;
+            if (step == 0)
+                bit = 0;
+            else if (step <= e)
+                bit = 1;
+            else if (step == e + 1)
+                bit = 0;
+            else if (step <= 2 * e + 1)
+                bit = (int)((a >> (2 * e + 1 - step)) & 1u);
+            else
+                bit = diff < 0;
+            const int s = row[slot];
+            rec[step] = (uint16_t)(s | (bit << 8));
+            row[slot] = bit ? tab->one[s] : tab->zero[s];
+        }
+        return (uint32_t)n;
+    }
+}
+
+FFGPU_HD uint32_t ff_encode_slice_records(const FFDevSlice &sl, const uint16_t *rec, uint32_t nrec,
+                                          uint32_t guard_rec, const FFRacTables *tab,
+                                          const FFRacPrefix &pre, const uint8_t *pre_bytes,
+                                          uint8_t *out, uint32_t *overflow, const int *rct, uint32_t v4_room)
+{
+    FFRacEnc c;
+    uint32_t guard_pos = 0, nb;
+    ff_enc_resume(&c, pre, pre_bytes, out, sl.bs_cap);
+    if (rct)
+        ff_enc_v4_header_tail(&c, tab, pre, rct[0], rct[1], 0);
+    for (uint32_t i = 0; i < nrec; i++) {
+        const uint32_t r = rec[i];
+        const int s = (int)(r & 0xFFu), bit = (int)(r >> 8);
+        const int r1 = (c.range * s) >> 8, rb = c.range - r1;
+        if (i == guard_rec)                          /* see ff_encode_slice_range: version 4 */
+            guard_pos = c.pos;
+        c.low += bit ? rb : 0;
+        c.range = bit ? r1 : rb;
+        if (c.range < 0x100)
+            ffrac_enc_shift1(&c);
+    }
+    nb = ffrac_enc_finish(&c, tab, 1);
+    *overflow = c.overflow;
+    if (v4_room && (int64_t)v4_room - (int64_t)guard_pos < (int64_t)sl.seg_w[sl.nseg - 1] * 35)
+        *overflow = 1;
+    return nb;
+}
+
 /* number of binary decisions the range coder spends on a token: the slice's total is its
  * serial cost and drives the longest-first scheduling of stage B */
 FFGPU_HD uint32_t ff_token_weight(uint32_t tok)

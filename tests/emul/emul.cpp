@@ -168,7 +168,25 @@ extern "C" int ffv1emul_encode(void *h, const uint8_t *const planes[4], const in
                                               &e->vstate[(size_t)i * P.total_ctx], pre[i], e->prebytes.data(),
                                               &e->bs[e->sl[i].bs_off], &ovf, &e->s.cur_tab,
                                               P.version > 3 ? &rct[2 * i] : nullptr);
-        else if (e->pass1)
+        else if (getenv("FFV1_EMUL_SPLIT") && !e->pass1) {
+            /* stage B in two halves: the state chains in coding order, then the bare coder */
+            const FFDevSlice &sl = e->sl[i];
+            std::vector<uint16_t> rec;
+            uint32_t guard = 0xFFFFFFFFu;
+            const uint32_t guard_tok = P.version > 3 ? sl.ntok - (uint32_t)sl.seg_w[sl.nseg - 1] : 0xFFFFFFFFu;
+            uint16_t tmp[80];
+            for (uint32_t t = 0; t < sl.ntok; t++) {
+                if (t == guard_tok) guard = (uint32_t)rec.size();
+                uint32_t n = ff_chain_token(e->tokens[sl.tok_off + t],
+                                            &e->rstate[(size_t)i * P.total_ctx * FF_CONTEXT_SIZE], &e->s.cur_tab, tmp);
+                if (n != ff_token_weight(e->tokens[sl.tok_off + t])) return FFGPU_EXTERNAL;
+                rec.insert(rec.end(), tmp, tmp + n);
+            }
+            bytes[i] = ff_encode_slice_records(sl, rec.data(), (uint32_t)rec.size(), guard, &e->s.cur_tab, pre[i],
+                                               e->prebytes.data(), &e->bs[sl.bs_off], &ovf,
+                                               P.version > 3 ? &rct[2 * i] : nullptr,
+                                               P.version > 3 ? (uint32_t)((16384 + (int64_t)P.width * P.height * 12) / P.nslices) : 0u);
+        } else if (e->pass1)
             bytes[i] = ff_encode_slice_range<true>(e->sl[i], &e->tokens[e->sl[i].tok_off],
                                              &e->rstate[(size_t)i * P.total_ctx * FF_CONTEXT_SIZE], &e->s.cur_tab,
                                              pre[i], e->prebytes.data(), &e->bs[e->sl[i].bs_off], &ovf, row,
