@@ -20,6 +20,7 @@
  * k_decode      decode_slice after its header (ffv1dec.c:304-359) for every slice of every
  *               packet of the group
  */
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <cub/block/block_reduce.cuh>
 #include <cub/block/block_scan.cuh>
@@ -578,6 +579,7 @@ __global__ void k_fill_state_initial(uint4 *__restrict__ state, size_t vec_per_s
 }
 
 /* ---------------- stage B ---------------- */
+template <bool LONE>
 __global__ void __launch_bounds__(CODE_THREADS)
 k_code_range(const FFDevParams P, const FFEncDev E, int nframes)
 {
@@ -588,7 +590,7 @@ k_code_range(const FFDevParams P, const FFEncDev E, int nframes)
     __syncthreads();
     ff_fill_tab16(threadIdx.x, CODE_THREADS);
     __syncthreads();
-    if (E.rec && *E.split_ok)                                /* k_chain_states + k_code_records did it */
+    if (!LONE && E.rec && *E.split_ok)                       /* k_chain_states + k_code_records did it */
         return;
     const int tid = ff_sched_item(blockIdx.x * CODE_THREADS + threadIdx.x, nframes * P.nslices,
                                   E.lane_stride, E.sched, E.heavy_stride);
@@ -611,11 +613,20 @@ k_code_range(const FFDevParams P, const FFEncDev E, int nframes)
         E.bs + (size_t)f * P.frame_bs + sl.bs_off, &ovf, 0, E.rct ? E.rct + 2 * (size_t)gid : (const int *)0, \
         E.rct ? (uint32_t)((16384 + (int64_t)P.width * P.height * 12) / P.nslices) : 0u, \
         E.rc_stat ? &pass : (const FFPassStats *)0
-    if (E.rc_stat)
+#define CODE_ARGS_LONE_  \
+        sl, E.tokens + (size_t)f * P.frame_tokens + sl.tok_off, \
+        E.state + st_slot * P.total_ctx * FF_CONTEXT_SIZE, &ff_s_tab, \
+        E.prefix[(size_t)E.frame_prefix_set[f] * P.nslices + s], E.prefix_bytes, \
+        E.bs + (size_t)f * P.frame_bs + sl.bs_off, &ovf, 0, E.rct ? E.rct + 2 * (size_t)gid : (const int *)0, \
+        E.rct ? (uint32_t)((16384 + (int64_t)P.width * P.height * 12) / P.nslices) : 0u
+    if (LONE)                           /* one slice per warp, no first-pass counters */
+        n = ff_encode_slice_range_lone(CODE_ARGS_LONE_);
+    else if (E.rc_stat)
         n = ff_encode_slice_range<true>(CODE_ARGS_);
     else
         n = ff_encode_slice_range<false>(CODE_ARGS_);
 #undef CODE_ARGS_
+#undef CODE_ARGS_LONE_
     E.slice_bytes[gid] = n;
     if (ovf)
         atomicOr(E.overflow, 1u);
@@ -920,6 +931,12 @@ extern "C" int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nfr
         if (P->ac == FF_AC_GOLOMB) {
             k_code_golomb<<<blocks, CODE_THREADS, 0, st>>>(*P, *E, nframes);
         } else {
+            /* one slice per warp: the straight-line coder (FFGPU_LONE=0: tuning hook) */
+            const int lone_ok = !(getenv("FFGPU_LONE") && !atoi(getenv("FFGPU_LONE")));
+            const bool lone = E->lane_stride == 32 && !E->rc_stat && lone_ok;
+            if (lone) {
+                k_code_range<true><<<blocks, CODE_THREADS, 0, st>>>(*P, *E, nframes);
+            } else {
             if (E->rec && E->weight) {
                 /* few, large slices: state chains by warps, then the bare arithmetic coder */
                 const int n = nframes * P->nslices;
@@ -928,7 +945,8 @@ extern "C" int ffk_encode_group(const FFDevParams *P, const FFEncDev *E, int nfr
                 k_code_records<<<blocks, CODE_THREADS, 0, st>>>(*P, *E, nframes);
                 launches += 3;
             }
-            k_code_range<<<blocks, CODE_THREADS, 0, st>>>(*P, *E, nframes);
+            k_code_range<false><<<blocks, CODE_THREADS, 0, st>>>(*P, *E, nframes);
+            }
         }
         mark(E->events, FFK_CODE + 1, st);
         launches++;
@@ -1012,7 +1030,7 @@ __global__ void k_dec_fill_state(uint4 *__restrict__ state, size_t vec_per_frame
 #ifndef FF_DEC_MINBLOCKS
 #define FF_DEC_MINBLOCKS 1
 #endif
-template <int SMODE, bool FIVE>
+template <int SMODE, bool FIVE, bool LONE = false>
 __global__ void __launch_bounds__(CODE_THREADS, FF_DEC_MINBLOCKS)
 k_decode(const FFDevParams P, const FFDecDev D, int nframes)
 {
@@ -1031,7 +1049,7 @@ k_decode(const FFDevParams P, const FFDecDev D, int nframes)
     const int tid = ff_sched_item(blockIdx.x * CODE_THREADS + threadIdx.x, nframes * D.max_slices,
                                   D.lane_stride, D.sched, D.heavy_stride);
     const bool have = tid >= 0;
-    if (SMODE == 0 && !have)
+    if ((SMODE == 0 || LONE) && !have)
         return;
     const int gid = have ? (D.order ? (int)D.order[tid] : tid) : 0;   /* largest slices first */
     const int f = gid / D.max_slices, s = gid - f * D.max_slices;
@@ -1063,6 +1081,7 @@ k_decode(const FFDevParams P, const FFDecDev D, int nframes)
             C.gate_wait = D.gate_wait;
             C.touched = D.touched ? D.touched + (size_t)gid * D.touched_words : (uint32_t *)0;
             C.any_five = D.any_five;
+            C.lone = LONE;
             if (w.w + 8 > D.line_stride) {
                 /* rectangle wider than the grid cell: picture-wide scratch from the pool */
                 const uint32_t slot_w = D.wide_used ? atomicAdd(D.wide_used, 1u) : 0xFFFFFFFFu;
@@ -1080,6 +1099,12 @@ k_decode(const FFDevParams P, const FFDecDev D, int nframes)
     if (SMODE == 0) {
         if (live)
             ff_decode_slice(P, w, D.pkt, C, &r, 0);
+    } else if (LONE) {
+        /* one live lane per warp (D.lane_stride == 32): the straight-line decoder */
+        if (live && w.pcm)
+            ff_decode_slice_pcm(P, w, D.pkt, C, &r);
+        else if (live)
+            ff_decode_slice_range_planar_lone<SMODE ? SMODE : 1, FIVE>(P, w, D.pkt, C, &r, 0);
     } else {
         if (live && w.pcm) {                         /* version 4 PCM slice: the plain way */
             ff_decode_slice_pcm(P, w, D.pkt, C, &r);
@@ -1143,7 +1168,16 @@ extern "C" int ffk_decode_group(const FFDevParams *P, const FFDecDev *D, int nfr
         const size_t smem = (size_t)D->qt_count * FF_QT_STRIDE * sizeof(int16_t);
         const int planar = D->generic ? 0 : ff_decode_planar_mode(P);
 #define DEC_LAUNCH(M, F) k_decode<M, F><<<blocks, CODE_THREADS, smem, st>>>(*P, *D, nframes)
-        if (planar == 1) {
+#define DEC_LAUNCH_LONE(M, F) k_decode<M, F, true><<<blocks, CODE_THREADS, smem, st>>>(*P, *D, nframes)
+        /* FFGPU_LONE=0: tuning hook, the warp-wide form also for one slice per warp */
+        const int lone_ok = !(getenv("FFGPU_LONE") && !atoi(getenv("FFGPU_LONE")));
+        if (planar && D->lane_stride == 32 && lone_ok) {
+            if (planar == 1) {
+                if (D->any_five) DEC_LAUNCH_LONE(1, true); else DEC_LAUNCH_LONE(1, false);
+            } else {
+                if (D->any_five) DEC_LAUNCH_LONE(2, true); else DEC_LAUNCH_LONE(2, false);
+            }
+        } else if (planar == 1) {
             if (D->any_five) DEC_LAUNCH(1, true); else DEC_LAUNCH(1, false);
         } else if (planar == 2) {
             if (D->any_five) DEC_LAUNCH(2, true); else DEC_LAUNCH(2, false);
@@ -1151,6 +1185,7 @@ extern "C" int ffk_decode_group(const FFDevParams *P, const FFDecDev *D, int nfr
             DEC_LAUNCH(0, false);
         }
 #undef DEC_LAUNCH
+#undef DEC_LAUNCH_LONE
     }
     mark(D->events, FFK_DECODE + 1, st);
     if (!launch_ok()) return FFGPU_EXTERNAL;

@@ -461,6 +461,12 @@ __device__ __forceinline__ void ff_sts8(uint32_t sa, uint32_t v)
 }
 #endif
 
+#if defined(__CUDA_ARCH__)
+#define FF_UNLIKELY(c) __builtin_expect(!!(c), 0)
+#else
+#define FF_UNLIKELY(c) (c)
+#endif
+
 /* Stage B, range coder.  The 32 lanes of a warp code 32 different slices, so the loop is
  * written as ONE BINARY DECISION PER ITERATION with a small per-lane state machine
  * (put_symbol_inline, ffv1enc.c:185-231, unrolled over `step`): a lane that is inside a
@@ -629,6 +635,161 @@ FFGPU_HD uint32_t ff_encode_slice_range(const FFDevSlice &sl, const uint32_t *to
     }
     if (cur_ctx >= 0)
         ff_row_store(FF_ROWW, state + (size_t)cur_ctx * FF_CONTEXT_SIZE);
+    nb = ffrac_enc_finish(&c, tab_, 1);              /* ffv1enc.c:1242 */
+    *overflow = c.overflow;
+    if (v4_room && (int64_t)v4_room - (int64_t)guard_pos < (int64_t)sl.seg_w[sl.nseg - 1] * 35)
+        *overflow = 1;
+    return nb;
+}
+
+#if defined(__CUDACC__)
+/* renorm_encoder step out of line, values in and out through registers: inlined at every
+ * decision site it makes the lone coder's loop ten times larger than the instruction caches
+ * (L0 6 KB, L1.5 32 KB), and a lone warp waits out every instruction fetch */
+typedef struct FFEncRenorm {
+    int32_t low, range, pending, run;
+    uint32_t pos, overflow;
+} FFEncRenorm;
+static __device__ __noinline__ FFEncRenorm ff_enc_renorm(int32_t low, int32_t range, int32_t pending, int32_t run,
+                                                         uint32_t pos, uint32_t overflow, uint8_t *buf, uint32_t cap)
+{
+    FFRacEnc c;
+    FFEncRenorm r;
+    c.low = low; c.range = range; c.pending = pending; c.run = run;
+    c.buf = buf; c.pos = pos; c.cap = cap; c.overflow = overflow;
+    ffrac_enc_shift1(&c);
+    r.low = c.low; r.range = c.range; r.pending = c.pending; r.run = c.run;
+    r.pos = c.pos; r.overflow = c.overflow;
+    return r;
+}
+#endif
+
+/* Stage B for launches that give every slice a warp of its own (E.lane_stride == 32: streams
+ * with a handful of large slices).  One live lane per warp and a few warps per SM: nothing
+ * diverges and nothing hides latency, the launch lasts as long as the lone lane of the
+ * heaviest slice needs.  So here put_symbol_inline (ffv1enc.c:185-231) is written the
+ * straight way, as nested loops over the decisions of a residual with the bit values known at
+ * compile time where the symbol layout fixes them, slot 0 of the current row (the zero flag)
+ * in a register, the next token fetched while the current one is coded, and the
+ * renormalisation out of line (the loop has to stay inside the instruction caches: a lone
+ * warp waits out every instruction fetch).  Same packets as
+ * ff_encode_slice_range, byte for byte; no first-pass counters (those launches take the
+ * other form). */
+FFGPU_HD uint32_t ff_encode_slice_range_lone(const FFDevSlice &sl, const uint32_t *tokens,
+                                             uint8_t *state, const FFRacTables *tab_,
+                                             const FFRacPrefix &pre, const uint8_t *pre_bytes,
+                                             uint8_t *out, uint32_t *overflow, uint32_t *row_,
+                                             const int *rct = 0, uint32_t v4_room = 0)
+{
+    FFRacEnc c;
+    const uint32_t n = sl.ntok;
+    const uint32_t guard_tok = v4_room ? n - (uint32_t)sl.seg_w[sl.nseg - 1] : 0xFFFFFFFFu;  /* see above */
+    uint32_t guard_pos = 0, nb;
+    int cur_ctx = -1;
+    uint32_t s0 = 128;
+    (void)row_;
+#if defined(__CUDA_ARCH__)
+    uint32_t row_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_rows[threadIdx.x * FF_ROW_WORDS]);
+    uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_tab);
+    row_sa = ff_opaque(row_sa);
+    tab_sa = ff_opaque(tab_sa);
+#define FF_E_LD(slot) ff_lds8(row_sa + (uint32_t)(slot))
+#define FF_E_ST(slot, v) ff_sts8(row_sa + (uint32_t)(slot), (v))
+#define FF_E_NEXT(s, bit) ff_lds8(tab_sa + (uint32_t)(s) + ((bit) ? 0u : 256u))
+#define FF_E_RENORM()                                                                         \
+    do {                                                                                      \
+        const FFEncRenorm rn_ = ff_enc_renorm(c.low, c.range, c.pending, c.run, c.pos,        \
+                                              c.overflow, c.buf, c.cap);                      \
+        c.low = rn_.low; c.range = rn_.range; c.pending = rn_.pending; c.run = rn_.run;       \
+        c.pos = rn_.pos; c.overflow = rn_.overflow;                                           \
+    } while (0)
+#else
+#define FF_E_RENORM() ffrac_enc_shift1(&c)
+#define FF_E_LD(slot) ((uint32_t)FF_ROWB(slot))
+#define FF_E_ST(slot, v) (FF_ROWB(slot) = (uint8_t)(v))
+#define FF_E_NEXT(s, bit) ((uint32_t)FF_TAB((s) + ((bit) ? 0 : 256)))
+#endif
+/* put_rac + one renorm_encoder step, rangecoder.h:71-121 */
+#define FF_E_PUT(s, bit)                                                          \
+    do {                                                                          \
+        const int r1_ = (c.range * (int)(s)) >> 8, rb_ = c.range - r1_;           \
+        c.low += (bit) ? rb_ : 0;                                                 \
+        c.range = (bit) ? r1_ : rb_;                                              \
+        if (FF_UNLIKELY(c.range < 0x100))                                         \
+            FF_E_RENORM();                                                        \
+    } while (0)
+/* a decision on a slot of the row other than 0 */
+#define FF_E_SLOT(slot, bit)                                                      \
+    do {                                                                          \
+        const uint32_t sl_ = (uint32_t)(slot);                                    \
+        const uint32_t st_ = FF_E_LD(sl_);                                        \
+        FF_E_PUT(st_, bit);                                                       \
+        FF_E_ST(sl_, FF_E_NEXT(st_, bit));                                        \
+    } while (0)
+
+    ff_enc_resume(&c, pre, pre_bytes, out, sl.bs_cap);
+    if (rct)
+        ff_enc_v4_header_tail(&c, tab_, pre, rct[0], rct[1], 0);
+    {
+        uint32_t nxt = n ? tokens[0] : 0u;           /* the token after the current one, fetched ahead */
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t tok = nxt;
+            const int ctx = (int)(tok & FF_TOKEN_CTX_MASK);
+            const int diff = (int32_t)tok >> FF_TOKEN_CTX_BITS;
+            if (i + 1 < n)
+                nxt = tokens[i + 1];
+            if (i == guard_tok)
+                guard_pos = c.pos;
+            if (ctx != cur_ctx) {
+                if (cur_ctx >= 0) {
+                    FF_E_ST(0, s0);
+                    ff_row_store(FF_ROWW, state + (size_t)cur_ctx * FF_CONTEXT_SIZE);
+                }
+                ff_row_load(FF_ROWW, state + (size_t)ctx * FF_CONTEXT_SIZE);
+                s0 = FF_E_LD(0);
+                cur_ctx = ctx;
+            }
+            if (diff == 0) {
+                FF_E_PUT(s0, 1);
+                s0 = FF_E_NEXT(s0, 1);
+            } else {
+                const uint32_t a = (uint32_t)(diff < 0 ? -diff : diff);
+                const int e = ffrac_ilog2(a);
+                FF_E_PUT(s0, 0);
+                s0 = FF_E_NEXT(s0, 0);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+                for (int j = 0; j < e; j++)                     /* unary exponent */
+                    FF_E_SLOT(1 + ff_min(j, 9), 1);
+                FF_E_SLOT(1 + ff_min(e, 9), 0);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+                for (int j = e - 1; j >= 0; j--) {              /* mantissa, MSB first */
+                    const int bit = (int)((a >> j) & 1u);
+                    FF_E_SLOT(22 + ff_min(j, 9), bit);
+                }
+                {
+                    const int bit = diff < 0;
+                    FF_E_SLOT(11 + ff_min(e, 10), bit);
+                }
+            }
+        }
+    }
+    if (cur_ctx >= 0) {
+        FF_E_ST(0, s0);
+        ff_row_store(FF_ROWW, state + (size_t)cur_ctx * FF_CONTEXT_SIZE);
+    }
+#undef FF_E_LD
+#undef FF_E_ST
+#undef FF_E_NEXT
+#undef FF_E_PUT
+#undef FF_E_SLOT
+#undef FF_E_RENORM
     nb = ffrac_enc_finish(&c, tab_, 1);              /* ffv1enc.c:1242 */
     *overflow = c.overflow;
     if (v4_room && (int64_t)v4_room - (int64_t)guard_pos < (int64_t)sl.seg_w[sl.nseg - 1] * 35)
@@ -1044,6 +1205,7 @@ typedef struct FFDecCtx {
     uint32_t *touched;          /* one bit per context of the slice: its state row exists.   */
                                 /* NULL: every row was initialised before the slice started  */
     int any_five;               /* some quant table of the stream uses 5 context inputs      */
+    int lone;                   /* the slice has a warp of its own: ff_decode_slice_range_planar_lone */
 } FFDecCtx;
 
 FFGPU_HD int ff_wrap_sample(const FFDevParams &P, int v)
@@ -1650,11 +1812,6 @@ FFGPU_HD void ff_decode_slice_golomb(const FFDevParams &P, const FFDecSlice &d, 
  *     slice) instead of by a kernel that fills the whole arena: ff_ffv1_clear_slice_state
  *     (ffv1.c:182-207) without the memset traffic.  Only for streams whose every frame is a
  *     key frame and that carry no initial-state tables. */
-#if defined(__CUDA_ARCH__)
-#define FF_UNLIKELY(c) __builtin_expect(!!(c), 0)
-#else
-#define FF_UNLIKELY(c) (c)
-#endif
 /* samples of the previous line fetched ahead of their use (2 or 4) */
 #ifndef FF_DEC_AHEAD
 #define FF_DEC_AHEAD 4
@@ -1990,6 +2147,252 @@ FFGPU_HD void ff_decode_slice_range_planar(const FFDevParams &P, const FFDecSlic
     res->error = err;
 }
 
+/* The same slice decoder for launches that give every slice a warp of its own (streams with a
+ * handful of large slices: D.lane_stride == 32, one live lane per warp and at most a few warps
+ * per SM).  Nothing diverges there and nothing hides latency either: the launch lasts as long
+ * as the lone lane of the heaviest slice needs, i.e. instructions per sample times the
+ * dependent-issue latency.  So this form is written for instruction count on one lane:
+ * get_symbol_inline (ffv1dec.c:42-64) as straight nested loops instead of the
+ * one-decision-per-iteration state machine above (no votes, no per-decision bookkeeping of
+ * where the lane is inside a symbol).  Same results, byte for byte. */
+template <int SMODE, bool FIVE>
+FFGPU_HD void ff_decode_slice_range_planar_lone(const FFDevParams &P, const FFDecSlice &d, const uint8_t *pkt,
+                                                const FFDecCtx &D, FFDecResult *res, uint32_t *row_)
+{
+#if !defined(__CUDA_ARCH__)
+    const FFRacTables *tab_ = D.tab;
+    const int16_t *qt_all_ = D.qt_all;
+#endif
+    typedef typename FFPix<SMODE>::type pix_t;
+    const uint32_t mask = (1u << P.cbits) - 1;
+    const uint8_t *buf = pkt + d.pkt_off;
+    int low = d.low, range = d.range, overread = d.overread;
+    uint32_t pos = d.pos;
+    const uint32_t end = d.size;
+    uint32_t nbyte = buf[pos];                        /* buf[pos], fetched ahead */
+    FFLineIt it;
+    int err = 0, cur_ctx = -1;
+    uint32_t s0 = 128;                                /* slot 0 of the current row, see above */
+    uint8_t *const scratch = (uint8_t *)D.lines;
+    const size_t lbytes = (size_t)D.line_stride * sizeof(int32_t);
+    (void)row_;
+#if defined(__CUDA_ARCH__)
+    uint32_t row_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_rows[threadIdx.x * FF_ROW_WORDS]);
+    uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(ff_s_tab16);
+    uint32_t qt_sa = (uint32_t)__cvta_generic_to_shared(ff_s_qt);
+    row_sa = ff_opaque(row_sa);                      /* see ff_encode_slice_range */
+    tab_sa = ff_opaque(tab_sa);
+    qt_sa = ff_opaque(qt_sa);
+    uint32_t q_sa = qt_sa;
+#define FF_QTL(i) ff_lds16s(q_sa + 2u * (uint32_t)(i))
+#define FF_ST_LD(sl) ff_lds8(row_sa + (uint32_t)(sl))
+#define FF_ST_ST(sl, v) ff_sts8(row_sa + (uint32_t)(sl), (v))
+#define FF_TAB16(st) ff_lds16u(tab_sa + 2u * (st))
+#define FF_LONE_REFILL()                                                          \
+    do {                                                                          \
+        const uint4 rf = ff_dec_refill(low, pos, overread, nbyte, buf, end);      \
+        range <<= 8;                                                              \
+        low = (int)rf.x;                                                          \
+        pos = rf.y;                                                               \
+        overread = (int)rf.z;                                                     \
+        nbyte = rf.w;                                                             \
+    } while (0)
+#else
+#define FF_QTL(i) FF_QT(qo, i)
+#define FF_ST_LD(sl) ((uint32_t)FF_ROWB(sl))
+#define FF_ST_ST(sl, v) (FF_ROWB(sl) = (uint8_t)(v))
+#define FF_TAB16(st) ((uint32_t)FF_TAB(st) | ((uint32_t)FF_TAB(256 + (st)) << 8))
+#define FF_LONE_REFILL()                                                          \
+    do {                                                                          \
+        const int in = pos < end;                                                 \
+        range <<= 8;                                                              \
+        low = (low << 8) + (in ? (int)nbyte : 0);                                 \
+        pos += (uint32_t)in;                                                      \
+        overread += !in;                                                          \
+        nbyte = buf[pos];                                                         \
+    } while (0)
+#endif
+/* one binary decision (get_rac + refill, rangecoder.h:123-152) on the state value `st`:
+ * the bit in `bit_`, the successor state in `ns_` */
+#define FF_LONE_GET(st, bit_, ns_)                                                \
+    do {                                                                          \
+        const uint32_t st_ = (st);                                                \
+        const uint32_t t16_ = FF_TAB16(st_);                                      \
+        const int r1_ = (range * (int)st_) >> 8;                                  \
+        range -= r1_;                                                             \
+        bit_ = low >= range;                                                      \
+        ns_ = bit_ ? (t16_ & 0xFFu) : (t16_ >> 8);                                \
+        low -= bit_ ? range : 0;                                                  \
+        range = bit_ ? r1_ : range;                                               \
+        if (FF_UNLIKELY(range < 0x100))                                           \
+            FF_LONE_REFILL();                                                     \
+    } while (0)
+
+    for (int k = 0; k < P.ncoded; k++) {              /* zero rows, as above */
+        const int sub = P.cp[k].hs || P.cp[k].vs;
+        if (k && !sub)
+            continue;
+        const int pw = ff_crshift(d.w, P.cp[k].hs);
+        const int nw = (pw * 2 + 3) / 4 + 1;
+        for (int l = 0; l < (sub ? 2 : 1); l++) {
+            uint32_t *z = (uint32_t *)(scratch + ((size_t)k * 2 + l) * lbytes);
+            for (int i = 0; i < nw; i++)
+                z[i] = 0;
+        }
+    }
+    if (ff_line_first(P, d, &it)) {
+        do {
+            const FFDevPlane cp = P.cp[it.k];
+            const int sub = cp.hs || cp.vs;
+            uint8_t *const ol = D.frame + P.plane_off[cp.mem] +
+                                (size_t)((d.y >> cp.vs) + it.y) * P.pitch[cp.mem] +
+                                (size_t)(d.x >> cp.hs) * cp.step + cp.off;
+            const int w = it.w;
+            const int qo = d.qidx[cp.set] * FF_QT_STRIDE;
+            const int five = FIVE ? FF_QT(qo, FF_MAX_CTX_INPUTS * 256) : 0;
+            const int sbase = P.set_base[cp.set];
+            const int step = SMODE == 1 ? cp.step : 2;
+            const uint8_t *pl, *ppl;
+            uint8_t *ll;
+            int T, LT, L, LL = 0, q0, q1;
+#if defined(__CUDA_ARCH__)
+            q_sa = qt_sa + 2u * (uint32_t)qo;
+#else
+            (void)qo;
+#endif
+            if (sub) {
+                uint8_t *l0 = scratch + (size_t)it.k * 2 * lbytes;
+                ll = (it.y & 1) ? l0 + lbytes : l0;
+                pl = (it.y & 1) ? l0 : l0 + lbytes;
+                ppl = ll;
+            } else {
+                ll = 0;
+                pl = it.y >= 1 ? ol - P.pitch[cp.mem] : scratch;
+                ppl = it.y >= 2 ? ol - 2 * (size_t)P.pitch[cp.mem] : scratch;
+            }
+            T = ff_pix_load<SMODE>(pl);
+            LT = ff_pix_load<SMODE>(ppl);
+            L = T;
+            q0 = ff_pix_load<SMODE>(pl + (size_t)ff_min(1, w - 1) * step);
+            q1 = ff_pix_load<SMODE>(pl + (size_t)ff_min(2, w - 1) * step);
+            if (overread > 2) {                       /* is_input_end at line start */
+                err = 1;
+                break;
+            }
+            for (int x = 0; x < w; x++) {
+                int ctx, sign, bit, diff, v;
+                uint32_t ns;
+                const int RT = q0;
+                if (FF_UNLIKELY(x && !(x & 1023) && overread > 2)) {
+                    err = 1;
+                    break;
+                }
+                q0 = q1;
+                q1 = ff_pix_load<SMODE>(pl + (size_t)ff_min(x + 3, w - 1) * step);
+                ctx = FF_QTL((L - LT) & 0xFF) + FF_QTL(256 + ((LT - T) & 0xFF)) +
+                      FF_QTL(512 + ((T - RT) & 0xFF));
+                if (FIVE && five) {
+                    const int TT = ff_pix_load<SMODE>(ppl + (size_t)x * step);
+                    ctx += FF_QTL(768 + ((LL - L) & 0xFF)) + FF_QTL(1024 + ((TT - T) & 0xFF));
+                }
+                sign = ctx < 0;
+                ctx = sbase + (sign ? -ctx : ctx);
+                if (ctx != cur_ctx) {
+                    if (cur_ctx >= 0) {
+                        FF_ST_ST(0, s0);
+                        ff_row_store(FF_ROWW, D.rstate + (size_t)cur_ctx * FF_CONTEXT_SIZE);
+                    }
+                    if (D.touched) {
+                        const uint32_t tw = D.touched[ctx >> 5], tb = 1u << (ctx & 31);
+                        if (tw & tb) {
+                            ff_row_load(FF_ROWW, D.rstate + (size_t)ctx * FF_CONTEXT_SIZE);
+                        } else {
+                            uint32_t *rw = FF_ROWW;
+                            D.touched[ctx >> 5] = tw | tb;
+                            rw[0] = rw[1] = rw[2] = rw[3] = rw[4] = rw[5] = rw[6] = rw[7] = 0x80808080u;
+                        }
+                    } else {
+                        ff_row_load(FF_ROWW, D.rstate + (size_t)ctx * FF_CONTEXT_SIZE);
+                    }
+                    s0 = FF_ST_LD(0);
+                    cur_ctx = ctx;
+                }
+                FF_LONE_GET(s0, bit, ns);             /* zero flag */
+                s0 = ns;
+                diff = 0;
+                if (!bit) {
+                    int e = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1                                      /* the loop has to stay inside the instruction caches */
+#endif
+                    for (;;) {                        /* unary exponent */
+                        const uint32_t sl = 1u + (uint32_t)ff_min(e, 9);
+                        FF_LONE_GET(FF_ST_LD(sl), bit, ns);
+                        FF_ST_ST(sl, ns);
+                        if (!bit)
+                            break;
+                        if (++e > 31) {               /* get_symbol returns AVERROR_INVALIDDATA */
+                            diff = FFRAC_SYMBOL_ERROR;
+                            break;
+                        }
+                    }
+                    if (diff == 0) {
+                        uint32_t a = 1;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+                        for (int i = e - 1; i >= 0; i--) {        /* mantissa */
+                            const uint32_t sl = 22u + (uint32_t)ff_min(i, 9);
+                            FF_LONE_GET(FF_ST_LD(sl), bit, ns);
+                            FF_ST_ST(sl, ns);
+                            a += a + (uint32_t)bit;
+                        }
+                        {
+                            const uint32_t sl = 11u + (uint32_t)ff_min(e, 10);
+                            FF_LONE_GET(FF_ST_LD(sl), bit, ns);
+                            FF_ST_ST(sl, ns);
+                        }
+                        diff = bit ? -(int)a : (int)a;
+                    }
+                }
+                diff = sign ? -diff : diff;
+                v = (int)(((uint32_t)ff_median3(L, L + T - LT, T) + (uint32_t)diff) & mask);
+                v = (int)(int16_t)v;
+                *(pix_t *)(ol + (size_t)x * step) = (pix_t)v;
+                if (ll)
+                    *(pix_t *)(ll + (size_t)x * step) = (pix_t)v;
+                LL = L;
+                L = v;
+                LT = T;
+                T = RT;
+            }
+            if (err)
+                break;
+        } while (ff_line_next(P, d, &it));
+    }
+    if (cur_ctx >= 0 && !D.touched) {                /* lazily created states die with the launch */
+        FF_ST_ST(0, s0);
+        ff_row_store(FF_ROWW, D.rstate + (size_t)cur_ctx * FF_CONTEXT_SIZE);
+    }
+#undef FF_QTL
+#undef FF_ST_LD
+#undef FF_ST_ST
+#undef FF_TAB16
+#undef FF_LONE_GET
+#undef FF_LONE_REFILL
+    {
+        FFRacDec c;
+        c.buf = buf; c.low = low; c.range = range; c.pos = pos; c.end = end; c.overread = overread;
+        if (P.version > 2) {                         /* end-of-slice check, ffv1dec.c:351-359 */
+            uint8_t term = 129;
+            ffrac_get(&c, D.tab, &term);
+        }
+        res->end_pos = c.pos;
+        res->overread = c.overread;
+    }
+    res->error = err;
+}
+
 /* A version 4 slice with slice_coding_mode == 1 ("PCM", decode_line ffv1dec_template.c:37-47):
  * every sample is `bits` raw decisions, each with a fresh state of 128; no prediction, no
  * contexts, no colour transform.  The reference encoder falls back to it when a slice
@@ -2063,7 +2466,15 @@ FFGPU_HD void ff_decode_slice(const FFDevParams &P, const FFDecSlice &d, const u
         ff_decode_slice_golomb(P, d, pkt, D, res);
     } else if (ff_decode_planar_mode(&P)) {
         /* planar YCbCr / gray (+alpha), 8-bit or LSB-packed 16-bit containers */
-        if (P.sbits <= 8) {
+        if (D.lone) {
+            if (P.sbits <= 8) {
+                if (D.any_five) ff_decode_slice_range_planar_lone<1, true>(P, d, pkt, D, res, row);
+                else            ff_decode_slice_range_planar_lone<1, false>(P, d, pkt, D, res, row);
+            } else {
+                if (D.any_five) ff_decode_slice_range_planar_lone<2, true>(P, d, pkt, D, res, row);
+                else            ff_decode_slice_range_planar_lone<2, false>(P, d, pkt, D, res, row);
+            }
+        } else if (P.sbits <= 8) {
             if (D.any_five) ff_decode_slice_range_planar<1, true>(P, d, pkt, D, res, row, 1);
             else            ff_decode_slice_range_planar<1, false>(P, d, pkt, D, res, row, 1);
         } else {

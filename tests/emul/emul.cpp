@@ -186,7 +186,14 @@ extern "C" int ffv1emul_encode(void *h, const uint8_t *const planes[4], const in
                                                e->prebytes.data(), &e->bs[sl.bs_off], &ovf,
                                                P.version > 3 ? &rct[2 * i] : nullptr,
                                                P.version > 3 ? (uint32_t)((16384 + (int64_t)P.width * P.height * 12) / P.nslices) : 0u);
-        } else if (e->pass1)
+        } else if (getenv("FFV1_EMUL_LONE") && !e->pass1)
+            /* the one-slice-per-warp form of the coder */
+            bytes[i] = ff_encode_slice_range_lone(e->sl[i], &e->tokens[e->sl[i].tok_off],
+                                             &e->rstate[(size_t)i * P.total_ctx * FF_CONTEXT_SIZE], &e->s.cur_tab,
+                                             pre[i], e->prebytes.data(), &e->bs[e->sl[i].bs_off], &ovf, row,
+                                             P.version > 3 ? &rct[2 * i] : nullptr,
+                                             P.version > 3 ? (uint32_t)((16384 + (int64_t)P.width * P.height * 12) / P.nslices) : 0u);
+        else if (e->pass1)
             bytes[i] = ff_encode_slice_range<true>(e->sl[i], &e->tokens[e->sl[i].tok_off],
                                              &e->rstate[(size_t)i * P.total_ctx * FF_CONTEXT_SIZE], &e->s.cur_tab,
                                              pre[i], e->prebytes.data(), &e->bs[e->sl[i].bs_off], &ovf, row,
@@ -342,6 +349,7 @@ extern "C" int ffv1emul_decode(void *h, const uint8_t *pkt_in, int size, uint8_t
         for (int q = 0; q < d->s.qt_count; q++)
             if (d->s.initial[q]) lazy = false;
         D.touched = lazy ? touched.data() : nullptr;
+        D.lone = getenv("FFV1_EMUL_LONE") != nullptr;   /* the one-slice-per-warp form of the decoder */
         if (lazy)                                   /* rows must come from the touched logic, not from the reset above */
             memset(rs, 0x55, (size_t)P.total_ctx * FF_CONTEXT_SIZE);
         alignas(16) uint32_t row[FF_ROW_WORDS];

@@ -45,6 +45,32 @@ def test_device_functions_match_oracle(fmt):
                 assert np.array_equal(a, b), (fmt, kw, kind)
 
 
+@pytest.mark.parametrize("form", ["FFV1_EMUL_SPLIT", "FFV1_EMUL_LONE"])
+def test_the_other_forms_of_the_slice_coders(form, monkeypatch):
+    """stage B in two halves (ff_chain_token + ff_encode_slice_records) and the straight-line
+    coders of one-slice-per-warp launches (ff_encode_slice_range_lone,
+    ff_decode_slice_range_planar_lone) give the same bytes and pictures as the oracle"""
+    monkeypatch.setenv(form, "1")
+    w, h = 80, 56
+    for fmt, kw in [("yuv420p", dict(slices=4, coder=1)), ("yuv420p10le", dict(slices=4, gop_size=1)),
+                    ("yuv444p16le", dict(coder=2, context=1)), ("gray", dict(coder=1, gop_size=1, context=1)),
+                    ("ya8", dict(coder=1, slices=4)), ("bgr0", dict(coder=1, slices=4)),
+                    ("gbrp16le", dict(slices=4, gop_size=1)), ("bgra", dict(level=4, strict=-2, coder=1, slices=4))]:
+        checker = "ref" if kw.get("level") == 4 else "oracle"    # the port does not restate version 4
+        if not cc.available(checker):
+            continue
+        orc = cc.Encoder(checker, w, h, fmt, **kw)
+        emu = cc.Encoder("emul", w, h, fmt, **kw)
+        do = cc.Decoder(checker, w, h, orc.extradata)
+        de = cc.Decoder("emul", w, h, orc.extradata)
+        for i, kind in enumerate(("testsrc2", "noise", "extremes", "smooth")):
+            planes = synth.GENERATORS[kind](fmt, w, h, i)
+            po = orc.encode(planes)
+            assert po == emu.encode(planes), (form, fmt, kw, kind)
+            for a, b in zip(do.decode(po), de.decode(po)):
+                assert np.array_equal(a, b), (form, fmt, kw, kind)
+
+
 def test_msb_aligned_sample_depth():
     """bits_per_raw_sample below the container depth in a 16-bit format (ffv1dec.c:158)"""
     w, h, fmt = 48, 32, "gray16le"

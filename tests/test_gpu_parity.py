@@ -67,6 +67,45 @@ def test_encoder_packets_match_oracle(fmt):
         enc.close()
 
 
+# The slice coders exist in several forms that the library picks by launch shape (slices per
+# launch): one slice per warp ("lone", the straight-line coders), one slice per warp with the
+# warp-wide loops, stage B in two halves, and one slice per lane.  The small pictures of this
+# file all take the first by default; the tuning hooks force the others.
+CODER_FORMS = [
+    dict(),
+    dict(FFGPU_LONE="0"),
+    dict(FFGPU_LONE="0", FFGPU_SPLIT="0"),
+    dict(FFGPU_LANE_STRIDE="1"),
+    dict(FFGPU_LANE_STRIDE="4"),
+]
+
+
+@pytest.mark.parametrize("env", CODER_FORMS, ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()) or "default")
+def test_every_form_of_the_slice_coders_matches_the_oracle(env, monkeypatch):
+    F = gpu()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    w, h = 211, 83
+    for fmt, kw in [("yuv420p10le", dict(slices=9, gop_size=1)), ("yuv444p", dict(slices=4, coder=1, gop_size=1)),
+                    ("yuv420p", dict(slices=4, coder=-2, context=1)), ("gray16le", dict(slices=4)),
+                    ("bgr0", dict(slices=4, coder=2, context=1, gop_size=1)), ("yuv422p", dict(coder=0, slices=4))]:
+        for kind in ("testsrc2", "noise", "smooth"):
+            enc = F.FFV1Encoder(w, h, fmt, **kw)
+            ref = cc.Encoder("oracle", w, h, fmt, **kw)
+            rdec = cc.Decoder("oracle", w, h, ref.extradata)
+            dec = F.FFV1Decoder(w, h, ref.extradata)
+            for fr in range(3):
+                planes = synth.GENERATORS[kind](fmt, w, h, fr)
+                pkt = ref.encode(planes)
+                assert enc.encode(planes) == pkt, (env, fmt, kind, fr)
+                want = rdec.decode(pkt)
+                got = dec.decode(pkt, fmt_hint=rdec.pix_fmt)
+                for a, b in zip(want, got):
+                    assert np.array_equal(a, b), (env, fmt, kind, fr)
+            enc.close()
+            dec.close()
+
+
 @pytest.mark.parametrize("fmt", FORMATS_SMALL)
 def test_decoder_pictures_match_oracle(fmt):
     F = gpu()
