@@ -41,12 +41,12 @@ WORKLOADS = {
     "C1": dict(desc="1080p yuv420p 8-bit, default 2x2 slices, Golomb-Rice, -g 1",
                w=1920, h=1080, fmt="yuv420p", opts=dict(gop_size=1), batch=768),
     "C3": dict(desc="4K bgr0 RCT, -coder range_tab -context 1, default 2x2 slices, -g 1",
-               w=3840, h=2160, fmt="bgr0", opts=dict(coder=2, context=1, gop_size=1), batch=96),
+               w=3840, h=2160, fmt="bgr0", opts=dict(coder=2, context=1, gop_size=1), batch=144),
     "C4": dict(desc="4K yuv444p16le, default 2x2 slices, range coder, -g 1: DECODE ONLY of a "
                     "reference-compatible stream",
-               w=3840, h=2160, fmt="yuv444p16le", opts=dict(gop_size=1), batch=96, decode_only=True),
+               w=3840, h=2160, fmt="yuv444p16le", opts=dict(gop_size=1), batch=144, decode_only=True),
     "C5": dict(desc="8K 7680x4320 yuv420p10le, default 3x3 slices, range coder, -g 1",
-               w=7680, h=4320, fmt="yuv420p10le", opts=dict(gop_size=1), batch=48),
+               w=7680, h=4320, fmt="yuv420p10le", opts=dict(gop_size=1), batch=64),
     "few": dict(desc="1080p yuv420p10le, default 3x3 slices, range coder (debug: one slice per warp)",
                 w=1920, h=1080, fmt="yuv420p10le", opts=dict(gop_size=1), batch=1),
     "small": dict(desc="640x360 yuv420p10le 60 slices (debug)", w=640, h=360, fmt="yuv420p10le",

@@ -634,9 +634,12 @@ static int enc_device_init(ffgpu_encoder *e)
         CK(cudaMalloc(&j->d_sort_tmp, j->sort_tmp_bytes));
         CK(cudaMalloc(&j->d_sched, sizeof(FFSched)));
         CK(cudaMemset(j->d_sched, 0, sizeof(FFSched)));
-        if (!golomb && !e->opt.pass1 && coder_lane_stride((long)B * P->nslices) >= 8 &&
+        const int stride_max = coder_lane_stride((long)B * P->nslices);
+        const int lone_off = getenv("FFGPU_LONE") && !atoi(getenv("FFGPU_LONE"));
+        if (!golomb && !e->opt.pass1 && stride_max >= 8 && (stride_max < 32 || lone_off) &&
             !(getenv("FFGPU_SPLIT") && !atoi(getenv("FFGPU_SPLIT")))) {
-            /* a group never has enough slices to fill the GPU's lanes: stage B in two halves.
+            /* a group never has enough slices to fill the GPU's lanes, but more than one per
+             * warp (those take the straight-line coder, k_code_range<true>): stage B in two halves.
              * Room for two decisions per sample on average (4 bytes per sample, like the
              * tokens); pictures that need more take the one-kernel coder, decided per group on
              * the device.  FFGPU_SPLIT=0 switches the split form off. */

@@ -1096,7 +1096,13 @@ k_decode(const FFDevParams P, const FFDecDev D, int nframes)
             live = C.lines != 0;
         }
     }
-    if (SMODE == 0) {
+    if (SMODE == 0 && LONE) {
+        /* range-coded RGB, one live lane per warp: the straight-line decoder */
+        if (live && w.pcm)
+            ff_decode_slice_pcm(P, w, D.pkt, C, &r);
+        else if (live)
+            ff_decode_slice_range_rgb_lone<FIVE>(P, w, D.pkt, C, &r, 0);
+    } else if (SMODE == 0) {
         if (live)
             ff_decode_slice(P, w, D.pkt, C, &r, 0);
     } else if (LONE) {
@@ -1177,6 +1183,9 @@ extern "C" int ffk_decode_group(const FFDevParams *P, const FFDecDev *D, int nfr
             } else {
                 if (D->any_five) DEC_LAUNCH_LONE(2, true); else DEC_LAUNCH_LONE(2, false);
             }
+        } else if (!planar && !D->generic && P->colorspace && P->ac != FF_AC_GOLOMB &&
+                   D->lane_stride == 32 && lone_ok) {
+            if (D->any_five) DEC_LAUNCH_LONE(0, true); else DEC_LAUNCH_LONE(0, false);
         } else if (planar == 1) {
             if (D->any_five) DEC_LAUNCH(1, true); else DEC_LAUNCH(1, false);
         } else if (planar == 2) {

@@ -2254,7 +2254,7 @@ FFGPU_HD void ff_decode_slice_range_planar_lone(const FFDevParams &P, const FFDe
             const int step = SMODE == 1 ? cp.step : 2;
             const uint8_t *pl, *ppl;
             uint8_t *ll;
-            int T, LT, L, LL = 0, q0, q1;
+            int T, LT, L, LL = 0, RT, R2, q0, qsum;
 #if defined(__CUDA_ARCH__)
             q_sa = qt_sa + 2u * (uint32_t)qo;
 #else
@@ -2273,30 +2273,46 @@ FFGPU_HD void ff_decode_slice_range_planar_lone(const FFDevParams &P, const FFDe
             T = ff_pix_load<SMODE>(pl);
             LT = ff_pix_load<SMODE>(ppl);
             L = T;
-            q0 = ff_pix_load<SMODE>(pl + (size_t)ff_min(1, w - 1) * step);
-            q1 = ff_pix_load<SMODE>(pl + (size_t)ff_min(2, w - 1) * step);
+            /* the previous line is read three samples ahead of its use */
+            RT = ff_pix_load<SMODE>(pl + (size_t)ff_min(1, w - 1) * step);
+            R2 = ff_pix_load<SMODE>(pl + (size_t)ff_min(2, w - 1) * step);
+            q0 = ff_pix_load<SMODE>(pl + (size_t)ff_min(3, w - 1) * step);
             if (overread > 2) {                       /* is_input_end at line start */
                 err = 1;
                 break;
             }
+            /* qsum: the context of the coming sample before sign and set offset
+             * (get_context, ffv1.h:173-186) */
+            qsum = FF_QTL((L - LT) & 0xFF) + FF_QTL(256 + ((LT - T) & 0xFF)) +
+                   FF_QTL(512 + ((T - RT) & 0xFF));
+            if (FIVE && five) {
+                const int TT = ff_pix_load<SMODE>(ppl);
+                qsum += FF_QTL(768 + ((LL - L) & 0xFF)) + FF_QTL(1024 + ((TT - T) & 0xFF));
+            }
             for (int x = 0; x < w; x++) {
-                int ctx, sign, bit, diff, v;
+                int bit, diff, v, part, qn;
                 uint32_t ns;
-                const int RT = q0;
+                const int sign = qsum < 0;
+                const int ctx = sbase + (sign ? -qsum : qsum);
+                const int pred = ff_median3(L, L + T - LT, T);
+                /* The context of sample x+1 needs this sample's value only for one of its
+                 * inputs (two with five inputs).  The rest (`part`) is summed up here, and
+                 * so is the v-dependent input under the assumption that the residual is
+                 * zero (`qn`, four of five samples in flat pictures): both overlap with the
+                 * decision below instead of following it. */
+                const int vs = (int)(int16_t)((uint32_t)pred & mask);
+                const int nq = ff_pix_load<SMODE>(pl + (size_t)ff_min(x + 4, w - 1) * step);
                 if (FF_UNLIKELY(x && !(x & 1023) && overread > 2)) {
                     err = 1;
                     break;
                 }
-                q0 = q1;
-                q1 = ff_pix_load<SMODE>(pl + (size_t)ff_min(x + 3, w - 1) * step);
-                ctx = FF_QTL((L - LT) & 0xFF) + FF_QTL(256 + ((LT - T) & 0xFF)) +
-                      FF_QTL(512 + ((T - RT) & 0xFF));
+                part = FF_QTL(256 + ((T - RT) & 0xFF)) + FF_QTL(512 + ((RT - R2) & 0xFF));
+                qn = FF_QTL((vs - T) & 0xFF);
                 if (FIVE && five) {
-                    const int TT = ff_pix_load<SMODE>(ppl + (size_t)x * step);
-                    ctx += FF_QTL(768 + ((LL - L) & 0xFF)) + FF_QTL(1024 + ((TT - T) & 0xFF));
+                    const int TTn = ff_pix_load<SMODE>(ppl + (size_t)ff_min(x + 1, w - 1) * step);
+                    part += FF_QTL(1024 + ((TTn - RT) & 0xFF));
+                    qn += FF_QTL(768 + ((L - vs) & 0xFF));
                 }
-                sign = ctx < 0;
-                ctx = sbase + (sign ? -ctx : ctx);
                 if (ctx != cur_ctx) {
                     if (cur_ctx >= 0) {
                         FF_ST_ST(0, s0);
@@ -2319,9 +2335,10 @@ FFGPU_HD void ff_decode_slice_range_planar_lone(const FFDevParams &P, const FFDe
                 }
                 FF_LONE_GET(s0, bit, ns);             /* zero flag */
                 s0 = ns;
-                diff = 0;
+                v = vs;
                 if (!bit) {
                     int e = 0;
+                    diff = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1                                      /* the loop has to stay inside the instruction caches */
 #endif
@@ -2354,23 +2371,258 @@ FFGPU_HD void ff_decode_slice_range_planar_lone(const FFDevParams &P, const FFDe
                         }
                         diff = bit ? -(int)a : (int)a;
                     }
+                    diff = sign ? -diff : diff;
+                    v = (int)(((uint32_t)pred + (uint32_t)diff) & mask);
+                    v = (int)(int16_t)v;
+                    qn = FF_QTL((v - T) & 0xFF);      /* the assumption did not hold */
+                    if (FIVE && five)
+                        qn += FF_QTL(768 + ((L - v) & 0xFF));
                 }
-                diff = sign ? -diff : diff;
-                v = (int)(((uint32_t)ff_median3(L, L + T - LT, T) + (uint32_t)diff) & mask);
-                v = (int)(int16_t)v;
                 *(pix_t *)(ol + (size_t)x * step) = (pix_t)v;
                 if (ll)
                     *(pix_t *)(ll + (size_t)x * step) = (pix_t)v;
+                qsum = part + qn;
                 LL = L;
                 L = v;
                 LT = T;
                 T = RT;
+                RT = R2;
+                R2 = q0;
+                q0 = nq;
             }
             if (err)
                 break;
         } while (ff_line_next(P, d, &it));
     }
     if (cur_ctx >= 0 && !D.touched) {                /* lazily created states die with the launch */
+        FF_ST_ST(0, s0);
+        ff_row_store(FF_ROWW, D.rstate + (size_t)cur_ctx * FF_CONTEXT_SIZE);
+    }
+#undef FF_QTL
+#undef FF_ST_LD
+#undef FF_ST_ST
+#undef FF_TAB16
+#undef FF_LONE_GET
+#undef FF_LONE_REFILL
+    {
+        FFRacDec c;
+        c.buf = buf; c.low = low; c.range = range; c.pos = pos; c.end = end; c.overread = overread;
+        if (P.version > 2) {                         /* end-of-slice check, ffv1dec.c:351-359 */
+            uint8_t term = 129;
+            ffrac_get(&c, D.tab, &term);
+        }
+        res->end_pos = c.pos;
+        res->overread = c.overread;
+    }
+    res->error = err;
+}
+
+/* The same for RGB slices (decode_rgb_frame, ffv1dec_template.c:131-200): the planes of a pixel
+ * row are coded line by line into int32 line buffers, and the row goes through the inverse
+ * colour transform once its last plane is done. */
+template <bool FIVE>
+FFGPU_HD void ff_decode_slice_range_rgb_lone(const FFDevParams &P, const FFDecSlice &d, const uint8_t *pkt,
+                                                const FFDecCtx &D, FFDecResult *res, uint32_t *row_)
+{
+#if !defined(__CUDA_ARCH__)
+    const FFRacTables *tab_ = D.tab;
+    const int16_t *qt_all_ = D.qt_all;
+#endif
+    const int use32 = P.use32;
+    const uint32_t mask = (1u << P.cbits) - 1;
+    const uint8_t *buf = pkt + d.pkt_off;
+    int low = d.low, range = d.range, overread = d.overread;
+    uint32_t pos = d.pos;
+    const uint32_t end = d.size;
+    uint32_t nbyte = buf[pos];                        /* buf[pos], fetched ahead */
+    FFLineIt it;
+    int err = 0, cur_ctx = -1;
+    uint32_t s0 = 128;                                /* slot 0 of the current row, see above */
+    (void)row_;
+#if defined(__CUDA_ARCH__)
+    uint32_t row_sa = (uint32_t)__cvta_generic_to_shared(&ff_s_rows[threadIdx.x * FF_ROW_WORDS]);
+    uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(ff_s_tab16);
+    uint32_t qt_sa = (uint32_t)__cvta_generic_to_shared(ff_s_qt);
+    row_sa = ff_opaque(row_sa);                      /* see ff_encode_slice_range */
+    tab_sa = ff_opaque(tab_sa);
+    qt_sa = ff_opaque(qt_sa);
+    uint32_t q_sa = qt_sa;
+#define FF_QTL(i) ff_lds16s(q_sa + 2u * (uint32_t)(i))
+#define FF_ST_LD(sl) ff_lds8(row_sa + (uint32_t)(sl))
+#define FF_ST_ST(sl, v) ff_sts8(row_sa + (uint32_t)(sl), (v))
+#define FF_TAB16(st) ff_lds16u(tab_sa + 2u * (st))
+#define FF_LONE_REFILL()                                                          \
+    do {                                                                          \
+        const uint4 rf = ff_dec_refill(low, pos, overread, nbyte, buf, end);      \
+        range <<= 8;                                                              \
+        low = (int)rf.x;                                                          \
+        pos = rf.y;                                                               \
+        overread = (int)rf.z;                                                     \
+        nbyte = rf.w;                                                             \
+    } while (0)
+#else
+#define FF_QTL(i) FF_QT(qo, i)
+#define FF_ST_LD(sl) ((uint32_t)FF_ROWB(sl))
+#define FF_ST_ST(sl, v) (FF_ROWB(sl) = (uint8_t)(v))
+#define FF_TAB16(st) ((uint32_t)FF_TAB(st) | ((uint32_t)FF_TAB(256 + (st)) << 8))
+#define FF_LONE_REFILL()                                                          \
+    do {                                                                          \
+        const int in = pos < end;                                                 \
+        range <<= 8;                                                              \
+        low = (low << 8) + (in ? (int)nbyte : 0);                                 \
+        pos += (uint32_t)in;                                                      \
+        overread += !in;                                                          \
+        nbyte = buf[pos];                                                         \
+    } while (0)
+#endif
+/* one binary decision (get_rac + refill, rangecoder.h:123-152) on the state value `st`:
+ * the bit in `bit_`, the successor state in `ns_` */
+#define FF_LONE_GET(st, bit_, ns_)                                                \
+    do {                                                                          \
+        const uint32_t st_ = (st);                                                \
+        const uint32_t t16_ = FF_TAB16(st_);                                      \
+        const int r1_ = (range * (int)st_) >> 8;                                  \
+        range -= r1_;                                                             \
+        bit_ = low >= range;                                                      \
+        ns_ = bit_ ? (t16_ & 0xFFu) : (t16_ >> 8);                                \
+        low -= bit_ ? range : 0;                                                  \
+        range = bit_ ? r1_ : range;                                               \
+        if (FF_UNLIKELY(range < 0x100))                                           \
+            FF_LONE_REFILL();                                                     \
+    } while (0)
+
+    for (int k = 0; k < P.ncoded; k++)                /* every plane starts from two zero lines */
+        for (int i = 0; i < 2 * D.line_stride; i++)
+            D.lines[(size_t)k * 2 * D.line_stride + i] = 0;
+    if (ff_line_first(P, d, &it)) {
+        do {
+            const FFDevPlane cp = P.cp[it.k];
+            int32_t *const l0 = D.lines + (size_t)it.k * 2 * D.line_stride;
+            int32_t *const cur = (it.y & 1) ? l0 + D.line_stride : l0;      /* still holds line y-2 */
+            const int32_t *const prev = (it.y & 1) ? l0 : l0 + D.line_stride;
+            const int w = d.w;
+            const int qo = d.qidx[cp.set] * FF_QT_STRIDE;
+            const int five = FIVE ? FF_QT(qo, FF_MAX_CTX_INPUTS * 256) : 0;
+            const int sbase = P.set_base[cp.set];
+            int T, LT, L, LL = 0, RT, R2, q0, qsum;
+#if defined(__CUDA_ARCH__)
+            q_sa = qt_sa + 2u * (uint32_t)qo;
+#else
+            (void)qo;
+#endif
+            T = prev[0];
+            LT = cur[0];
+            L = T;
+            RT = prev[ff_min(1, w - 1)];
+            R2 = prev[ff_min(2, w - 1)];
+            q0 = prev[ff_min(3, w - 1)];
+            if (overread > 2) {                       /* is_input_end at line start */
+                err = 1;
+                break;
+            }
+            qsum = FF_QTL((L - LT) & 0xFF) + FF_QTL(256 + ((LT - T) & 0xFF)) +
+                   FF_QTL(512 + ((T - RT) & 0xFF));
+            if (FIVE && five)
+                qsum += FF_QTL(768 + ((LL - L) & 0xFF)) + FF_QTL(1024 + ((cur[0] - T) & 0xFF));
+            for (int x = 0; x < w; x++) {
+                int bit, diff, v, part, qn;
+                uint32_t ns;
+                const int sign = qsum < 0;
+                const int ctx = sbase + (sign ? -qsum : qsum);
+                const int pred = ff_median3(L, L + T - LT, T);
+                /* see ff_decode_slice_range_planar_lone: the context of sample x+1, but for
+                 * the inputs that need this sample's value, is summed up ahead of the
+                 * decision, and those under the assumption of a zero residual */
+                const int vm = (int)((uint32_t)pred & mask);
+                const int vs = use32 ? vm : (int)(int16_t)vm;
+                const int nq = prev[ff_min(x + 4, w - 1)];
+                if (FF_UNLIKELY(x && !(x & 1023) && overread > 2)) {
+                    err = 1;
+                    break;
+                }
+                part = FF_QTL(256 + ((T - RT) & 0xFF)) + FF_QTL(512 + ((RT - R2) & 0xFF));
+                qn = FF_QTL((vs - T) & 0xFF);
+                if (FIVE && five) {
+                    part += FF_QTL(1024 + ((cur[ff_min(x + 1, w - 1)] - RT) & 0xFF));
+                    qn += FF_QTL(768 + ((L - vs) & 0xFF));
+                }
+                if (ctx != cur_ctx) {
+                    if (cur_ctx >= 0) {
+                        FF_ST_ST(0, s0);
+                        ff_row_store(FF_ROWW, D.rstate + (size_t)cur_ctx * FF_CONTEXT_SIZE);
+                    }
+                    ff_row_load(FF_ROWW, D.rstate + (size_t)ctx * FF_CONTEXT_SIZE);
+                    s0 = FF_ST_LD(0);
+                    cur_ctx = ctx;
+                }
+                FF_LONE_GET(s0, bit, ns);             /* zero flag */
+                s0 = ns;
+                v = vs;
+                if (!bit) {
+                    int e = 0;
+                    diff = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+                    for (;;) {                        /* unary exponent */
+                        const uint32_t sl = 1u + (uint32_t)ff_min(e, 9);
+                        FF_LONE_GET(FF_ST_LD(sl), bit, ns);
+                        FF_ST_ST(sl, ns);
+                        if (!bit)
+                            break;
+                        if (++e > 31) {               /* get_symbol returns AVERROR_INVALIDDATA */
+                            diff = FFRAC_SYMBOL_ERROR;
+                            break;
+                        }
+                    }
+                    if (diff == 0) {
+                        uint32_t a = 1;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+                        for (int i = e - 1; i >= 0; i--) {        /* mantissa */
+                            const uint32_t sl = 22u + (uint32_t)ff_min(i, 9);
+                            FF_LONE_GET(FF_ST_LD(sl), bit, ns);
+                            FF_ST_ST(sl, ns);
+                            a += a + (uint32_t)bit;
+                        }
+                        {
+                            const uint32_t sl = 11u + (uint32_t)ff_min(e, 10);
+                            FF_LONE_GET(FF_ST_LD(sl), bit, ns);
+                            FF_ST_ST(sl, ns);
+                        }
+                        diff = bit ? -(int)a : (int)a;
+                    }
+                    diff = sign ? -diff : diff;
+                    v = (int)(((uint32_t)pred + (uint32_t)diff) & mask);
+                    v = use32 ? v : (int)(int16_t)v;
+                    qn = FF_QTL((v - T) & 0xFF);      /* the assumption did not hold */
+                    if (FIVE && five)
+                        qn += FF_QTL(768 + ((L - v) & 0xFF));
+                }
+                cur[x] = v;
+                qsum = part + qn;
+                LL = L;
+                L = v;
+                LT = T;
+                T = RT;
+                RT = R2;
+                R2 = q0;
+                q0 = nq;
+            }
+            if (err)
+                break;
+            if (it.k == P.ncoded - 1) {              /* the pixel row is complete: inverse RCT, store */
+                const int o = (it.y & 1) ? D.line_stride : 0;
+                ff_store_line_rgb(P, D.frame, d.x, d.y + it.y, d.w,
+                                  D.lines + o, D.lines + 2 * D.line_stride + o,
+                                  D.lines + 4 * D.line_stride + o,
+                                  P.ncoded > 3 ? D.lines + 6 * D.line_stride + o : (const int32_t *)0,
+                                  d.rct_by, d.rct_ry, 0);
+            }
+        } while (ff_line_next(P, d, &it));
+    }
+    if (cur_ctx >= 0) {
         FF_ST_ST(0, s0);
         ff_row_store(FF_ROWW, D.rstate + (size_t)cur_ctx * FF_CONTEXT_SIZE);
     }
@@ -2481,6 +2733,11 @@ FFGPU_HD void ff_decode_slice(const FFDevParams &P, const FFDecSlice &d, const u
             if (D.any_five) ff_decode_slice_range_planar<2, true>(P, d, pkt, D, res, row, 1);
             else            ff_decode_slice_range_planar<2, false>(P, d, pkt, D, res, row, 1);
         }
+#if !defined(__CUDA_ARCH__)          /* on the device k_decode<0, FIVE, true> calls it, see there */
+    } else if (D.lone && P.colorspace != 0) {
+        if (D.any_five) ff_decode_slice_range_rgb_lone<true>(P, d, pkt, D, res, row);
+        else            ff_decode_slice_range_rgb_lone<false>(P, d, pkt, D, res, row);
+#endif
     } else {
         ff_decode_slice_range(P, d, pkt, D, res, row);
     }
