@@ -46,7 +46,7 @@ WORKLOADS = {
                     "reference-compatible stream",
                w=3840, h=2160, fmt="yuv444p16le", opts=dict(gop_size=1), batch=144, decode_only=True),
     "C5": dict(desc="8K 7680x4320 yuv420p10le, default 3x3 slices, range coder, -g 1",
-               w=7680, h=4320, fmt="yuv420p10le", opts=dict(gop_size=1), batch=64),
+               w=7680, h=4320, fmt="yuv420p10le", opts=dict(gop_size=1), batch=96),
     "few": dict(desc="1080p yuv420p10le, default 3x3 slices, range coder (debug: one slice per warp)",
                 w=1920, h=1080, fmt="yuv420p10le", opts=dict(gop_size=1), batch=1),
     "small": dict(desc="640x360 yuv420p10le 60 slices (debug)", w=640, h=360, fmt="yuv420p10le",

@@ -731,7 +731,9 @@ FFGPU_HD uint32_t ff_encode_slice_range_lone(const FFDevSlice &sl, const uint32_
     if (rct)
         ff_enc_v4_header_tail(&c, tab_, pre, rct[0], rct[1], 0);
     {
-        uint32_t nxt = n ? tokens[0] : 0u;           /* the token after the current one, fetched ahead */
+        /* the two tokens after the current one, fetched ahead: a new line of the token
+         * stream comes from L2 (one in 32 tokens), about two zero-flag tokens away */
+        uint32_t nxt = n ? tokens[0] : 0u, nxt2 = n > 1 ? tokens[1] : 0u;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -739,8 +741,9 @@ FFGPU_HD uint32_t ff_encode_slice_range_lone(const FFDevSlice &sl, const uint32_
             const uint32_t tok = nxt;
             const int ctx = (int)(tok & FF_TOKEN_CTX_MASK);
             const int diff = (int32_t)tok >> FF_TOKEN_CTX_BITS;
-            if (i + 1 < n)
-                nxt = tokens[i + 1];
+            nxt = nxt2;
+            if (i + 2 < n)
+                nxt2 = tokens[i + 2];
             if (i == guard_tok)
                 guard_pos = c.pos;
             if (ctx != cur_ctx) {

@@ -5,7 +5,7 @@
 set -x
 mkdir -p gpurun_out
 for wl in C4 C5 C3; do
-  timeout 170 python bench.py --workload $wl --steps 2 --warmup 3 --e2e-repeat 1 --e2e-depth 3 --no-pageable > gpurun_out/r02_bench_${wl}_lone.json 2> gpurun_out/${wl}_lone.err; echo "$wl rc=$?"; tail -2 gpurun_out/${wl}_lone.err
+  timeout 125 python bench.py --workload $wl --steps 2 --warmup 3 --e2e-repeat 1 --e2e-depth 3 --no-pageable > gpurun_out/r02_bench_${wl}_lone.json 2> gpurun_out/${wl}_lone.err; echo "$wl rc=$?"; tail -2 gpurun_out/${wl}_lone.err
 done
 for f in gpurun_out/r02_bench_*_lone.json; do python - "$f" <<'PY'
 import json,sys
@@ -17,5 +17,5 @@ except Exception as ex:
     print(sys.argv[1], "ERR", ex)
 PY
 done
-timeout 200 python -m pytest tests -m gpu -q -x -k "every_form or full_size or fate or wider or resident or damaged" > gpurun_out/pytest_final2.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_final2.log
+timeout 110 python -m pytest tests -m gpu -q -x -k "every_form or fate or damaged or wider or resident or (decoder_pictures and (bgr0 or gbrp16le or rgb48le)) or (version4_rgb and bgra)" > gpurun_out/pytest_final2.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_final2.log
 tail -4 gpurun_out/pytest_final2.log
