@@ -71,6 +71,28 @@ def test_the_other_forms_of_the_slice_coders(form, monkeypatch):
                 assert np.array_equal(a, b), (form, fmt, kw, kind)
 
 
+@pytest.mark.parametrize("form", [None, "FFV1_EMUL_LONE"])
+def test_pictures_narrower_than_the_look_ahead(form, monkeypatch):
+    """the decoders read the previous line several samples ahead of their use, clamped to the
+    line's last sample: lines of 1..5 samples (and their subsampled chroma) exercise every clamp"""
+    if form:
+        monkeypatch.setenv(form, "1")
+    for (w, h) in [(2, 2), (3, 5), (4, 3), (5, 1), (7, 2), (9, 4)]:
+        for fmt, kw in [("yuv420p", dict(coder=1)), ("yuv444p10le", dict()), ("gray16le", dict(context=1)),
+                        ("yuv410p", dict(coder=1, context=1)), ("ya8", dict(coder=1)), ("bgr0", dict(coder=1, context=1)),
+                        ("gbrp16le", dict())]:
+            orc = cc.Encoder("oracle", w, h, fmt, **kw)
+            emu = cc.Encoder("emul", w, h, fmt, **kw)
+            do = cc.Decoder("oracle", w, h, orc.extradata)
+            de = cc.Decoder("emul", w, h, orc.extradata)
+            for i, kind in enumerate(("noise", "testsrc2", "extremes")):
+                planes = synth.GENERATORS[kind](fmt, w, h, i)
+                po = orc.encode(planes)
+                assert po == emu.encode(planes), (form, w, h, fmt, kind)
+                for a, b in zip(do.decode(po), de.decode(po)):
+                    assert np.array_equal(a, b), (form, w, h, fmt, kind)
+
+
 def test_msb_aligned_sample_depth():
     """bits_per_raw_sample below the container depth in a 16-bit format (ffv1dec.c:158)"""
     w, h, fmt = 48, 32, "gray16le"
