@@ -71,6 +71,31 @@ def test_the_other_forms_of_the_slice_coders(form, monkeypatch):
                 assert np.array_equal(a, b), (form, fmt, kw, kind)
 
 
+@pytest.mark.parametrize("form", ["FFV1_EMUL_SPLIT", "FFV1_EMUL_LONE"])
+def test_the_other_forms_over_the_whole_format_matrix(form, monkeypatch):
+    """the GPU tests' small pictures all land in one-slice-per-warp launches, i.e. in the
+    straight-line coders: every format x option set of the main parity test through them (and
+    through the two-halves stage B), at a size whose slices are ragged"""
+    monkeypatch.setenv(form, "1")
+    w, h = 131, 67
+    extra = [dict(slices=4, gop_size=1), dict(coder=1, gop_size=1, slices=9), dict(coder=2, context=1, slices=4)]
+    for fmt in FORMATS:
+        for kw in OPTIONS + extra:
+            try:
+                orc = cc.Encoder("oracle", w, h, fmt, **kw)
+            except cc.CodecError:
+                continue
+            emu = cc.Encoder("emul", w, h, fmt, **kw)
+            do = cc.Decoder("oracle", w, h, orc.extradata)
+            de = cc.Decoder("emul", w, h, orc.extradata)
+            for i, kind in enumerate(("testsrc2", "noise", "extremes")):
+                planes = synth.GENERATORS[kind](fmt, w, h, i)
+                po = orc.encode(planes)
+                assert po == emu.encode(planes), (form, fmt, kw, kind)
+                for a, b in zip(do.decode(po), de.decode(po)):
+                    assert np.array_equal(a, b), (form, fmt, kw, kind)
+
+
 @pytest.mark.parametrize("form", [None, "FFV1_EMUL_LONE"])
 def test_pictures_narrower_than_the_look_ahead(form, monkeypatch):
     """the decoders read the previous line several samples ahead of their use, clamped to the
