@@ -547,28 +547,60 @@ static int enc_free_job(EncJob *j)
     return 0;
 }
 
-static int enc_device_init(ffgpu_encoder *e)
+/* a host array that exists only to be uploaded: device allocation + copy, then free(host) */
+static int upload_and_free(void **dev, void *host, size_t bytes)
+{
+    cudaError_t ce;
+    if (!host)
+        return fail(FFGPU_ENOMEM, "out of memory");
+    ce = cudaMalloc(dev, bytes);
+    if (ce == cudaSuccess)
+        ce = cudaMemcpy(*dev, host, bytes, cudaMemcpyHostToDevice);
+    free(host);
+    if (ce != cudaSuccess)
+        return fail(FFGPU_EXTERNAL, "CUDA: table upload failed: %s", cudaGetErrorString(ce));
+    return 0;
+}
+
+/* everything enc_device_create() made, complete or not */
+static void enc_device_release(ffgpu_encoder *e)
+{
+    cudaSetDevice(e->opt.device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i <= FFK_ENC_KERNELS; i++)
+        if (e->events[i]) {
+            cudaEventDestroy((cudaEvent_t)e->events[i]);
+            e->events[i] = NULL;
+        }
+    for (int i = 0; i < MAX_DEPTH; i++)
+        enc_free_job(&e->jobs[i]);
+    if (e->up_stream) cudaStreamDestroy(e->up_stream);
+    cudaFree(e->d_slices); cudaFree(e->d_qt); cudaFree(e->d_tab); cudaFree(e->d_prefix);
+    cudaFree(e->d_prefix_bytes); cudaFree(e->d_state_shared); cudaFree(e->d_iota);
+    cudaFree(e->d_rc_stat); cudaFree(e->d_rc_stat2); cudaFree(e->d_initial);
+    e->up_stream = NULL;
+    e->d_slices = NULL; e->d_qt = NULL; e->d_tab = NULL; e->d_prefix = NULL;
+    e->d_prefix_bytes = NULL; e->d_state_shared = NULL; e->d_iota = NULL;
+    e->d_rc_stat = e->d_rc_stat2 = NULL; e->d_initial = NULL;
+    e->dev_ready = 0;
+}
+
+static int enc_device_create(ffgpu_encoder *e)
 {
     const FFDevParams *P = &e->P;
     const int golomb = P->ac == FF_AC_GOLOMB;
     const size_t state_frame = (size_t)P->nslices * P->total_ctx * (golomb ? 8 : FF_CONTEXT_SIZE);
     int16_t *qt;
-    int ndev = 0;
+    int r;
 
-    if (e->dev_ready)
-        return 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
-        return fail(FFGPU_EXTERNAL, "no CUDA device: the FFV1 pixel path has no CPU fallback");
     CK(cudaSetDevice(e->opt.device));
     CK(cudaMalloc(&e->d_slices, sizeof(FFDevSlice) * P->nslices));
     CK(cudaMemcpy(e->d_slices, e->h_slices, sizeof(FFDevSlice) * P->nslices, cudaMemcpyHostToDevice));
     qt = (int16_t *)malloc(sizeof(int16_t) * FF_MAX_QUANT_TABLES * FF_QT_STRIDE);
-    if (!qt)
-        return fail(FFGPU_ENOMEM, "out of memory");
-    flatten_qt(&e->s, qt);
-    CK(cudaMalloc(&e->d_qt, sizeof(int16_t) * FF_MAX_QUANT_TABLES * FF_QT_STRIDE));
-    CK(cudaMemcpy(e->d_qt, qt, sizeof(int16_t) * FF_MAX_QUANT_TABLES * FF_QT_STRIDE, cudaMemcpyHostToDevice));
-    free(qt);
+    if (qt)
+        flatten_qt(&e->s, qt);
+    if ((r = upload_and_free((void **)&e->d_qt, qt, sizeof(int16_t) * FF_MAX_QUANT_TABLES * FF_QT_STRIDE)) < 0)
+        return r;
     CK(cudaMalloc(&e->d_tab, sizeof(FFRacTables)));
     CK(cudaMemcpy(e->d_tab, &e->s.cur_tab, sizeof(FFRacTables), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&e->d_prefix, sizeof(FFRacPrefix) * NPREFIX_SETS * P->nslices));
@@ -593,13 +625,10 @@ static int enc_device_init(ffgpu_encoder *e)
     {
         const size_t n = (size_t)e->max_batch * P->nslices;
         uint32_t *iota = (uint32_t *)malloc(n * sizeof(uint32_t));
-        if (!iota)
-            return fail(FFGPU_ENOMEM, "out of memory");
-        for (size_t i = 0; i < n; i++)
+        for (size_t i = 0; iota && i < n; i++)
             iota[i] = (uint32_t)i;
-        CK(cudaMalloc(&e->d_iota, n * sizeof(uint32_t)));
-        CK(cudaMemcpy(e->d_iota, iota, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        free(iota);
+        if ((r = upload_and_free((void **)&e->d_iota, iota, n * sizeof(uint32_t))) < 0)
+            return r;
     }
     for (int i = 0; i < e->depth; i++) {
         EncJob *j = &e->jobs[i];
@@ -668,6 +697,22 @@ static int enc_device_init(ffgpu_encoder *e)
         if (!j->pts || !j->key)
             return fail(FFGPU_ENOMEM, "out of memory");
     }
+    return 0;
+}
+
+/* the device side of a handle appears with the first picture.  A failure part-way (out of
+ * device or page-locked memory) leaves nothing behind: the next call starts over. */
+static int enc_device_init(ffgpu_encoder *e)
+{
+    int ndev = 0, r;
+    if (e->dev_ready)
+        return 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(FFGPU_EXTERNAL, "no CUDA device: the FFV1 pixel path has no CPU fallback");
+    if ((r = enc_device_create(e)) < 0) {
+        enc_device_release(e);
+        return r;
+    }
     e->dev_ready = 1;
     return 0;
 }
@@ -691,17 +736,16 @@ extern "C" int ffgpu_ffv1_encode_init(ffgpu_encoder **penc, const ffgpu_enc_opti
         e->opt.stats_in = e->stats_in;
     }
     if ((r = ff_stream_from_options(&e->s, &e->opt)) < 0) {
-        free(e);
+        ffgpu_ffv1_encode_close(e);             /* frees what exists so far (stats_in, state tables) */
         return fail(r, "encode_init: options rejected (%d)", r);
     }
     if ((r = ff_write_extradata(&e->s, opt->gop_size, &e->extradata, &e->extradata_size)) < 0) {
-        free(e);
+        ffgpu_ffv1_encode_close(e);
         return fail(r, "encode_init: extradata");
     }
     e->h_slices = (FFDevSlice *)calloc((size_t)e->s.nh * e->s.nv, sizeof(FFDevSlice));
     if (!e->h_slices) {
-        free(e->extradata);
-        free(e);
+        ffgpu_ffv1_encode_close(e);
         return fail(FFGPU_ENOMEM, "out of memory");
     }
     ff_fill_dev_params(&e->s, 1, &e->P, e->h_slices);
@@ -1453,15 +1497,7 @@ extern "C" int ffgpu_ffv1_encode_close(ffgpu_encoder *e)
         cudaSetDevice(e->opt.device);
         cudaDeviceSynchronize();
         trace_dump();
-        for (int i = 0; i <= FFK_ENC_KERNELS; i++)
-            if (e->events[i])
-                cudaEventDestroy((cudaEvent_t)e->events[i]);
-        for (int i = 0; i < MAX_DEPTH; i++)
-            enc_free_job(&e->jobs[i]);
-        if (e->up_stream) cudaStreamDestroy(e->up_stream);
-        cudaFree(e->d_slices); cudaFree(e->d_qt); cudaFree(e->d_tab); cudaFree(e->d_prefix);
-        cudaFree(e->d_prefix_bytes); cudaFree(e->d_state_shared); cudaFree(e->d_iota);
-        cudaFree(e->d_rc_stat); cudaFree(e->d_rc_stat2); cudaFree(e->d_initial);
+        enc_device_release(e);
     }
     free(e->stats_in);
     free(e->h_slices);
@@ -1641,25 +1677,37 @@ static int dec_size_states(ffgpu_decoder *d, const uint8_t *pkt, size_t size)
     return 0;
 }
 
-static int dec_device_init(ffgpu_decoder *d)
+/* everything dec_device_create() made, complete or not */
+static void dec_device_release(ffgpu_decoder *d)
+{
+    cudaSetDevice(d->opt.device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < MAX_DEPTH; i++)
+        dec_free_job(&d->jobs[i]);
+    if (d->down_stream) cudaStreamDestroy(d->down_stream);
+    cudaFree(d->d_qt); cudaFree(d->d_tab); cudaFree(d->d_initial); cudaFree(d->d_state_shared);
+    cudaFree(d->d_prev); cudaFree(d->d_iota);
+    if (d->prev_ready) cudaEventDestroy(d->prev_ready);
+    d->down_stream = NULL;
+    d->d_qt = NULL; d->d_tab = NULL; d->d_initial = NULL; d->d_state_shared = NULL;
+    d->d_prev = NULL; d->d_iota = NULL;
+    d->prev_ready = NULL;
+    d->dev_ready = 0;
+}
+
+static int dec_device_create(ffgpu_decoder *d)
 {
     const FFDevParams *P = &d->P;
     const int golomb = P->ac == FF_AC_GOLOMB;
     const size_t state_frame = (size_t)d->max_slices * P->total_ctx * (golomb ? 8 : FF_CONTEXT_SIZE);
     int16_t *qt;
-    int ndev = 0, any_initial = 0;
-    if (d->dev_ready)
-        return 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
-        return fail(FFGPU_EXTERNAL, "no CUDA device: the FFV1 pixel path has no CPU fallback");
+    int any_initial = 0, r;
     CK(cudaSetDevice(d->opt.device));
     qt = (int16_t *)malloc(sizeof(int16_t) * FF_MAX_QUANT_TABLES * FF_QT_STRIDE);
-    if (!qt)
-        return fail(FFGPU_ENOMEM, "out of memory");
-    flatten_qt(&d->s, qt);
-    CK(cudaMalloc(&d->d_qt, sizeof(int16_t) * FF_MAX_QUANT_TABLES * FF_QT_STRIDE));
-    CK(cudaMemcpy(d->d_qt, qt, sizeof(int16_t) * FF_MAX_QUANT_TABLES * FF_QT_STRIDE, cudaMemcpyHostToDevice));
-    free(qt);
+    if (qt)
+        flatten_qt(&d->s, qt);
+    if ((r = upload_and_free((void **)&d->d_qt, qt, sizeof(int16_t) * FF_MAX_QUANT_TABLES * FF_QT_STRIDE)) < 0)
+        return r;
     CK(cudaMalloc(&d->d_tab, sizeof(FFRacTables)));
     CK(cudaMemcpy(d->d_tab, &d->s.cur_tab, sizeof(FFRacTables), cudaMemcpyHostToDevice));
     for (int i = 0; i < d->s.qt_count; i++)
@@ -1667,16 +1715,14 @@ static int dec_device_init(ffgpu_decoder *d)
     if (any_initial) {
         const size_t per = (size_t)d->max_ctx * FF_CONTEXT_SIZE;
         uint8_t *tmp = (uint8_t *)malloc(per * FF_MAX_QUANT_TABLES);
-        if (!tmp)
-            return fail(FFGPU_ENOMEM, "out of memory");
-        memset(tmp, 128, per * FF_MAX_QUANT_TABLES);
-        for (int i = 0; i < d->s.qt_count; i++)
+        if (tmp)
+            memset(tmp, 128, per * FF_MAX_QUANT_TABLES);
+        for (int i = 0; tmp && i < d->s.qt_count; i++)
             if (d->s.initial[i])
                 memcpy(tmp + per * i, d->s.initial[i],
                        (size_t)(d->s.ctx_count[i] < d->max_ctx ? d->s.ctx_count[i] : d->max_ctx) * FF_CONTEXT_SIZE);
-        CK(cudaMalloc(&d->d_initial, per * FF_MAX_QUANT_TABLES));
-        CK(cudaMemcpy(d->d_initial, tmp, per * FF_MAX_QUANT_TABLES, cudaMemcpyHostToDevice));
-        free(tmp);
+        if ((r = upload_and_free((void **)&d->d_initial, tmp, per * FF_MAX_QUANT_TABLES)) < 0)
+            return r;
     }
     if (!d->intra)
         CK(cudaMalloc(&d->d_state_shared, state_frame));
@@ -1697,13 +1743,10 @@ static int dec_device_init(ffgpu_decoder *d)
     {
         const size_t n = (size_t)d->max_batch * d->max_slices;
         uint32_t *iota = (uint32_t *)malloc(n * sizeof(uint32_t));
-        if (!iota)
-            return fail(FFGPU_ENOMEM, "out of memory");
-        for (size_t i = 0; i < n; i++)
+        for (size_t i = 0; iota && i < n; i++)
             iota[i] = (uint32_t)i;
-        CK(cudaMalloc(&d->d_iota, n * sizeof(uint32_t)));
-        CK(cudaMemcpy(d->d_iota, iota, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        free(iota);
+        if ((r = upload_and_free((void **)&d->d_iota, iota, n * sizeof(uint32_t))) < 0)
+            return r;
     }
     for (int i = 0; i < d->depth; i++) {
         DecJob *j = &d->jobs[i];
@@ -1746,6 +1789,21 @@ static int dec_device_init(ffgpu_decoder *d)
         if (!j->meta)
             return fail(FFGPU_ENOMEM, "out of memory");
     }
+    return 0;
+}
+
+/* the device side appears with the first packet; a failure part-way leaves nothing behind */
+static int dec_device_init(ffgpu_decoder *d)
+{
+    int ndev = 0, r;
+    if (d->dev_ready)
+        return 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(FFGPU_EXTERNAL, "no CUDA device: the FFV1 pixel path has no CPU fallback");
+    if ((r = dec_device_create(d)) < 0) {
+        dec_device_release(d);
+        return r;
+    }
     d->dev_ready = 1;
     return 0;
 }
@@ -1772,13 +1830,11 @@ extern "C" int ffgpu_ffv1_decode_init(ffgpu_decoder **pdec, const ffgpu_dec_opti
     d->s.cur_tab = d->s.def_tab;
     if (opt->extradata_size > 0) {
         if ((r = ff_parse_extradata(&d->s, opt->extradata, opt->extradata_size)) < 0) {
-            ff_stream_free(&d->s);
-            free(d);
+            ffgpu_ffv1_decode_close(d);
             return fail(r, "decode_init: invalid extradata (%d)", r);
         }
         if ((r = dec_setup_stream(d)) < 0) {
-            ff_stream_free(&d->s);
-            free(d);
+            ffgpu_ffv1_decode_close(d);
             return r;
         }
     }
@@ -2489,12 +2545,7 @@ extern "C" int ffgpu_ffv1_decode_close(ffgpu_decoder *d)
         cudaSetDevice(d->opt.device);
         cudaDeviceSynchronize();
         trace_dump();
-        for (int i = 0; i < MAX_DEPTH; i++)
-            dec_free_job(&d->jobs[i]);
-        if (d->down_stream) cudaStreamDestroy(d->down_stream);
-        cudaFree(d->d_qt); cudaFree(d->d_tab); cudaFree(d->d_initial); cudaFree(d->d_state_shared);
-        cudaFree(d->d_prev); cudaFree(d->d_iota);
-        if (d->prev_ready) cudaEventDestroy(d->prev_ready);
+        dec_device_release(d);
     }
     free(d->h_slices);
     ff_stream_free(&d->s);

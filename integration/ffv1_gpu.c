@@ -192,9 +192,14 @@ static int gpu_send_frame(AVCodecContext *avctx, const AVFrame *pict)
     }
     if (s->fifo_count == GPU_FIFO)
         return AVERROR(EAGAIN);
+    /* the planes are read asynchronously: hold a reference until the packet is out, and give
+     * the library the planes of THAT reference (for a frame that is not refcounted
+     * av_frame_clone copies the picture, and the caller may reuse its own right away) */
+    if (!(ref = av_frame_clone(pict)))
+        return AVERROR(ENOMEM);
     for (i = 0; i < 4; i++) {
-        p.data[i] = pict->data[i];
-        p.linesize[i] = pict->linesize[i];
+        p.data[i] = ref->data[i];
+        p.linesize[i] = ref->linesize[i];
     }
     p.interlaced_frame = pict->interlaced_frame;
     p.top_field_first = pict->top_field_first;
@@ -207,12 +212,10 @@ static int gpu_send_frame(AVCodecContext *avctx, const AVFrame *pict)
     if (ret < 0) {
         if (ret != AVERROR(EAGAIN))
             av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
+        av_frame_free(&ref);
         return ret;
     }
-    /* the planes are read asynchronously: hold the frame until its packet is out */
-    if (!(ref = av_frame_clone(pict)))
-        return AVERROR(ENOMEM);
-    return fifo_push(s, ref);
+    return fifo_push(s, ref);                  /* cannot fail: room was checked above */
 }
 
 static int gpu_receive_packet(AVCodecContext *avctx, AVPacket *pkt)
