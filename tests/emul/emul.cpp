@@ -276,7 +276,7 @@ extern "C" void *ffv1emul_decoder_open(int w, int h, const uint8_t *ex, int exsi
     *err = 0;
     if (!w || !h) *err = FFGPU_INVALIDDATA;
     if (*err >= 0 && exsize > 0) *err = ff_parse_extradata(&d->s, ex, exsize);
-    if (*err < 0) { delete d; return nullptr; }
+    if (*err < 0) { ff_stream_free(&d->s); delete d; return nullptr; }
     d->hs.max_slices = d->s.nh * d->s.nv;
     return d;
 }

@@ -323,3 +323,18 @@ def test_two_pass_matches_the_reference(fmt):
                 break
             for a, b in zip(want, de.decode(pkt)):
                 assert np.array_equal(a, b), (fmt, kw)
+
+
+def test_damaged_input_under_the_sanitizers():
+    """tests/emul/fuzz: the parsers and both forms of the slice decoders over mutated packets
+    and mutated extradata, built with -fsanitize=address,undefined -- any out-of-bounds access
+    on hostile input (a device fault on the GPU) fails here"""
+    import os
+    import subprocess
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul")
+    b = subprocess.run(["make", "-C", here, "fuzz"], capture_output=True, text=True)
+    if b.returncode != 0:
+        pytest.skip("sanitizer build not available: " + b.stderr[-200:])
+    for seed in (1, 7):
+        r = subprocess.run([os.path.join(here, "fuzz"), "40", str(seed)], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "fuzz ok" in r.stdout, (seed, r.stdout[-500:], r.stderr[-3000:])
