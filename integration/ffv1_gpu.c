@@ -38,8 +38,7 @@
 #define CUDA_POP(s)  do { } while (0)
 #endif
 
-#define GPU_FIFO 2048
-#define GPU_STATS_OUT_SIZE (1024 * 1024 * 6)   /* STATS_OUT_SIZE, ffv1enc.c:911 */          /* >= pictures the launch groups of one handle can hold in flight */
+#define GPU_STATS_OUT_SIZE (1024 * 1024 * 6)   /* STATS_OUT_SIZE, ffv1enc.c:911 */
 
 typedef struct FFV1GpuContext {
     AVClass *class;            /* first member: avcodec_open2 applies the AVOptions (utils.c:630-639) */
@@ -58,18 +57,40 @@ typedef struct FFV1GpuContext {
      * reference to every input frame (the library reads the planes asynchronously until the
      * packet is out, like ffv1enc.c:1194-1196 keeps its av_frame_ref).  Decoder: the output
      * frames the pictures are downloaded into. */
-    AVFrame *fifo[GPU_FIFO];
-    int fifo_head, fifo_count;
+    AVFrame **fifo;            /* ring that grows with what the launch groups hold in flight
+                                * (up to gpu_batch x gpu_depth pictures per GPU) */
+    int fifo_head, fifo_count, fifo_cap;
     AVPacket *pending;         /* decoder: a packet the library could not take yet */
     int draining, eof;
     void *cu_ctx;              /* AV_PIX_FMT_CUDA input: the hw device's CUcontext, else NULL */
 } FFV1GpuContext;
 
+/* room for one more entry; the only way fifo_push can fail, so callers reserve BEFORE they
+ * hand a picture to the library */
+static int fifo_reserve(FFV1GpuContext *s)
+{
+    AVFrame **ring;
+    int cap, i;
+    if (s->fifo_count < s->fifo_cap)
+        return 0;
+    cap = s->fifo_cap ? 2 * s->fifo_cap : 256;
+    if (!(ring = av_mallocz_array(cap, sizeof(*ring))))
+        return AVERROR(ENOMEM);
+    for (i = 0; i < s->fifo_count; i++)
+        ring[i] = s->fifo[(s->fifo_head + i) % s->fifo_cap];
+    av_free(s->fifo);
+    s->fifo = ring;
+    s->fifo_cap = cap;
+    s->fifo_head = 0;
+    return 0;
+}
+
 static int fifo_push(FFV1GpuContext *s, AVFrame *f)
 {
-    if (s->fifo_count == GPU_FIFO)
-        return AVERROR(ENOMEM);
-    s->fifo[(s->fifo_head + s->fifo_count++) % GPU_FIFO] = f;
+    int ret = fifo_reserve(s);
+    if (ret < 0)
+        return ret;
+    s->fifo[(s->fifo_head + s->fifo_count++) % s->fifo_cap] = f;
     return 0;
 }
 
@@ -80,7 +101,7 @@ static AVFrame *fifo_pop(FFV1GpuContext *s)
         return NULL;
     f = s->fifo[s->fifo_head];
     s->fifo[s->fifo_head] = NULL;
-    s->fifo_head = (s->fifo_head + 1) % GPU_FIFO;
+    s->fifo_head = (s->fifo_head + 1) % s->fifo_cap;
     s->fifo_count--;
     return f;
 }
@@ -190,8 +211,8 @@ static int gpu_send_frame(AVCodecContext *avctx, const AVFrame *pict)
         CUDA_POP(s);
         return ret;
     }
-    if (s->fifo_count == GPU_FIFO)
-        return AVERROR(EAGAIN);
+    if ((ret = fifo_reserve(s)) < 0)
+        return ret;
     /* the planes are read asynchronously: hold a reference until the packet is out, and give
      * the library the planes of THAT reference (for a frame that is not refcounted
      * av_frame_clone copies the picture, and the caller may reuse its own right away) */
@@ -215,7 +236,7 @@ static int gpu_send_frame(AVCodecContext *avctx, const AVFrame *pict)
         av_frame_free(&ref);
         return ret;
     }
-    return fifo_push(s, ref);                  /* cannot fail: room was checked above */
+    return fifo_push(s, ref);                  /* cannot fail: room was reserved above */
 }
 
 static int gpu_receive_packet(AVCodecContext *avctx, AVPacket *pkt)
@@ -271,16 +292,20 @@ static int gpu_receive_packet(AVCodecContext *avctx, AVPacket *pkt)
 static av_cold int gpu_close(AVCodecContext *avctx)
 {
     FFV1GpuContext *s = avctx->priv_data;
-    int i;
+    AVFrame *f;
+    /* the library first: it waits for the GPU, which may still read the frames' planes */
     CUDA_PUSH(s);
     ffgpu_ffv1_encode_close(s->enc);
     ffgpu_ffv1_decode_close(s->dec);
     CUDA_POP(s);
     s->enc = NULL;
     s->dec = NULL;
-    for (i = 0; i < GPU_FIFO; i++)
-        av_frame_free(&s->fifo[i]);
+    while ((f = fifo_pop(s)))
+        av_frame_free(&f);
+    av_freep(&s->fifo);
+    s->fifo_cap = s->fifo_head = 0;
     av_packet_free(&s->pending);
+    av_freep(&avctx->stats_out);               /* like ff_ffv1_close, ffv1.c:235 */
     return 0;
 }
 
@@ -459,14 +484,22 @@ static void gpu_flush(AVCodecContext *avctx)
     FFV1GpuContext *s = avctx->priv_data;
     ffgpu_picture_out out;
     AVFrame *f;
+    int ret;
     if (!s->dec)
         return;
-    /* avcodec_flush_buffers: drop what is in flight */
-    ffgpu_ffv1_decode_send_packet(s->dec, NULL, 0, 0, NULL);
-    do {
-        memset(&out, 0, sizeof(out));
-    } while (ffgpu_ffv1_decode_receive_frame(s->dec, &out) != AVERROR_EOF && s->fifo_count &&
-             (f = fifo_pop(s), av_frame_free(&f), 1));
+    /* avcodec_flush_buffers: drop what is in flight.  The library is drained to its EOF so
+     * that it takes packets again afterwards (a flushed handle refuses them until then); the
+     * pictures land in the frames queued for them, which are dropped. */
+    if (!s->eof) {
+        if (!s->draining)
+            ffgpu_ffv1_decode_send_packet(s->dec, NULL, 0, 0, NULL);
+        do {
+            memset(&out, 0, sizeof(out));
+            ret = ffgpu_ffv1_decode_receive_frame(s->dec, &out);
+            if (ret != AVERROR_EOF && ret != AVERROR(EAGAIN) && (f = fifo_pop(s)))
+                av_frame_free(&f);             /* a picture, or one that failed */
+        } while (ret != AVERROR_EOF && ret != AVERROR(EAGAIN) && (ret >= 0 || s->fifo_count));
+    }
     while ((f = fifo_pop(s)))
         av_frame_free(&f);
     av_packet_unref(s->pending);
@@ -521,6 +554,9 @@ AVCodec ff_ffv1_gpu_encoder = {
     .receive_packet = gpu_receive_packet,
     .close          = gpu_close,
     .capabilities   = AV_CODEC_CAP_DELAY,
+    /* gpu_close copes with a half-made context: init needs no clean-up paths of its own
+     * (the reference encoder sets no caps_internal and cleans up by hand, ffv1enc.c:517-928) */
+    .caps_internal  = FF_CODEC_CAP_INIT_CLEANUP,
     .pix_fmts       = (const enum AVPixelFormat[]) {   /* ffv1enc.c:1333-1355 */
         AV_PIX_FMT_YUV420P,   AV_PIX_FMT_YUVA420P,  AV_PIX_FMT_YUVA422P,  AV_PIX_FMT_YUV444P,
         AV_PIX_FMT_YUVA444P,  AV_PIX_FMT_YUV440P,   AV_PIX_FMT_YUV422P,   AV_PIX_FMT_YUV411P,
