@@ -233,12 +233,33 @@ def run_cpu(wl, frames, threads, budget_s, max_frames):
                 enc_fps=n / t_enc, dec_fps=n / t_dec, fps=n / (t_enc + t_dec))
 
 
+def picture_bytes(wl):
+    import cpucodec as cc
+    return sum(bw * rows for bw, rows in cc.plane_geometry(wl["fmt"], wl["w"], wl["h"]))
+
+
+def distinct_pictures(wl, B):
+    """how many different pictures a step cycles through"""
+    return min(8 if picture_bytes(wl) < (64 << 20) else 4, B)
+
+
+def run_config(args, wl, src_desc):
+    """`config` of the JSON line: the workload both arms are quoted on, key for key the same in
+    the GPU arm and in --impl reference (whose bounded sample of it is described in its
+    `cpu_baseline.sample`)"""
+    B = args.batch or wl["batch"]
+    return {"workload": args.workload + ": " + wl["desc"], "frames_per_step_per_gpu": B,
+            "distinct_pictures": distinct_pictures(wl, B), "source": src_desc,
+            "l2": "inputs larger than L2 (%.0f MB per step)" % (B * picture_bytes(wl) / 1e6),
+            "partition": "pictures round-robin over ranks, no collective"}
+
+
 def reference_arm(args, wl, rank, world, real_stdout):
     """--impl reference: rank 0 alone times the reference CPU implementation"""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    frames, src_desc = make_frames(wl, 4, 0, args.source)
+    frames, src_desc = make_frames(wl, distinct_pictures(wl, args.batch or wl["batch"]), 0, args.source)
     which, kind = cpu_codec_kind()
     sample = 8
     res = []
@@ -255,8 +276,7 @@ def reference_arm(args, wl, rank, world, real_stdout):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_t / max(len(res), 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": args.workload + ": " + wl["desc"], "frames_per_step": sample,
-                   "source": src_desc},
+        "config": run_config(args, wl, src_desc), "frames_per_step": sample,
         "encode_fps": tot_frames / sum(r["t_enc"] for r in res),
         "decode_fps": tot_frames / sum(r["t_dec"] for r in res),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
@@ -370,7 +390,7 @@ def main():
     w, h, fmt, opts = wl["w"], wl["h"], wl["fmt"], wl["opts"]
     frame_bytes, planes = F.frame_layout(fmt, w, h)
     B = args.batch or wl["batch"]
-    distinct = min(8 if frame_bytes < (64 << 20) else 4, B)
+    distinct = distinct_pictures(wl, B)
     dec_only = bool(wl.get("decode_only"))
 
     # ---- synthetic input: `distinct` pictures (this rank's share of the stream), cycled ----
@@ -813,10 +833,7 @@ def main():
         "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": 1e3 * dev_time / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": args.workload + ": " + wl["desc"], "frames_per_step_per_gpu": B,
-                   "distinct_pictures": distinct, "source": src_desc,
-                   "l2": "inputs larger than L2 (%.0f MB per step)" % (B * frame_bytes / 1e6),
-                   "partition": "pictures round-robin over ranks, no collective"},
+        "config": run_config(args, wl, src_desc),
         "encode_fps": enc_fps, "decode_fps": dec_fps,
         "pixel_GBps": value * raw_bytes / 1e9,
         "packet_bytes_per_picture": pkt_bytes / B, "raw_bytes_per_picture": raw_bytes,

@@ -24,7 +24,10 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["value"] == d["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
-    assert "workload" in d["config"]
+    # `config` is built by the one function both arms use (bench.run_config): key for key the
+    # GPU arm's, so the driver compares like with like
+    assert set(d["config"]) == {"workload", "frames_per_step_per_gpu", "distinct_pictures", "source", "l2",
+                                "partition"}
 
 
 def test_reference_arm_other_ranks_exit_quietly():
