@@ -51,6 +51,7 @@ struct Enc {
     std::vector<uint32_t> tokens, crc;
     uint8_t *extradata = nullptr;
     int extradata_size = 0, gop = 12, pic = 0;
+    int ps = 3, sar_num = 0, sar_den = 1;       /* per-picture slice header fields, ffv1enc.c:944-949 */
     /* two-pass coding */
     int pass1 = 0, gob_count = 0;
     std::vector<unsigned long long> rc_stat, rc_stat2;
@@ -160,7 +161,8 @@ extern "C" int ffv1emul_encode(void *h, const uint8_t *const planes[4], const in
         pass.rc_stat = e->rc_stat.data();
         pass.rc_stat2 = e->rc_stat2.data();
         pass.ctx_count = e->s.ctx_count[e->s.context_model];
-        int rc = ff_enc_slice_prefix(&e->s, i, &r, keyf, 3, 0, 1, &pre[i], &e->prebytes[(size_t)i * 2048], 2048);
+        int rc = ff_enc_slice_prefix(&e->s, i, &r, keyf, e->ps, e->sar_num, e->sar_den, &pre[i],
+                                     &e->prebytes[(size_t)i * 2048], 2048);
         if (rc < 0) return rc;
         pre[i].byte_off = (uint32_t)i * 2048;
         if (P.ac == FF_AC_GOLOMB)
@@ -222,6 +224,14 @@ extern "C" int ffv1emul_encode(void *h, const uint8_t *const planes[4], const in
     return (int)off;
 }
 
+/* picture structure (3 progressive, 1 / 2 interlaced top / bottom field first) and sample
+ * aspect ratio of the pictures that follow */
+extern "C" void ffv1emul_encoder_frame_props(void *h, int ps, int sar_num, int sar_den)
+{
+    Enc *e = (Enc *)h;
+    e->ps = ps; e->sar_num = sar_num; e->sar_den = sar_den;
+}
+
 extern "C" int ffv1emul_encoder_stats_out(void *h, char *buf, int cap)
 {
     Enc *e = (Enc *)h;
@@ -262,6 +272,7 @@ struct Dec {
     std::vector<uint2> vstate;
     std::vector<int32_t> lines;
     int cur = 0, have_last = 0, damaged = 0;
+    FFDecFrameInfo last_info;
 };
 
 extern "C" void *ffv1emul_decoder_open(int w, int h, const uint8_t *ex, int exsize, int threads, int *err)
@@ -283,6 +294,45 @@ extern "C" void *ffv1emul_decoder_open(int w, int h, const uint8_t *ex, int exsi
 
 extern "C" int ffv1emul_decoder_damaged(void *h) { return ((Dec *)h)->damaged; }
 
+/* what the C ABI reports beside the pictures: output format (NULL until known), stream
+ * parameters, the frame header of a version 0/1 stream, the last picture's properties */
+extern "C" const char *ffv1emul_decoder_pix_fmt(void *h)
+{
+    Dec *d = (Dec *)h;
+    return d->s.pf ? d->s.pf->name : nullptr;
+}
+
+extern "C" void ffv1emul_decoder_info(void *h, int info[8])
+{
+    Dec *d = (Dec *)h;
+    info[0] = d->s.version; info[1] = d->s.micro_version; info[2] = d->s.ac; info[3] = d->s.nh;
+    info[4] = d->s.nv; info[5] = d->s.ec; info[6] = d->s.bits; info[7] = d->s.colorspace;
+}
+
+extern "C" int ffv1emul_decoder_probe(void *h, const uint8_t *pkt, int size)
+{
+    Dec *d = (Dec *)h;
+    if (d->s.pf)
+        return 0;
+    if (d->s.version >= 2)                      /* parameters came with the extradata */
+        return ff_pick_decoder_format(&d->s);
+    std::vector<uint8_t> padded((size_t)size + 64, 0);
+    memcpy(padded.data(), pkt, size);
+    FFDecSlice tmp[1];
+    FFDecFrameInfo info;
+    FFDecHostState hs = d->hs;
+    hs.max_slices = 1;
+    const int r = ff_dec_parse_packet(&d->s, &hs, padded.data(), size, 0, tmp, &info);
+    return r < 0 ? r : 0;
+}
+
+extern "C" void ffv1emul_decoder_frame_props(void *h, int props[5])
+{
+    const FFDecFrameInfo &i = ((Dec *)h)->last_info;
+    props[0] = i.key_frame; props[1] = i.interlaced_frame; props[2] = i.top_field_first;
+    props[3] = i.sar_num; props[4] = i.sar_den;
+}
+
 extern "C" int ffv1emul_decode(void *h, const uint8_t *pkt_in, int size, uint8_t *planes[4], int ls[4],
                                const char **fmt, int *key)
 {
@@ -294,6 +344,7 @@ extern "C" int ffv1emul_decode(void *h, const uint8_t *pkt_in, int size, uint8_t
     d->hs.device_parse = 1;                 /* exercise the device-side header parser too */
     int n = ff_dec_parse_packet(&d->s, &d->hs, pkt.data(), size, 0, work.data(), &info);
     if (n < 0) return n;
+    d->last_info = info;
     if (!d->have_params || info.key_frame) {
         d->sl.resize(d->s.nh * d->s.nv);
         ff_fill_dev_params(&d->s, 0, &d->P, d->sl.data());
