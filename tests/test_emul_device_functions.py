@@ -13,6 +13,18 @@ import synth
 
 pytestmark = pytest.mark.skipif(not cc.available("emul"), reason="tests/emul not built")
 
+# the forms a launch can take: warp-wide loops, the straight-line coders of
+# one-slice-per-warp launches, the encoder's stage B in two halves
+FORMS = [None, "FFV1_EMUL_LONE", "FFV1_EMUL_SPLIT"]
+
+
+def use_form(monkeypatch, form):
+    for f in FORMS[1:]:
+        monkeypatch.delenv(f, raising=False)
+    if form:
+        monkeypatch.setenv(form, "1")
+
+
 FORMATS = ["yuv420p", "yuv410p", "gray", "ya8", "yuva420p", "yuv420p10le", "yuv444p16le", "gray16le",
            "yuva444p10le", "bgr0", "bgra", "gbrp10le", "gbrp16le", "gbrap12le", "rgb48le"]
 OPTIONS = [dict(), dict(slices=4), dict(slices=9, coder=2), dict(slices=4, coder=-2, context=1),
@@ -131,7 +143,9 @@ def test_msb_aligned_sample_depth():
     assert np.array_equal(a[0], b[0])
 
 
-def test_damaged_packets():
+@pytest.mark.parametrize("form", FORMS[:2])
+def test_damaged_packets(form, monkeypatch):
+    use_form(monkeypatch, form)
     w, h = 128, 96
     for fmt in ("yuv420p", "yuv420p10le"):
         enc = cc.Encoder("oracle", w, h, fmt, slices=4, gop_size=1)
@@ -160,7 +174,8 @@ def test_damaged_packets():
                 assert np.array_equal(a, b)
 
 
-def test_wide_slice_header_decodes_like_the_reference():
+@pytest.mark.parametrize("form", FORMS[:2])
+def test_wide_slice_header_decodes_like_the_reference(form, monkeypatch):
     """a slice header naming a rectangle wider than its grid cell (hand-coded with
     tests/ffv1_bits.py): product device functions == reference == oracle"""
     import numpy as np
@@ -168,6 +183,7 @@ def test_wide_slice_header_decodes_like_the_reference():
     import random
     if not cc.available("ref"):
         pytest.skip("oracle/_ref not built")
+    use_form(monkeypatch, form)
     w, h, fmt = 192, 96, "yuv420p"
     enc = cc.Encoder("ref", w, h, fmt, slices=24, coder=-2, level=3, gop_size=1)
     p0 = enc.encode(synth.smooth(fmt, w, h, 0))
@@ -199,13 +215,15 @@ V4_OPTIONS = [dict(slices=4, coder=2), dict(slices=9, coder=-2, context=1), dict
               dict(slices=4, coder=1, gop_size=1)]
 
 
+@pytest.mark.parametrize("form", FORMS)
 @pytest.mark.parametrize("fmt", V4_RGB)
-def test_version4_rgb_matches_the_reference(fmt):
+def test_version4_rgb_matches_the_reference(fmt, form, monkeypatch):
     """FFV1 version 4: per-slice RCT coefficients (choose_rct_params), the longer
     slice header, Golomb-Rice slices closed on the device.  The oracle port does not restate
     version 4; the checker is the compiled reference (oracle/_ref)."""
     if not cc.available("ref"):
         pytest.skip("oracle/_ref not built")
+    use_form(monkeypatch, form)
     w, h = 96, 64
     for kw in V4_OPTIONS:
         kw = dict(kw, level=4, strict=-2)
@@ -234,12 +252,14 @@ def test_version4_rgb_matches_the_reference(fmt):
 
 @pytest.mark.parametrize("fmt", ["yuv420p", "yuv444p10le", "yuv422p10le", "gray", "ya8", "yuva420p",
                                  "yuv420p16le", "yuv444p16le"])
-def test_version4_ycbcr_streams_decode(fmt):
+@pytest.mark.parametrize("form", FORMS[:2])
+def test_version4_ycbcr_streams_decode(fmt, form, monkeypatch):
     """the reference also writes version 4 YCbCr streams (their RCT coefficients come from
     reads outside the planes, so only the decoder can be compared): slice_reset_contexts,
     the plane-context numbering of gray+alpha, coefficients that are parsed and ignored"""
     if not cc.available("ref"):
         pytest.skip("oracle/_ref not built")
+    use_form(monkeypatch, form)
     w, h = 96, 64
     for kw in (dict(slices=4, coder=2), dict(coder=0), dict(slices=9, coder=1, gop_size=1)):
         ref = cc.Encoder("ref", w, h, fmt, level=4, strict=-2, **kw)
@@ -251,13 +271,15 @@ def test_version4_ycbcr_streams_decode(fmt):
                 assert np.array_equal(a, b), (fmt, kw, kind)
 
 
-def test_version4_pcm_slice_decodes_like_the_reference():
+@pytest.mark.parametrize("form", FORMS[:2])
+def test_version4_pcm_slice_decodes_like_the_reference(form, monkeypatch):
     """slice_coding_mode == 1 (raw bits, ffv1dec_template.c:37-47): the reference encoder only
     writes such slices when a packet buffer overflows, so one is hand-coded here"""
     import ffv1_bits as fb
     import random
     if not cc.available("ref"):
         pytest.skip("oracle/_ref not built")
+    use_form(monkeypatch, form)
     w, h = 64, 32
     for fmt, bits, nsym in (("bgr0", 8, 3), ("gbrp10le", 10, 3), ("yuv444p10le", 10, 3)):
         enc = cc.Encoder("ref", w, h, fmt, level=4, strict=-2, slices=4, coder=-2, gop_size=1)
@@ -323,6 +345,34 @@ def test_two_pass_matches_the_reference(fmt):
                 break
             for a, b in zip(want, de.decode(pkt)):
                 assert np.array_equal(a, b), (fmt, kw)
+
+
+@pytest.mark.parametrize("form", FORMS[1:])
+@pytest.mark.parametrize("fmt,kw", [("yuv420p", dict(slices=4, coder=2)), ("bgr0", dict(slices=4, coder=-2, gop_size=1)),
+                                    ("gray", dict(coder=1, gop_size=1, slices=9))])
+def test_second_pass_through_the_other_forms(fmt, kw, form, monkeypatch):
+    """a second pass (sorted transition table, initial states from the extradata instead of
+    128) through the straight-line coders and the two-halves stage B: packets and pictures of
+    the compiled reference"""
+    if not cc.available("ref"):
+        pytest.skip("oracle/_ref not built")
+    w, h = 80, 48
+    frames = [synth.GENERATORS[k](fmt, w, h, i) for i, k in enumerate(("smooth", "testsrc2", "noise", "smooth"))]
+    r1 = cc.Encoder("ref", w, h, fmt, pass1=1, **kw)
+    for f in frames:
+        r1.encode(f)
+    stats = r1.stats_out()
+    use_form(monkeypatch, form)
+    r2 = cc.Encoder("ref", w, h, fmt, pass2=1, stats_in=stats, **kw)
+    e2 = cc.Encoder("emul", w, h, fmt, pass2=1, stats_in=stats, **kw)
+    assert r2.extradata == e2.extradata
+    dr = cc.Decoder("ref", w, h, r2.extradata)
+    de = cc.Decoder("emul", w, h, r2.extradata)
+    for f in frames:
+        pkt = r2.encode(f)
+        assert e2.encode(f) == pkt, (fmt, kw, form)
+        for a, b in zip(dr.decode(pkt), de.decode(pkt)):
+            assert np.array_equal(a, b), (fmt, kw, form)
 
 
 def test_damaged_input_under_the_sanitizers():
