@@ -291,10 +291,25 @@ static int mem_kind(const void *p)
     return a.type == cudaMemoryTypeHost ? MEM_PINNED : MEM_DEVICE;
 }
 
+/* does a picture in caller memory go through the pinned staging of the handle?  Pageable
+ * memory always; bottom-up pictures (negative linesize) in any HOST memory as well, because a
+ * pitched DMA cannot walk backwards.  -1: bottom-up planes in device memory, not supported. */
+static int needs_staging(const void *plane0, const int linesize[4])
+{
+    const int kind = mem_kind(plane0);
+    int bottom_up = 0;
+    for (int k = 0; k < 4; k++)
+        bottom_up |= linesize[k] < 0;
+    if (bottom_up && kind == MEM_DEVICE)
+        return -1;
+    return kind == MEM_PAGEABLE || bottom_up;
+}
+
 struct CopyTask {
     uint8_t *dst;
     const uint8_t *src;
-    size_t dst_pitch, src_pitch, rowbytes;
+    ptrdiff_t dst_pitch, src_pitch;     /* signed: a bottom-up picture has a negative linesize */
+    size_t rowbytes;
     int rows;
 };
 
@@ -315,12 +330,12 @@ static struct {
 
 static void copy_rows(const CopyTask *t)
 {
-    if (t->dst_pitch == t->src_pitch && t->rowbytes == t->dst_pitch) {
+    if (t->dst_pitch == t->src_pitch && t->dst_pitch > 0 && t->rowbytes == (size_t)t->dst_pitch) {
         memcpy(t->dst, t->src, (size_t)t->rows * t->rowbytes);
         return;
     }
     for (int y = 0; y < t->rows; y++)
-        memcpy(t->dst + (size_t)y * t->dst_pitch, t->src + (size_t)y * t->src_pitch, t->rowbytes);
+        memcpy(t->dst + (ptrdiff_t)y * t->dst_pitch, t->src + (ptrdiff_t)y * t->src_pitch, t->rowbytes);
 }
 
 static void *pool_worker(void *)
@@ -380,8 +395,8 @@ static void par_copy(const CopyTask *tasks, int ntasks)
         for (int k = 0; k < parts; k++) {
             CopyTask c = tasks[i];
             const int y0 = (int)((long)tasks[i].rows * k / parts), y1 = (int)((long)tasks[i].rows * (k + 1) / parts);
-            c.dst += (size_t)y0 * c.dst_pitch;
-            c.src += (size_t)y0 * c.src_pitch;
+            c.dst += (ptrdiff_t)y0 * c.dst_pitch;
+            c.src += (ptrdiff_t)y0 * c.src_pitch;
             c.rows = y1 - y0;
             g_pool.chunk[g_pool.nchunks++] = c;
         }
@@ -412,14 +427,16 @@ static int stage_picture(const FFDevParams *P, const FFPixFmt *pf, int w, int h,
     for (int k = 0; k < pf->nplanes; k++) {
         int rb, rows;
         ff_plane_geometry(pf, w, h, k, &rb, &rows);
-        if (!data[k] || linesize[k] < rb)
+        /* a negative linesize (bottom-up picture, e.g. after vflip) is as good as a positive one,
+         * like for the reference's pointer arithmetic (ffv1enc.c:283, ffv1dec.c:141) */
+        if (!data[k] || (linesize[k] < 0 ? -(long)linesize[k] : (long)linesize[k]) < rb)
             return fail(FFGPU_EINVAL, "picture plane %d missing or linesize too small", k);
         if (to_stage) {
-            t[n].dst = stage + P->plane_off[k]; t[n].dst_pitch = (size_t)P->pitch[k];
-            t[n].src = data[k];                 t[n].src_pitch = (size_t)linesize[k];
+            t[n].dst = stage + P->plane_off[k]; t[n].dst_pitch = (ptrdiff_t)P->pitch[k];
+            t[n].src = data[k];                 t[n].src_pitch = (ptrdiff_t)linesize[k];
         } else {
-            t[n].dst = data[k];                 t[n].dst_pitch = (size_t)linesize[k];
-            t[n].src = stage + P->plane_off[k]; t[n].src_pitch = (size_t)P->pitch[k];
+            t[n].dst = data[k];                 t[n].dst_pitch = (ptrdiff_t)linesize[k];
+            t[n].src = stage + P->plane_off[k]; t[n].src_pitch = (ptrdiff_t)P->pitch[k];
         }
         t[n].rowbytes = (size_t)rb;
         t[n].rows = rows;
@@ -1116,7 +1133,10 @@ extern "C" int ffgpu_ffv1_encode_send_frame(ffgpu_encoder *e, const ffgpu_pictur
     }
     if (j->n == 0)
         trace_mark(e->up_stream, "enc h2d", (int)(j - e->jobs), 0);
-    if (mem_kind(pic->data[0]) == MEM_PAGEABLE) {
+    const int staged = needs_staging(pic->data[0], pic->linesize);
+    if (staged < 0)
+        return fail(FFGPU_EINVAL, "bottom-up pictures (negative linesize) in device memory are not supported");
+    if (staged) {
         /* an ordinary AVFrame: host memcpy into pinned staging, one linear DMA from there */
         uint8_t *data[4], *st;
         /* the first pageable picture creates the staging of EVERY launch group, so that no
@@ -2055,7 +2075,10 @@ static int dec_add_packet(ffgpu_decoder *d, DecJob *j, const uint8_t *pkt, size_
     if (dst) {
         m->dst = *dst;
         m->has_dst = 1;
-        m->staged = mem_kind(dst->data[0]) == MEM_PAGEABLE;
+        const int staged = needs_staging(dst->data[0], dst->linesize);
+        if (staged < 0)
+            return fail(FFGPU_EINVAL, "bottom-up pictures (negative linesize) in device memory are not supported");
+        m->staged = staged;
         /* the first pageable destination creates the staging of every launch group */
         for (int g = 0; g < d->depth && m->staged && !j->h_stage; g++)
             if (!d->jobs[g].h_stage)

@@ -28,17 +28,20 @@ cp "$REPO/integration/ffv1_gpu.c" "$WORK/src/libavcodec/ffv1_gpu.c"
 cp "$REPO/include/ffgpu.h" "$WORK/src/libavcodec/ffgpu.h"
 mkdir -p "$WORK/build"
 cd "$WORK/build"
-if [ ! -f ffbuild/config.mak ]; then
+FILTERS=testsrc2,testsrc,mandelbrot,scale,format,null,noise,nullsrc,geq,color,trim,select,vflip
+# configure again when the feature list above changed (the scratch tree outlives a run)
+if [ ! -f ffbuild/config.mak ] || [ "$(cat .filters 2>/dev/null)" != "$FILTERS" ]; then
     "$WORK/src/configure" --disable-asm --disable-doc --disable-everything --disable-autodetect \
         --enable-encoder=ffv1,ffv1_gpu,rawvideo,wrapped_avframe \
         --enable-decoder=ffv1,ffv1_gpu,rawvideo,wrapped_avframe \
         --enable-muxer=nut,avi,matroska,framemd5,framecrc,md5,null,rawvideo \
         --enable-demuxer=nut,avi,matroska,rawvideo \
         --enable-protocol=file,pipe,md5 --enable-indev=lavfi \
-        --enable-filter=testsrc2,testsrc,mandelbrot,scale,format,null,noise,nullsrc,geq,color,trim,select \
+        --enable-filter=$FILTERS \
         --disable-ffplay --disable-ffprobe \
         --extra-ldflags="-L$REPO/ffmpeg_ffv2_b200" --extra-libs="-lffgpu -lpthread -ldl -lrt" \
         > configure.log 2>&1 || { tail -20 configure.log; tail -30 ffbuild/config.log; exit 1; }
+    echo "$FILTERS" > .filters
 fi
 make -j"$(nproc)" ffmpeg > make.log 2>&1 || { tail -30 make.log; exit 1; }
 cp ffmpeg "$OUT/ffmpeg"

@@ -37,7 +37,7 @@ static void upload(const FFDevParams &P, const FFPixFmt *pf, int w, int h,
         int rb, rows;
         ff_plane_geometry(pf, w, h, k, &rb, &rows);
         for (int y = 0; y < rows; y++)
-            memcpy(frame + P.plane_off[k] + (size_t)y * P.pitch[k], planes[k] + (size_t)y * ls[k], rb);
+            memcpy(frame + P.plane_off[k] + (size_t)y * P.pitch[k], planes[k] + (ptrdiff_t)y * ls[k], rb);
     }
 }
 

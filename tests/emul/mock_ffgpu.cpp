@@ -318,7 +318,7 @@ static void copy_out(const ffgpu_picture_out *dst, const char *fmt, int w, int h
     for (int k = 0; k < np; k++) {
         ffv1emul_plane_geometry(fmt, w, h, k, &bw, &rows);
         for (int y = 0; y < rows; y++)
-            memcpy(dst->data[k] + (size_t)y * dst->linesize[k], planes[k] + (size_t)y * ls[k], bw);
+            memcpy(dst->data[k] + (ptrdiff_t)y * dst->linesize[k], planes[k] + (ptrdiff_t)y * ls[k], bw);
     }
 }
 

@@ -130,6 +130,16 @@ def test_more_pictures_in_flight_than_the_ring_starts_with(tmp_path, mock_dir):
     assert len(want) == n and got == want
 
 
+def test_bottom_up_pictures_from_a_filter(mock_dir):
+    """`-vf vflip` hands the encoder AVFrames with a negative linesize: the glue passes the
+    planes of its own reference on as they are"""
+    n, opts = 7, ["-slices", "4", "-g", "1"]
+    common = src(128, 96, n, "yuv420p10le") + ["-vf", "vflip"]
+    cpu = md5_lines(ffmpeg(mock_dir, *common, "-c:v", "ffv1", *opts, "-f", "framemd5", "-"))
+    gpu = md5_lines(ffmpeg(mock_dir, *common, "-c:v", "ffv1_gpu", *opts, "-f", "framemd5", "-"))
+    assert len(cpu) == n and gpu == cpu
+
+
 @pytest.mark.parametrize("level", ["0", "1"])
 def test_streams_that_announce_their_format_in_the_first_key_frame(tmp_path, mock_dir, level):
     """version 0 / 1: no extradata, the glue probes the first packet before it allocates"""

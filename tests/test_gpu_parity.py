@@ -746,3 +746,62 @@ def test_two_pass_matches_the_reference(fmt):
             got = dec.decode(pkt, fmt_hint=dref.pix_fmt)
             for a, b in zip(want, got):
                 assert np.array_equal(a, b), (fmt, kw)
+
+
+def test_bottom_up_pictures():
+    """AVFrames with a negative linesize (what `-vf vflip` hands an encoder): the reference
+    walks them by pointer arithmetic (ffv1enc.c:283), the library stages them row by row --
+    pageable and pinned host memory alike -- and the decoder writes into such a picture"""
+    import torch
+    from ffmpeg_ffv2_b200.codec import PictureOut
+    F = gpu()
+    w, h = 176, 98
+    for fmt, kw in (("yuv420p10le", dict(slices=12, gop_size=1)), ("bgr0", dict(coder=1, gop_size=1)),
+                    ("yuv420p", dict())):
+        ref = cc.Encoder("oracle", w, h, fmt, **kw)
+        enc = F.FFV1Encoder(w, h, fmt, **kw)
+        dec = F.FFV1Decoder(w, h, enc.extradata)
+        for i, pinned in enumerate((False, True, False)):
+            src = synth.testsrc2_like(fmt, w, h, i)
+            want = ref.encode(src)
+            # the same picture stored bottom-up: row 0 is the LAST row in memory
+            if pinned:
+                hold = [torch.from_numpy(np.ascontiguousarray(a[::-1])).pin_memory() for a in src]
+                stored = [t.numpy() for t in hold]
+            else:
+                stored = [np.ascontiguousarray(a[::-1]) for a in src]
+            views = [a[::-1] for a in stored]
+            assert all(v.strides[0] < 0 for v in views)
+            assert enc.encode(views) == want, (fmt, i)
+            # decoder: destination planes given up front, bottom-up as well
+            dst_store = [np.zeros_like(a) for a in src]
+            out = PictureOut()
+            for k, a in enumerate(dst_store):
+                v = a[::-1]
+                out.data[k] = v.ctypes.data
+                out.linesize[k] = v.strides[0]
+            assert dec.send_packet(want, pts=i, dst=(out, dst_store))
+            assert dec.send_packet(None)
+            got = dec.receive_frame()
+            assert got not in (None, F.EOF)
+            assert dec.receive_frame() == F.EOF
+            for a, b in zip(dst_store, src):
+                assert np.array_equal(a[::-1], b), (fmt, i)
+    # the same through the reference's own ffmpeg: `-vf vflip` in front of the encoder
+    ROOT = os.path.dirname(HERE)
+    ffmpeg = os.path.join(ROOT, "oracle", "_ref", "ffmpeg")
+    if os.path.exists(ffmpeg):
+        import subprocess
+        env = dict(os.environ)
+        env["LD_LIBRARY_PATH"] = os.path.join(ROOT, "ffmpeg_ffv2_b200") + ":" + env.get("LD_LIBRARY_PATH", "")
+        out = {}
+        for codec in ("ffv1", "ffv1_gpu"):
+            r = subprocess.run([ffmpeg, "-hide_banner", "-loglevel", "error", "-nostdin", "-f", "lavfi", "-i",
+                                "testsrc2=s=640x360:r=25", "-frames:v", "9", "-pix_fmt", "yuv420p10le", "-vf", "vflip",
+                                "-c:v", codec, "-slices", "12", "-g", "1", "-f", "framemd5", "-"],
+                               capture_output=True, env=env, timeout=150)
+            if b"No such filter" in r.stderr:
+                pytest.skip("this build of oracle/_ref/ffmpeg has no vflip filter")
+            assert r.returncode == 0, r.stderr.decode(errors="replace")[-2000:]
+            out[codec] = [l for l in r.stdout.decode().splitlines() if l and not l.startswith("#")]
+        assert len(out["ffv1"]) == 9 and out["ffv1_gpu"] == out["ffv1"]

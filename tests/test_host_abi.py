@@ -133,3 +133,20 @@ def test_e2e_driver_builds_and_links_against_the_abi():
     assert hasattr(lib, "ffgpu_e2e_run") and hasattr(lib, "ffgpu_e2e_free_packets")
     src = open(os.path.join(os.path.dirname(__file__), "..", "tools", "e2e_driver.c")).read()
     assert "oracle" not in src and "ffv1_" not in src.replace("ffgpu_ffv1_", "")
+
+
+def test_staging_copies_of_the_library_without_a_gpu():
+    """tests/emul/host_staging_test.cu includes ffgpu_api.cu and calls its static host
+    functions: pictures between caller planes and the pinned staging layout, top-down and
+    bottom-up (negative linesize), through the copy-thread pool and inline"""
+    import shutil
+    import subprocess
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul")
+    if not (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
+        pytest.skip("nvcc not available")
+    b = subprocess.run(["make", "-C", here, "host_staging_test"], capture_output=True, text=True)
+    assert b.returncode == 0, b.stderr[-2000:]
+    for threads in ("1", "5"):
+        r = subprocess.run([os.path.join(here, "host_staging_test")], capture_output=True, text=True, timeout=300,
+                           env=dict(os.environ, FFGPU_COPY_THREADS=threads))
+        assert r.returncode == 0 and "host copy ok" in r.stdout, (threads, r.stdout[-500:], r.stderr[-1000:])
