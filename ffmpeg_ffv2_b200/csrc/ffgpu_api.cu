@@ -1127,10 +1127,10 @@ extern "C" int ffgpu_ffv1_encode_send_frame(ffgpu_encoder *e, const ffgpu_pictur
     j = &e->jobs[e->fill];                         /* a full prefix cache launches the filling group */
     if (j->state == JOB_RUNNING || j->state == JOB_DRAINING)
         return FFGPU_EAGAIN;
-    if (j->state == JOB_FREE) {
-        j->state = JOB_FILLING;
+    /* a free group becomes the filling one only when its first picture is in: a failure on
+     * the way (staging allocation, a bad plane) leaves the handle as it was */
+    if (j->state == JOB_FREE)
         j->n = 0;
-    }
     if (j->n == 0)
         trace_mark(e->up_stream, "enc h2d", (int)(j - e->jobs), 0);
     const int staged = needs_staging(pic->data[0], pic->linesize);
@@ -1154,6 +1154,7 @@ extern "C" int ffgpu_ffv1_encode_send_frame(ffgpu_encoder *e, const ffgpu_pictur
     } else if ((r = upload_picture(&e->P, e->s.pf, e->s.width, e->s.height, pic,
                                    j->d_frames + (size_t)j->n * e->P.frame_bytes, e->up_stream)) < 0)
         return r;
+    j->state = JOB_FILLING;
     j->h_frame_set[j->n] = (uint8_t)set;
     j->h_frame_key[j->n] = (uint8_t)key;
     e->gob_count += key;

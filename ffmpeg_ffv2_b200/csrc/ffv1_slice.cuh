@@ -25,8 +25,8 @@
 #define FF_TOKEN_CTX_BITS 15
 #define FF_TOKEN_CTX_MASK 0x7FFF
 
-#if !defined(__CUDACC__)
-typedef struct uint2 { uint32_t x, y; } uint2;    /* CPU emulation build only */
+#if !defined(__CUDACC__) && !defined(__VECTOR_TYPES_H__)
+typedef struct uint2 { uint32_t x, y; } uint2;    /* CPU emulation builds without the CUDA headers */
 #endif
 
 /* ff_log2_run[41], libavcodec/bitstream.c:39-46: 0,0,0,0,1,1,1,1,2,2,2,2,3,3,3,3,

@@ -25,7 +25,8 @@ SOURCES = {
 
 def ffmpeg(*args, stdin=None):
     env = dict(os.environ)
-    env["LD_LIBRARY_PATH"] = os.path.join(ROOT, "ffmpeg_ffv2_b200") + ":" + env.get("LD_LIBRARY_PATH", "")
+    import ffmpeg_ffv2_b200 as F
+    env["LD_LIBRARY_PATH"] = os.path.dirname(F.lib_path()) + ":" + env.get("LD_LIBRARY_PATH", "")
     r = subprocess.run([FFMPEG, "-hide_banner", "-loglevel", "error", "-nostdin"] + list(args),
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=150)
     assert r.returncode == 0, r.stderr.decode(errors="replace")[-2000:]

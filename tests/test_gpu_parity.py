@@ -765,7 +765,7 @@ def test_bottom_up_pictures():
             src = synth.testsrc2_like(fmt, w, h, i)
             want = ref.encode(src)
             # the same picture stored bottom-up: row 0 is the LAST row in memory
-            if pinned:
+            if pinned and torch.cuda.is_available():
                 hold = [torch.from_numpy(np.ascontiguousarray(a[::-1])).pin_memory() for a in src]
                 stored = [t.numpy() for t in hold]
             else:
@@ -793,7 +793,7 @@ def test_bottom_up_pictures():
     if os.path.exists(ffmpeg):
         import subprocess
         env = dict(os.environ)
-        env["LD_LIBRARY_PATH"] = os.path.join(ROOT, "ffmpeg_ffv2_b200") + ":" + env.get("LD_LIBRARY_PATH", "")
+        env["LD_LIBRARY_PATH"] = os.path.dirname(F.lib_path()) + ":" + env.get("LD_LIBRARY_PATH", "")
         out = {}
         for codec in ("ffv1", "ffv1_gpu"):
             r = subprocess.run([ffmpeg, "-hide_banner", "-loglevel", "error", "-nostdin", "-f", "lavfi", "-i",

@@ -1,0 +1,110 @@
+"""The HOST side of libffgpu.so without a GPU.
+
+tests/emul/cpu/libffgpu.so is the unmodified csrc/ffgpu_api.cu (handles, launch groups,
+routing over several devices, staging, packet arenas, damage bookkeeping, error paths)
+compiled as C++ over a stand-in CUDA runtime (tests/emul/fake_cuda.cpp: host memory, no
+asynchrony) and CPU launchers (tests/emul/fake_kernels.cpp: the product's own
+__host__ __device__ slice functions, one loop iteration per work item, the coder form chosen
+from the launch shape like the real launchers).  It is test infrastructure: only this file
+loads it (through FFGPU_LIB, in child processes); the product has no CPU path.
+
+With it the `-m gpu` tests themselves -- written against the public C ABI -- run here: what
+they then check is everything in the library except the CUDA kernels' own wrappers, which
+only the B200 run covers."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CPU_DIR = os.path.join(HERE, "emul", "cpu")
+CPU_LIB = os.path.join(CPU_DIR, "libffgpu.so")
+
+
+@pytest.fixture(scope="module")
+def cpu_env():
+    if not os.path.isdir("/usr/local/cuda/include"):
+        pytest.skip("CUDA headers not available")
+    r = subprocess.run(["make", "-C", os.path.join(HERE, "emul"), "cpu/libffgpu.so"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    env = dict(os.environ)
+    env.update(FFGPU_HOST_PIPELINE_RUN="1", FFGPU_LIB=CPU_LIB, FAKE_CUDA_DEVICES="2",
+               LD_LIBRARY_PATH=CPU_DIR + ":" + env.get("LD_LIBRARY_PATH", ""))
+    return env
+
+
+def test_the_gpu_tests_through_the_host_pipeline(cpu_env):
+    """every `-m gpu` test that fits a CPU (no 4K/8K pictures, no torch.cuda tensors): parity
+    with the oracle through send/receive and the synchronous calls, every coder form, two
+    "devices" behind one routing handle, two-pass, version 4, damaged packets, wide slice
+    headers, prefix-cache overflow, incompressible pictures that outgrow the buffers,
+    bottom-up pictures, the libavcodec glue under the vtable harness and inside the
+    reference's ffmpeg (defaults with carried states, two-pass logs)"""
+    select = ("not full_size and not resident and not C2 and not C3 and not C4 and not two_gpus_option")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_gpu_parity.py"),
+                        os.path.join(HERE, "test_ffmpeg_dropin.py"), "-m", "gpu", "-q", "-n", "4", "-k", select,
+                        "-p", "no:cacheprovider"],
+                       capture_output=True, text=True, env=cpu_env, timeout=1500, cwd=ROOT)
+    tail = r.stdout[-4000:] + r.stderr[-2000:]
+    assert r.returncode == 0, tail
+    assert " passed" in r.stdout and "failed" not in r.stdout, tail
+
+
+ALLOC_FAILURES = textwrap.dedent("""
+    import ctypes as C, os, sys
+    sys.path.insert(0, %(root)r); sys.path.insert(0, %(tests)r)
+    import numpy as np
+    import ffmpeg_ffv2_b200 as F, cpucodec as cc, synth
+    lib = F.lib()
+    live = lib.fake_cuda_live_blocks; live.restype = C.c_long
+    reset = lib.fake_cuda_reset_alloc_counter
+    w, h, fmt = 96, 64, "yuv420p10le"
+    kw = dict(slices=4, gop_size=1, max_batch=2, pipeline_depth=2)
+    src = synth.testsrc2_like(fmt, w, h, 0)
+    want = cc.Encoder("oracle", w, h, fmt, slices=4, gop_size=1).encode(src)
+    assert live() == 0
+    failed = ok = 0
+    for k in range(1, 400):
+        enc = F.FFV1Encoder(w, h, fmt, **kw)
+        dec = F.FFV1Decoder(w, h, enc.extradata, max_batch=2, pipeline_depth=2)
+        os.environ["FAKE_CUDA_FAIL_ALLOC"] = str(k); reset()
+        hit = False
+        try:
+            pkt = enc.encode(src)
+        except F.FFGpuError as e:
+            assert e.code in (F.EXTERNAL, -12), e
+            hit = True
+            # a failure while the device side is being created releases all of it; later ones
+            # (the staging of the first pageable picture) leave a working handle
+            assert live() == 0 or enc.launches == 0 and k > 20, ("device memory kept after a failed start", k, live())
+        if not hit:
+            try:
+                out = dec.decode(want)
+            except F.FFGpuError as e:
+                assert e.code in (F.EXTERNAL, -12), e
+                hit = True
+        os.environ["FAKE_CUDA_FAIL_ALLOC"] = "0"
+        # the next call starts over on the same handles
+        assert enc.encode(src) == want, k
+        out = dec.decode(want)
+        assert all(np.array_equal(a, b) for a, b in zip(out, src)), k
+        enc.close(); dec.close()
+        assert live() == 0, ("leak after close", k, live())
+        failed += hit; ok += not hit
+        if not hit:
+            break
+    assert failed >= 20 and ok == 1, (failed, ok)
+    print("alloc failures ok", failed)
+""")
+
+
+def test_a_failed_allocation_leaves_nothing_behind(cpu_env):
+    """the k-th device or pinned allocation of a starting handle fails, for every k: the call
+    reports the CUDA error, nothing stays allocated, the NEXT call on the same handle starts
+    over and succeeds, and close() returns every block (the stand-in runtime counts them)"""
+    r = subprocess.run([sys.executable, "-c", ALLOC_FAILURES % dict(root=ROOT, tests=HERE)],
+                       capture_output=True, text=True, env=cpu_env, timeout=600)
+    assert r.returncode == 0 and "alloc failures ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
