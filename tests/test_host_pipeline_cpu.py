@@ -108,3 +108,33 @@ def test_a_failed_allocation_leaves_nothing_behind(cpu_env):
     r = subprocess.run([sys.executable, "-c", ALLOC_FAILURES % dict(root=ROOT, tests=HERE)],
                        capture_output=True, text=True, env=cpu_env, timeout=600)
     assert r.returncode == 0 and "alloc failures ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_the_host_pipeline_under_the_sanitizers(cpu_env):
+    """the same library built with -fsanitize=address,undefined: the stand-in runtime hands out
+    ordinary heap blocks, so every "device" array (token and bitstream arenas, line scratch,
+    state rows, packet arenas, result tables) has red zones, and the device functions as well
+    as the host code around them are checked for out-of-bounds accesses and undefined
+    behaviour on damaged, incompressible, wide-header and routed streams"""
+    emul = os.path.join(HERE, "emul")
+    r = subprocess.run(["make", "-C", emul, "cpu-asan/libffgpu.so"], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("sanitizer build not available: " + r.stderr[-300:])
+    libs = [subprocess.run(["gcc", "-print-file-name=" + n], capture_output=True, text=True).stdout.strip()
+            for n in ("libasan.so", "libubsan.so")]
+    if not all(os.path.isabs(p) and os.path.exists(p) for p in libs):
+        pytest.skip("sanitizer runtimes not found")
+    env = dict(cpu_env)
+    d = os.path.join(emul, "cpu-asan")
+    env.update(FFGPU_LIB=os.path.join(d, "libffgpu.so"), LD_PRELOAD=" ".join(libs),
+               ASAN_OPTIONS="detect_leaks=0:abort_on_error=0",
+               LD_LIBRARY_PATH=d + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    select = ("every_form or damaged or wider or prefix_sets or incompressible or several_gpus or pipelined "
+              "or bottom_up or version4_ycbcr or (version4_rgb and (bgra or gbrp16le)) or "
+              "((encoder_packets or decoder_pictures) and (yuv420p10le or ya8 or rgb48le or yuva420p))")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_gpu_parity.py"), "-m", "gpu", "-q",
+                        "-n", "4", "-k", select, "-p", "no:cacheprovider"],
+                       capture_output=True, text=True, env=env, timeout=1500, cwd=ROOT)
+    tail = r.stdout[-4000:] + r.stderr[-3000:]
+    assert r.returncode == 0, tail
+    assert " passed" in r.stdout and "failed" not in r.stdout and "Sanitizer" not in tail, tail
