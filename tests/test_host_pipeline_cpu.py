@@ -138,3 +138,23 @@ def test_the_host_pipeline_under_the_sanitizers(cpu_env):
     tail = r.stdout[-4000:] + r.stderr[-3000:]
     assert r.returncode == 0, tail
     assert " passed" in r.stdout and "failed" not in r.stdout and "Sanitizer" not in tail, tail
+
+
+def test_damaged_streams_through_the_public_api_under_the_sanitizers(cpu_env):
+    """tests/emul/api_fuzz.py: mutated packets and extradata into decode_frame, send_packet /
+    receive_frame and a routing handle over two stand-in devices, sanitizer build"""
+    emul = os.path.join(HERE, "emul")
+    r = subprocess.run(["make", "-C", emul, "cpu-asan/libffgpu.so"], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("sanitizer build not available: " + r.stderr[-300:])
+    libs = [subprocess.run(["gcc", "-print-file-name=" + n], capture_output=True, text=True).stdout.strip()
+            for n in ("libasan.so", "libubsan.so")]
+    if not all(os.path.isabs(p) and os.path.exists(p) for p in libs):
+        pytest.skip("sanitizer runtimes not found")
+    env = dict(cpu_env)
+    env.update(FFGPU_LIB=os.path.join(emul, "cpu-asan", "libffgpu.so"), LD_PRELOAD=" ".join(libs),
+               ASAN_OPTIONS="detect_leaks=0:abort_on_error=0")
+    for seed in ("1", "9"):
+        r = subprocess.run([sys.executable, os.path.join(emul, "api_fuzz.py"), seed, "40"],
+                           capture_output=True, text=True, env=env, timeout=900)
+        assert r.returncode == 0 and "api fuzz ok" in r.stdout, (seed, r.stdout[-1000:], r.stderr[-3000:])
