@@ -158,3 +158,21 @@ def test_damaged_streams_through_the_public_api_under_the_sanitizers(cpu_env):
         r = subprocess.run([sys.executable, os.path.join(emul, "api_fuzz.py"), seed, "40"],
                            capture_output=True, text=True, env=env, timeout=900)
         assert r.returncode == 0 and "api fuzz ok" in r.stdout, (seed, r.stdout[-1000:], r.stderr[-3000:])
+
+
+def test_two_caller_threads_under_the_thread_sanitizer():
+    """tests/emul/tsan_e2e.c: bench.py's C host loop (an encoder thread and a decoder thread on
+    the public C ABI, tools/e2e_driver.c) over the host-pipeline sources built with
+    -fsanitize=thread: routing handles over two stand-in devices, pageable pictures through
+    the shared copy-thread pool; 64 pictures must come back identical and race-free"""
+    emul = os.path.join(HERE, "emul")
+    if not os.path.isdir("/usr/local/cuda/include"):
+        pytest.skip("CUDA headers not available")
+    b = subprocess.run(["make", "-C", emul, "tsan_e2e"], capture_output=True, text=True)
+    if b.returncode != 0:
+        pytest.skip("thread sanitizer build not available: " + b.stderr[-300:])
+    r = subprocess.run([os.path.join(emul, "tsan_e2e")], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, FAKE_CUDA_DEVICES="2", FFGPU_COPY_THREADS="4"))
+    out = r.stdout + r.stderr
+    assert r.returncode == 0 and "decoded=64" in out and "mismatching planes: 0" in out, out[-3000:]
+    assert "ThreadSanitizer" not in out, out[-3000:]
