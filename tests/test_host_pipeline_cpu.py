@@ -176,3 +176,115 @@ def test_two_caller_threads_under_the_thread_sanitizer():
     out = r.stdout + r.stderr
     assert r.returncode == 0 and "decoded=64" in out and "mismatching planes: 0" in out, out[-3000:]
     assert "ThreadSanitizer" not in out, out[-3000:]
+
+
+DEVICE_BATCHES = textwrap.dedent("""
+    import ctypes as C, sys
+    sys.path.insert(0, %(root)r); sys.path.insert(0, %(tests)r)
+    import numpy as np
+    import ffmpeg_ffv2_b200 as F, cpucodec as cc, synth
+    lib = F.lib()
+    lib.cudaMalloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    lib.cudaFree.argtypes = [C.c_void_p]
+    def dev_alloc(n):
+        p = C.c_void_p()
+        assert lib.cudaMalloc(C.byref(p), n) == 0
+        return p.value
+    w, h, fmt = 320, 180, "yuv420p10le"
+    kw = dict(slices=20, gop_size=1)
+    n = 5
+    frame_bytes, planes = F.frame_layout(fmt, w, h)
+    host = np.zeros((n, frame_bytes), np.uint8)
+    srcs = [synth.testsrc2_like(fmt, w, h, i) for i in range(n)]
+    for i, src in enumerate(srcs):
+        for (off, pitch, rows, rb), a in zip(planes, src):
+            host[i, off:off + pitch * rows].reshape(rows, pitch)[:, :rb] = a
+    # --- ffgpu_ffv1_encode_device / _device_fetch / ffgpu_ffv1_decode_device / _device_status
+    d_in = dev_alloc(host.nbytes)
+    C.memmove(d_in, host.ctypes.data, host.nbytes)
+    enc = F.FFV1Encoder(w, h, fmt, max_batch=8, **kw)
+    enc.encode_device(d_in, n)
+    ref = cc.Encoder("oracle", w, h, fmt, **kw)
+    want = [ref.encode(s) for s in srcs]
+    pkts = [enc.device_fetch(i) for i in range(n)]
+    assert pkts == want
+    dec = F.FFV1Decoder(w, h, enc.extradata, max_batch=8)
+    d_out = dev_alloc(host.nbytes)
+    dec.decode_device(pkts, d_out)
+    assert dec.device_status() == [0] * n
+    back = np.zeros_like(host)
+    C.memmove(back.ctypes.data, d_out, host.nbytes)
+    for i in range(n):
+        for (off, pitch, rows, rb), a in zip(planes, srcs[i]):
+            assert np.array_equal(back[i, off:off + pitch * rows].reshape(rows, pitch)[:, :rb], a)
+    # a damaged picture in the batch is reported, the others are clean
+    bad = bytearray(pkts[2]); bad[len(bad) // 2] ^= 0x40
+    dec.decode_device(pkts[:2] + [bytes(bad)] + pkts[3:], d_out)
+    st = dec.device_status()
+    assert st[2] >= 1 and st[:2] == [0, 0] and st[3:] == [0, 0], st
+    # more pictures than the handle was opened for
+    try:
+        dec.decode_device(pkts * 3, d_out)
+        raise SystemExit("oversized batch accepted")
+    except F.FFGpuError as e:
+        assert e.code == F.EINVAL
+    # --- device pointers in ffgpu_picture / ffgpu_picture_out (AV_PIX_FMT_CUDA frames), own pitch
+    enc2 = F.FFV1Encoder(w, h, fmt, max_batch=2, pipeline_depth=2, **kw)
+    dec2 = F.FFV1Decoder(w, h, enc2.extradata, max_batch=2, pipeline_depth=2)
+    got = []
+    for i, src in enumerate(srcs):
+        pic = F.codec.Picture()
+        for k, a in enumerate(src):
+            padded = np.ascontiguousarray(np.pad(a, ((0, 0), (0, 64))))
+            p = dev_alloc(padded.nbytes)
+            C.memmove(p, padded.ctypes.data, padded.nbytes)
+            pic.data[k] = p
+            pic.linesize[k] = padded.strides[0]
+        pic.sar_num, pic.sar_den, pic.pts = 0, 1, i
+        while True:
+            r = lib.ffgpu_ffv1_encode_send_frame(enc2.h, C.byref(pic))
+            if r == 0:
+                break
+            assert r == F.EAGAIN, r
+            got.append(enc2.receive_packet()[0])
+    enc2.send_frame(None)
+    while True:
+        r = enc2.receive_packet()
+        if r == F.EOF:
+            break
+        if r is not None:
+            got.append(r[0])
+    assert got == want
+    outs = []
+    for i, p in enumerate(want):
+        po = F.codec.PictureOut()
+        shapes = []
+        for k, a in enumerate(srcs[i]):
+            pitch = a.shape[1] + 48
+            ptr = dev_alloc(pitch * a.shape[0])
+            po.data[k] = ptr
+            po.linesize[k] = pitch
+            shapes.append((ptr, pitch, a.shape))
+        outs.append(shapes)
+        while not dec2.send_packet(p, pts=i, dst=(po, None)):
+            assert dec2.receive_frame() not in (None, F.EOF)
+    dec2.send_packet(None)
+    while dec2.receive_frame() != F.EOF:
+        pass
+    for i, shapes in enumerate(outs):
+        for (ptr, pitch, shape), a in zip(shapes, srcs[i]):
+            buf = np.zeros((shape[0], pitch), np.uint8)
+            C.memmove(buf.ctypes.data, ptr, buf.nbytes)
+            assert np.array_equal(buf[:, :shape[1]], a), i
+    print("device batches ok")
+""")
+
+
+def test_device_resident_batches_and_device_pointer_planes(cpu_env):
+    """the entry points for pictures that stay in device memory (encode_device, device_fetch,
+    decode_device, decode_device_status incl. a damaged picture and an oversized batch) and
+    device pointers in ffgpu_picture / ffgpu_picture_out with a pitch of their own, on
+    "device" memory of the stand-in runtime"""
+    r = subprocess.run([sys.executable, "-c", DEVICE_BATCHES % dict(root=ROOT, tests=HERE)],
+                       capture_output=True, text=True, env=cpu_env, timeout=600)
+    assert r.returncode == 0 and "device batches ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
