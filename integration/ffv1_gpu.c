@@ -31,6 +31,7 @@
 #if CONFIG_CUDA
 #include "libavutil/hwcontext.h"
 #include "libavutil/hwcontext_cuda.h"
+#include "hwaccel.h"
 #define CUDA_PUSH(s) do { if ((s)->cu_ctx) ffgpu_cuda_push_context((s)->cu_ctx); } while (0)
 #define CUDA_POP(s)  do { if ((s)->cu_ctx) ffgpu_cuda_pop_context(); } while (0)
 #else
@@ -62,7 +63,9 @@ typedef struct FFV1GpuContext {
     int fifo_head, fifo_count, fifo_cap;
     AVPacket *pending;         /* decoder: a packet the library could not take yet */
     int draining, eof;
-    void *cu_ctx;              /* AV_PIX_FMT_CUDA input: the hw device's CUcontext, else NULL */
+    void *cu_ctx;              /* AV_PIX_FMT_CUDA frames in or out: the hw device's CUcontext, else NULL */
+    int negotiated;            /* decoder: the output format has been offered to the caller */
+    int cuda_out;              /* decoder: pictures are written into AV_PIX_FMT_CUDA frames */
 } FFV1GpuContext;
 
 /* room for one more entry; the only way fifo_push can fail, so callers reserve BEFORE they
@@ -309,6 +312,58 @@ static av_cold int gpu_close(AVCodecContext *avctx)
     return 0;
 }
 
+/* Output format of the decoder.  Ordinarily the stream's own format.  In a build with the
+ * CUDA hw context, and when the caller supplied a CUDA device or frames context, the decoder
+ * also offers AV_PIX_FMT_CUDA through get_format (the way libavcodec/cuviddec.c:845-915
+ * does): the pictures then STAY on the GPU -- ff_get_buffer hands out frames of an
+ * AVHWFramesContext whose planes are device pointers, and the library downloads nothing
+ * (hwupload-free chains such as ffv1_gpu -> scale_cuda -> an NVENC encoder).
+ * hwcontext_cuda.c knows the layouts of yuv420p, yuv444p, yuv444p16 and 0rgb32/0bgr32; any
+ * other stream format falls back to frames in host memory. */
+static int gpu_output_format(AVCodecContext *avctx, enum AVPixelFormat sw_fmt)
+{
+    FFV1GpuContext *s = avctx->priv_data;
+#if CONFIG_CUDA
+    if (!s->negotiated && (avctx->hw_device_ctx || avctx->hw_frames_ctx)) {
+        const enum AVPixelFormat fmts[3] = { AV_PIX_FMT_CUDA, sw_fmt, AV_PIX_FMT_NONE };
+        int ret;
+        avctx->sw_pix_fmt = sw_fmt;
+        if ((ret = ff_get_format(avctx, fmts)) < 0)
+            return ret;
+        if (ret == AV_PIX_FMT_CUDA) {
+            AVHWFramesContext *frames;
+            if (!avctx->hw_frames_ctx) {
+                if (!(avctx->hw_frames_ctx = av_hwframe_ctx_alloc(avctx->hw_device_ctx)))
+                    return AVERROR(ENOMEM);
+                frames = (AVHWFramesContext *)avctx->hw_frames_ctx->data;
+                frames->format    = AV_PIX_FMT_CUDA;
+                frames->sw_format = sw_fmt;
+                frames->width     = avctx->coded_width  ? avctx->coded_width  : avctx->width;
+                frames->height    = avctx->coded_height ? avctx->coded_height : avctx->height;
+                if ((ret = av_hwframe_ctx_init(avctx->hw_frames_ctx)) < 0) {
+                    av_log(avctx, AV_LOG_WARNING, "no CUDA frames of format %s: pictures go to host memory\n",
+                           av_get_pix_fmt_name(sw_fmt));
+                    av_buffer_unref(&avctx->hw_frames_ctx);
+                }
+            }
+            if (avctx->hw_frames_ctx) {
+                frames = (AVHWFramesContext *)avctx->hw_frames_ctx->data;
+                if (frames->format != AV_PIX_FMT_CUDA || frames->sw_format != sw_fmt) {
+                    av_log(avctx, AV_LOG_ERROR, "hw_frames_ctx does not hold CUDA frames of format %s\n",
+                           av_get_pix_fmt_name(sw_fmt));
+                    return AVERROR(EINVAL);
+                }
+                s->cu_ctx = ((AVCUDADeviceContext *)frames->device_ctx->hwctx)->cuda_ctx;
+                s->cuda_out = 1;
+            }
+        }
+    }
+#endif
+    s->negotiated = 1;
+    avctx->pix_fmt = s->cuda_out ? AV_PIX_FMT_CUDA : sw_fmt;
+    return 0;
+}
+
 static av_cold int gpu_decode_init(AVCodecContext *avctx)
 {
     FFV1GpuContext *s = avctx->priv_data;
@@ -366,14 +421,17 @@ static int gpu_decode_frame(AVCodecContext *avctx, void *data, int *got_frame, A
         }
         name = ffgpu_ffv1_decoder_pix_fmt(s->dec);
     }
-    avctx->pix_fmt = av_get_pix_fmt(name);
+    if ((ret = gpu_output_format(avctx, av_get_pix_fmt(name))) < 0)
+        return ret;
     if ((ret = ff_get_buffer(avctx, frame, AV_GET_BUFFER_FLAG_REF)) < 0)
         return ret;
     for (i = 0; i < 4; i++) {
         out.data[i] = frame->data[i];
         out.linesize[i] = frame->linesize[i];
     }
+    CUDA_PUSH(s);
     ret = ffgpu_ffv1_decode_frame(s->dec, avpkt->data, avpkt->size, &out, got_frame);
+    CUDA_POP(s);
     if (ret < 0) {
         av_log(avctx, AV_LOG_ERROR, "%s\n", ffgpu_last_error());
         av_frame_unref(frame);
@@ -400,7 +458,9 @@ static int gpu_receive_frame(AVCodecContext *avctx, AVFrame *frame)
         return AVERROR_EOF;
     for (;;) {
         memset(&out, 0, sizeof(out));
+        CUDA_PUSH(s);
         ret = ffgpu_ffv1_decode_receive_frame(s->dec, &out);
+        CUDA_POP(s);
         if (ret == 0) {
             AVFrame *f = fifo_pop(s);
             av_assert0(f);
@@ -425,7 +485,10 @@ static int gpu_receive_frame(AVCodecContext *avctx, AVFrame *frame)
             ret = ff_decode_get_packet(avctx, s->pending);
             if (ret == AVERROR_EOF) {
                 s->draining = 1;
-                if ((ret = ffgpu_ffv1_decode_send_packet(s->dec, NULL, 0, 0, NULL)) < 0)
+                CUDA_PUSH(s);
+                ret = ffgpu_ffv1_decode_send_packet(s->dec, NULL, 0, 0, NULL);
+                CUDA_POP(s);
+                if (ret < 0)
                     return ret;
                 continue;
             }
@@ -440,7 +503,10 @@ static int gpu_receive_frame(AVCodecContext *avctx, AVFrame *frame)
             }
             name = ffgpu_ffv1_decoder_pix_fmt(s->dec);
         }
-        avctx->pix_fmt = av_get_pix_fmt(name);
+        if ((ret = gpu_output_format(avctx, av_get_pix_fmt(name))) < 0) {
+            av_packet_unref(s->pending);
+            return ret;
+        }
         {
             AVFrame *f = av_frame_alloc();
             ffgpu_picture_out dst = { { 0 } };
@@ -459,8 +525,10 @@ static int gpu_receive_frame(AVCodecContext *avctx, AVFrame *frame)
                 dst.data[i] = f->data[i];
                 dst.linesize[i] = f->linesize[i];
             }
+            CUDA_PUSH(s);
             ret = ffgpu_ffv1_decode_send_packet(s->dec, s->pending->data, s->pending->size,
                                                 s->pending->pts, &dst);
+            CUDA_POP(s);
             if (ret == AVERROR(EAGAIN)) {      /* every launch group is busy: receive blocks next */
                 av_frame_free(&f);
                 continue;
@@ -490,6 +558,7 @@ static void gpu_flush(AVCodecContext *avctx)
     /* avcodec_flush_buffers: drop what is in flight.  The library is drained to its EOF so
      * that it takes packets again afterwards (a flushed handle refuses them until then); the
      * pictures land in the frames queued for them, which are dropped. */
+    CUDA_PUSH(s);
     if (!s->eof) {
         if (!s->draining)
             ffgpu_ffv1_decode_send_packet(s->dec, NULL, 0, 0, NULL);
@@ -500,6 +569,7 @@ static void gpu_flush(AVCodecContext *avctx)
                 av_frame_free(&f);             /* a picture, or one that failed */
         } while (ret != AVERROR_EOF && ret != AVERROR(EAGAIN) && (ret >= 0 || s->fifo_count));
     }
+    CUDA_POP(s);
     while ((f = fifo_pop(s)))
         av_frame_free(&f);
     av_packet_unref(s->pending);
@@ -581,6 +651,22 @@ AVCodec ff_ffv1_gpu_encoder = {
     .priv_class     = &enc_class,
 };
 
+#if CONFIG_CUDA
+/* pictures that stay on the GPU: offered like libavcodec/cuviddec.c:1132-1143 */
+static const AVCodecHWConfigInternal *gpu_dec_hw_configs[] = {
+    &(const AVCodecHWConfigInternal) {
+        .public = {
+            .pix_fmt     = AV_PIX_FMT_CUDA,
+            .methods     = AV_CODEC_HW_CONFIG_METHOD_HW_DEVICE_CTX | AV_CODEC_HW_CONFIG_METHOD_HW_FRAMES_CTX |
+                           AV_CODEC_HW_CONFIG_METHOD_INTERNAL,
+            .device_type = AV_HWDEVICE_TYPE_CUDA
+        },
+        .hwaccel = NULL,
+    },
+    NULL
+};
+#endif
+
 AVCodec ff_ffv1_gpu_decoder = {
     .name           = "ffv1_gpu",
     .long_name      = NULL_IF_CONFIG_SMALL("FFmpeg video codec #1 (B200 CUDA slice path)"),
@@ -595,4 +681,7 @@ AVCodec ff_ffv1_gpu_decoder = {
     .capabilities   = AV_CODEC_CAP_DR1 | AV_CODEC_CAP_DELAY,
     .caps_internal  = FF_CODEC_CAP_INIT_CLEANUP,
     .priv_class     = &dec_class,
+#if CONFIG_CUDA
+    .hw_configs     = gpu_dec_hw_configs,
+#endif
 };

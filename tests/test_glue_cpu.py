@@ -221,3 +221,15 @@ def test_nothing_is_freed_early_or_left_behind(tmp_path, asan_env):
                         "-level", "4", "-f", "null", "-"], capture_output=True, env=env, timeout=120)
     assert r.returncode not in (0, 97), r.stderr.decode(errors="replace")[-2000:]
     assert b"AddressSanitizer" not in r.stderr and b"LeakSanitizer" not in r.stderr
+
+
+def test_the_cuda_frames_half_of_the_glue_compiles():
+    """`#if CONFIG_CUDA`: AV_PIX_FMT_CUDA frames into the encoder and out of the decoder
+    (hw_configs, get_format negotiation, AVHWFramesContext, the context bracket).  This tree has
+    no hwcontext_cuda to link against, so the code is type-checked against the reference's
+    headers with CONFIG_CUDA=1; its library side (device pointers in ffgpu_picture /
+    ffgpu_picture_out) is what test_gpu_parity and test_host_pipeline_cpu exercise"""
+    if not (os.path.isdir("/root/reference/libavcodec") and os.path.exists("/usr/local/cuda/include/cuda.h")):
+        pytest.skip("reference headers or cuda.h not available")
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "glue-cuda-check"], capture_output=True, text=True)
+    assert r.returncode == 0 and "warning" not in r.stderr, r.stderr[-3000:]
