@@ -254,21 +254,106 @@ def run_config(args, wl, src_desc):
             "partition": "pictures round-robin over ranks, no collective"}
 
 
+def run_cpu_instances(wl, frames, instances, threads, per_instance):
+    """`instances` independent encoder+decoder pairs of the reference codec, each with
+    `threads` slice threads, side by side (the calls release the GIL): frame-level on top of
+    slice-level parallelism, what N ffmpeg processes on one box give.  Every instance codes
+    `per_instance` pictures; the phases (all encode, then all decode) are timed as a whole."""
+    import threading
+    import cpucodec as cc
+    which, kind = cpu_codec_kind()
+    encs, decs = [], []
+    for _ in range(instances):
+        warm = cc.Encoder(which, wl["w"], wl["h"], wl["fmt"], threads=threads, **wl["opts"])
+        warm.encode(frames[0])                  # first-touch of the packet buffer, untimed
+        warm.close()
+        e = cc.Encoder(which, wl["w"], wl["h"], wl["fmt"], threads=threads, **wl["opts"])
+        e.encode(frames[0])
+        encs.append(e)
+        decs.append(cc.Decoder(which, wl["w"], wl["h"], e.extradata, threads=threads))
+    pkts = [[] for _ in range(instances)]
+    errors = []
+
+    def phase(fn):
+        ts = [threading.Thread(target=fn, args=(i,)) for i in range(instances)]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return time.perf_counter() - t0
+
+    def enc_fn(i):
+        try:
+            for k in range(per_instance):
+                pkts[i].append(encs[i].encode(frames[(i + k) % len(frames)]))
+        except Exception as e:                  # noqa: BLE001
+            errors.append(e)
+
+    def dec_fn(i):
+        try:
+            for pkt in pkts[i]:
+                decs[i].decode(pkt, copy=False)
+        except Exception as e:                  # noqa: BLE001
+            errors.append(e)
+
+    for i in range(instances):
+        decs[i].decode(encs[i].encode(frames[0]), copy=False)        # decoder warm-up, untimed
+    t_enc = phase(enc_fn)
+    t_dec = phase(dec_fn)
+    for e in encs:
+        e.close()
+    if errors:
+        raise errors[0]
+    n = instances * per_instance
+    return dict(kind=kind, frames=n, t_enc=t_enc, t_dec=t_dec,
+                enc_fps=n / t_enc, dec_fps=n / t_dec, fps=n / (t_enc + t_dec))
+
+
+def best_cpu_split(wl, frames, dec_only):
+    """untimed calibration: which split of the box's threads into codec instances x slice
+    threads codes this workload fastest -> ((instances, threads), {split: pictures/s})"""
+    cores = os.cpu_count() or 1
+    splits, calib = [(1, cores)], {}
+    if picture_bytes(wl) <= (64 << 20):         # 8K pictures: one instance (memory, time)
+        splits += [(n, max(1, cores // n)) for n in (2, 4) if cores >= 2 * n]
+    best = splits[0]
+    if len(splits) > 1:
+        for sp in splits:
+            try:
+                r = run_cpu_instances(wl, frames, sp[0], sp[1], max(2, 4 // sp[0]))
+                calib[sp] = r["dec_fps"] if dec_only else r["fps"]
+            except Exception as e:              # noqa: BLE001
+                print("cpu baseline: %d instances failed in calibration (%s)" % (sp[0], e), file=sys.stderr)
+        if calib:
+            best = max(calib, key=calib.get)
+    return best, calib
+
+
 def reference_arm(args, wl, rank, world, real_stdout):
-    """--impl reference: rank 0 alone times the reference CPU implementation"""
+    """--impl reference: rank 0 alone times the reference CPU implementation, on every host
+    thread.  The reference's own parallelism is slice threads (pthread_slice.c); independent
+    codec instances side by side add frame-level parallelism on top.  An untimed calibration
+    picks the split of the box's threads (1, 2 or 4 instances) that codes the workload
+    fastest, and the timed steps run that split."""
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    cores = os.cpu_count() or 1
     frames, src_desc = make_frames(wl, distinct_pictures(wl, args.batch or wl["batch"]), 0, args.source)
     which, kind = cpu_codec_kind()
+    dec_only = bool(wl.get("decode_only"))
     sample = 8
+
+    best, calib = best_cpu_split(wl, frames, dec_only)
+    inst, threads = best
+    per = max(1, sample // inst)
+    sample = per * inst
     res = []
     for step in range(args.warmup + args.steps):
-        r = run_cpu(wl, frames, threads, 1e9, sample)
+        r = run_cpu_instances(wl, frames, inst, threads, per)
         if step >= args.warmup:
             res.append(r)
     tot_frames = sum(r["frames"] for r in res)
-    dec_only = bool(wl.get("decode_only"))
     tot_t = sum((0.0 if dec_only else r["t_enc"]) + r["t_dec"] for r in res)
     fps = tot_frames / tot_t
     out = {
@@ -279,10 +364,13 @@ def reference_arm(args, wl, rank, world, real_stdout):
         "config": run_config(args, wl, src_desc), "frames_per_step": sample,
         "encode_fps": tot_frames / sum(r["t_enc"] for r in res),
         "decode_fps": tot_frames / sum(r["t_dec"] for r in res),
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
-                         "sample": "%d pictures %s per step, %d steps, %d slice threads "
-                                   "(the reference's own ffv1enc.c/ffv1dec.c, oracle/_ref)" % (
-                             sample, "decoded" if dec_only else "encoded+decoded", len(res), threads)},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
+                         "instances": inst, "slice_threads_per_instance": threads,
+                         "calibration_fps": {"%dx%d" % k: round(v, 2) for k, v in calib.items()},
+                         "sample": "%d pictures %s per step, %d steps; %d codec instance(s) x %d slice threads "
+                                   "(the reference's own ffv1enc.c/ffv1dec.c, oracle/_ref), the fastest split of "
+                                   "the box's %d threads in an untimed calibration" % (
+                             sample, "decoded" if dec_only else "encoded+decoded", len(res), inst, threads, cores)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), file=real_stdout, flush=True)
@@ -821,11 +909,24 @@ def main():
         if getattr(bind_to_gpu_numa, "all_cpus", None):      # the CPU baseline gets every host core
             os.sched_setaffinity(0, bind_to_gpu_numa.all_cpus)
         threads = os.cpu_count() or 1
-        r = run_cpu(wl, srcs, threads, 16.0, 400)
+        inst, calib = 1, {}
+        try:
+            # the same choice as `--impl reference`: the fastest split of the host threads into
+            # codec instances x slice threads, then about 12 s of work on it
+            (inst, per_thr), calib = best_cpu_split(wl, srcs, dec_only)
+            rate = calib.get((inst, per_thr), 0.0)
+            per = int(min(400, max(4, rate * 12.0)) // inst) or 1
+            r = run_cpu_instances(wl, srcs, inst, per_thr, per)
+        except Exception as e:                   # noqa: BLE001
+            print("cpu baseline: instance split failed (%s): one instance, slice threads only" % e, file=sys.stderr)
+            inst, per_thr = 1, threads
+            r = run_cpu(wl, srcs, threads, 16.0, 400)
         cpu = {"value": r["dec_fps"] if dec_only else r["fps"], "unit": "frames/s", "cores": threads,
                "kind": r["kind"], "encode_fps": r["enc_fps"], "decode_fps": r["dec_fps"],
-               "sample": "%d pictures encoded+decoded once (%.1f s), %d slice threads%s" % (
-                   r["frames"], r["t_enc"] + r["t_dec"], threads,
+               "instances": inst, "slice_threads_per_instance": per_thr,
+               "calibration_fps": {"%dx%d" % k: round(v, 2) for k, v in calib.items()},
+               "sample": "%d pictures encoded+decoded once (%.1f s), %d codec instance(s) x %d slice threads%s" % (
+                   r["frames"], r["t_enc"] + r["t_dec"], inst, per_thr,
                    "; value = decode only" if dec_only else "")}
 
     out = {
