@@ -288,3 +288,14 @@ def test_device_resident_batches_and_device_pointer_planes(cpu_env):
     r = subprocess.run([sys.executable, "-c", DEVICE_BATCHES % dict(root=ROOT, tests=HERE)],
                        capture_output=True, text=True, env=cpu_env, timeout=600)
     assert r.returncode == 0 and "device batches ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_random_call_sequences_keep_the_stream_in_order(cpu_env):
+    """tests/emul/api_sequences.py: pictures / packets sent, results received and streams
+    flushed (also mid-stream) in random order, one device and routing handles, every group
+    size and depth, carried-state streams routed by whole GOPs: complete, ordered,
+    oracle-identical output, never EAGAIN on both sides, input accepted again after an EOF"""
+    for seed in ("1", "7"):
+        r = subprocess.run([sys.executable, os.path.join(HERE, "emul", "api_sequences.py"), seed, "40"],
+                           capture_output=True, text=True, env=cpu_env, timeout=900)
+        assert r.returncode == 0 and "api sequences ok" in r.stdout, (seed, r.stdout[-1000:], r.stderr[-3000:])
