@@ -198,6 +198,9 @@ FFGPU_HD int ffrac_get(FFRacDec *c, const FFRacTables *t, uint8_t *state)
 /* get_symbol_inline.  On the e > 31 error the reference returns AVERROR_INVALIDDATA *as the
  * symbol value* (ffv1dec.c:54-55); callers see the same number here. */
 #define FFRAC_SYMBOL_ERROR (-1094995529)
+/* -v modulo 2^32: a damaged stream can produce 0x80000000 (32 mantissa bits), whose signed
+ * negation is undefined; the reference wraps (ffv1dec.c:61-63, :208-209) */
+#define FF_NEG32(v) ((int)(0u - (uint32_t)(v)))
 FFGPU_HD int ffrac_get_symbol(FFRacDec *c, const FFRacTables *t, uint8_t *st, int is_signed)
 {
     int e = 0, i;
@@ -212,7 +215,7 @@ FFGPU_HD int ffrac_get_symbol(FFRacDec *c, const FFRacTables *t, uint8_t *st, in
     for (i = e - 1; i >= 0; i--)
         a += a + (uint32_t)ffrac_get(c, t, st + 22 + (i < 9 ? i : 9));
     if (is_signed && ffrac_get(c, t, st + 11 + (e < 10 ? e : 10)))
-        return -(int)a;
+        return (int)(0u - a);
     return (int)a;
 }
 

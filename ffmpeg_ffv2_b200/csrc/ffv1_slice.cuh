@@ -1686,12 +1686,12 @@ FFGPU_HD void ff_decode_slice_range(const FFDevParams &P, const FFDecSlice &d, c
             mi--;
             slot = mi < 0 ? 11 + ff_min(e, 10) : 22 + ff_min(mi, 9);
         } else {
-            diff = bit ? -(int)a : (int)a;
+            diff = bit ? (int)(0u - a) : (int)a;
             done = 1;
         }
         if (done) {
             int v;
-            diff = sign ? -diff : diff;
+            diff = sign ? FF_NEG32(diff) : diff;
             v = (int)(((uint32_t)ff_median3(L, L + T - LT, T) + (uint32_t)diff) & mask);
             v = use32 ? v : (int)(int16_t)v;
             if (!usepic)
@@ -2105,14 +2105,14 @@ FFGPU_HD void ff_decode_slice_range_planar(const FFDevParams &P, const FFDecSlic
             mi--;
             slot = mi < 0 ? 11 + ff_min(e, 10) : 22 + ff_min(mi, 9);
         } else {
-            diff = bit ? -(int)a : (int)a;
+            diff = bit ? (int)(0u - a) : (int)a;
             done = 1;
         }
         if (!done && slot != slot_was)               /* state of the next decision, fetched ahead */
             sreg = FF_ST_LD(slot);
         if (done) {
             int v;
-            diff = sign ? -diff : diff;
+            diff = sign ? FF_NEG32(diff) : diff;
             v = (int)(((uint32_t)ff_median3(L, L + T - LT, T) + (uint32_t)diff) & mask);
             v = (int)(int16_t)v;
             *(pix_t *)(ol + (size_t)x * step) = (pix_t)v;     /* decode_plane's store, ffv1dec.c:142-161 */
@@ -2372,9 +2372,9 @@ FFGPU_HD void ff_decode_slice_range_planar_lone(const FFDevParams &P, const FFDe
                             FF_LONE_GET(FF_ST_LD(sl), bit, ns);
                             FF_ST_ST(sl, ns);
                         }
-                        diff = bit ? -(int)a : (int)a;
+                        diff = bit ? (int)(0u - a) : (int)a;
                     }
-                    diff = sign ? -diff : diff;
+                    diff = sign ? FF_NEG32(diff) : diff;
                     v = (int)(((uint32_t)pred + (uint32_t)diff) & mask);
                     v = (int)(int16_t)v;
                     qn = FF_QTL((v - T) & 0xFF);      /* the assumption did not hold */
@@ -2594,9 +2594,9 @@ FFGPU_HD void ff_decode_slice_range_rgb_lone(const FFDevParams &P, const FFDecSl
                             FF_LONE_GET(FF_ST_LD(sl), bit, ns);
                             FF_ST_ST(sl, ns);
                         }
-                        diff = bit ? -(int)a : (int)a;
+                        diff = bit ? (int)(0u - a) : (int)a;
                     }
-                    diff = sign ? -diff : diff;
+                    diff = sign ? FF_NEG32(diff) : diff;
                     v = (int)(((uint32_t)pred + (uint32_t)diff) & mask);
                     v = use32 ? v : (int)(int16_t)v;
                     qn = FF_QTL((v - T) & 0xFF);      /* the assumption did not hold */
