@@ -927,8 +927,9 @@ FFGPU_HD void ff_vlc_store(uint2 *p, const FFVlc &s)
 FFGPU_HD void ff_vlc_adapt(FFVlc *s, int v)
 {
     int drift = s->drift, count = s->count;
-    s->error_sum = (s->error_sum + (v < 0 ? -v : v)) & 0xFFFF;
-    drift += v;
+    /* modulo 2^32 like the reference's wrapping ints: a damaged stream delivers any v */
+    s->error_sum = (int)(((uint32_t)s->error_sum + (v < 0 ? 0u - (uint32_t)v : (uint32_t)v)) & 0xFFFF);
+    drift = (int)((uint32_t)drift + (uint32_t)v);
     if (count == 128) {
         count >>= 1;
         drift >>= 1;
@@ -1189,7 +1190,7 @@ FFGPU_HD int ff_vlc_get(FFBitR *r, uint2 *sp, int bits)
     }
     v = (int)(u >> 1) ^ -(int)(u & 1);
     v ^= (2 * s.drift + s.count) >> 31;
-    ret = ff_fold(v + s.bias, bits);
+    ret = ff_fold((int)((uint32_t)v + (uint32_t)s.bias), bits);
     ff_vlc_adapt(&s, v);
     ff_vlc_store(sp, s);
     return ret;

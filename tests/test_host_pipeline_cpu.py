@@ -140,6 +140,61 @@ def test_the_host_pipeline_under_the_sanitizers(cpu_env):
     assert " passed" in r.stdout and "failed" not in r.stdout and "Sanitizer" not in tail, tail
 
 
+UNRESET_STATES = textwrap.dedent("""
+    import sys
+    sys.path.insert(0, %(root)r); sys.path.insert(0, %(tests)r)
+    import ffmpeg_ffv2_b200 as F, cpucodec as cc, synth
+    w, h = 96, 64
+    hits = 0
+    for fmt, kw in (("ya8", dict(slices=6, gop_size=1)), ("yuv420p", dict(slices=4, gop_size=1)),
+                    ("yuv420p", dict(slices=4, gop_size=1, level=4, strict=-2))):
+        ref = cc.Encoder("oracle" if kw.get("level") != 4 else "ref", w, h, fmt, **kw)
+        pk = [ref.encode(synth.noise(fmt, w, h, i)) for i in range(2)]
+        for b in range(256):
+            # the first byte of a packet carries the key-frame bit of the range coder
+            # both pictures in one launch group: the second one's state slot has never been used
+            dec = F.FFV1Decoder(w, h, ref.extradata, max_batch=3, pipeline_depth=2)
+            try:
+                for f, p in enumerate((pk[0], bytes([b]) + pk[1][1:])):
+                    while not dec.send_packet(p, pts=f, dst=dec.alloc_picture()):
+                        dec.receive_frame()
+                dec.send_packet(None)
+                while True:
+                    r = dec.receive_frame()
+                    if r == F.EOF:
+                        break
+                    hits += r is not None and not r[0].key_frame
+            except F.FFGpuError:
+                pass
+            dec.close()
+    assert hits > 0, "no packet was taken for a non-key frame"
+    print("unreset states ok", hits)
+""")
+
+
+def test_states_that_no_key_frame_has_reset(cpu_env):
+    """a packet whose key-frame bit is cleared in an intra-only Golomb-Rice stream decodes with
+    states no key frame initialised.  The arenas start zeroed like the reference's av_mallocz'ed
+    ones: on the stand-in runtime's 0xA5-filled allocations get_vlc_symbol's k search
+    (ffv1dec.c:77-81) met count == 0 and did not end (found by tests/emul/api_fuzz.py)"""
+    emul = os.path.join(HERE, "emul")
+    r = subprocess.run(["make", "-C", emul, "cpu-asan/libffgpu.so"], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("sanitizer build not available: " + r.stderr[-300:])
+    libs = [subprocess.run(["gcc", "-print-file-name=" + n], capture_output=True, text=True).stdout.strip()
+            for n in ("libasan.so", "libubsan.so")]
+    if not all(os.path.isabs(p) and os.path.exists(p) for p in libs):
+        pytest.skip("sanitizer runtimes not found")
+    env = dict(cpu_env)
+    d = os.path.join(emul, "cpu-asan")
+    env.update(FFGPU_LIB=os.path.join(d, "libffgpu.so"), LD_PRELOAD=" ".join(libs),
+               ASAN_OPTIONS="detect_leaks=0:abort_on_error=0",
+               LD_LIBRARY_PATH=d + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([sys.executable, "-c", UNRESET_STATES % dict(root=ROOT, tests=HERE)],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "unreset states ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
 def test_damaged_streams_through_the_public_api_under_the_sanitizers(cpu_env):
     """tests/emul/api_fuzz.py: mutated packets and extradata into decode_frame, send_packet /
     receive_frame and a routing handle over two stand-in devices, sanitizer build"""
