@@ -1745,10 +1745,11 @@ static int dec_device_create(ffgpu_decoder *d)
         if ((r = upload_and_free((void **)&d->d_initial, tmp, per * FF_MAX_QUANT_TABLES)) < 0)
             return r;
     }
-    /* State arenas start zeroed, like the reference's av_mallocz'ed ones (ffv1.c:70-90): a
-     * damaged stream can reach a state no key frame has reset (a cleared key-frame bit in an
-     * intra-only stream, a slice that was skipped in the key frame), and get_vlc_symbol's
-     * k search (ffv1dec.c:77-81) does not end on a garbage state with count 0 */
+    /* The carried states start zeroed, like the reference's av_mallocz'ed ones (ffv1.c:70-90):
+     * a damaged stream can reach a state no key frame has reset (a slice that was skipped in
+     * the key frame), and get_vlc_symbol's k search (ffv1dec.c:77-81) does not end on a
+     * garbage state with count 0.  Intra-only streams reset the states of every picture
+     * whatever its key-frame bit says (ff_dec_parse_packet). */
     if (!d->intra) {
         CK(cudaMalloc(&d->d_state_shared, state_frame));
         CK(cudaMemset(d->d_state_shared, 0, state_frame));
@@ -1792,10 +1793,8 @@ static int dec_device_create(ffgpu_decoder *d)
         CK(cudaMalloc(&j->d_work, B * d->max_slices * sizeof(FFDecSlice)));
         CK(cudaHostAlloc(&j->h_nslices, B * sizeof(int), cudaHostAllocDefault));
         CK(cudaMalloc(&j->d_nslices, B * sizeof(int)));
-        if (d->intra) {
-            CK(cudaMalloc(&j->d_state, B * state_frame));
-            CK(cudaMemset(j->d_state, 0, B * state_frame));
-        }
+        if (d->intra)
+            CK(cudaMalloc(&j->d_state, B * state_frame));     /* reset for every picture, see ff_dec_parse_packet */
         CK(cudaMalloc(&j->d_sched, sizeof(FFSched)));
         CK(cudaMemset(j->d_sched, 0, sizeof(FFSched)));
         if (d->lazy_states)

@@ -1241,7 +1241,11 @@ int ff_dec_parse_packet(FFStream *s, FFDecHostState *hs, const uint8_t *pkt, siz
             d->pkt_off = pkt_off;
             d->size = (uint32_t)((end - pkt) + v);
         }
-        d->key_frame = info->key_frame;
+        /* the slice's states are reset: key frames, and every picture of an intra-only stream,
+         * whose decoder keeps no states between pictures -- a packet of such a stream with a
+         * cleared key-frame bit (damage; the encoder never writes one) must not decode with
+         * states nothing has initialised */
+        d->key_frame = info->key_frame || (s->version > 2 && s->intra);
     }
 
     /* per slice: continue (slice 0) or start (others) the range decoder, parse the slice
